@@ -1,0 +1,281 @@
+"""ORACLE (test infrastructure, NOT product code): ctypes front-end of oracle/liborc.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
+It wraps the C++ restatement of the reference routines (see oracle/orc_*.hpp for file:line cites).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+LMAX_EXTRAP_HIGHL = 8000
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liborc.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp", ".inc"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.orc_bessel_create.restype = C.c_void_p
+        L.orc_bessel_destroy.argtypes = [C.c_void_p]
+        L.orc_bessel_numxx.argtypes = [C.c_void_p]
+        L.orc_bessel_get.argtypes = [C.c_void_p, c_dp, c_dp, c_dp]
+        L.orc_project.restype = C.c_longlong
+        L.orc_quadform.restype = C.c_double
+        L.orc_pliklite.restype = C.c_double
+        L.orc_cmblikes_chisq.restype = C.c_double
+    return _LIB
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(c_dp if a.dtype == np.float64 else c_ip)
+
+
+def ranges_build(ops, max_points=200000):
+    """ops: list of (kind, start, end, delta_or_nstep, islog); kind 0 = Add_delta, 1 = Add."""
+    o = _d(ops).reshape(-1, 5)
+    pts = np.zeros(max_points)
+    dpts = np.zeros(max_points)
+    reg = np.zeros((100, 6))
+    n = C.c_int(0)
+    cnt = lib().orc_ranges_build(len(o), _p(o), max_points, C.byref(n), _p(pts), _p(dpts), _p(reg))
+    if cnt < 0:
+        raise RuntimeError("orc_ranges_build failed")
+    return pts[: n.value].copy(), dpts[: n.value].copy(), reg[:cnt].copy()
+
+
+def ranges_indexof(ops, x):
+    o = _d(ops).reshape(-1, 5)
+    x = _d(x)
+    idx = np.zeros(len(x), dtype=np.int32)
+    if lib().orc_ranges_indexof(len(o), _p(o), len(x), _p(x), _p(idx)) != 0:
+        raise RuntimeError("orc_ranges_indexof failed")
+    return idx
+
+
+def initlval(max_l, lSampleBoost=1.0, AccurateReionization=True):
+    out = np.zeros(4100, dtype=np.int32)
+    n = lib().orc_initlval(int(max_l), C.c_double(lSampleBoost), int(AccurateReionization), _p(out), len(out))
+    if n < 0:
+        raise RuntimeError("orc_initlval failed")
+    return out[:n].copy()
+
+
+def spline(x, y, d11=1e40, d1n=1e40):
+    x = _d(x)
+    y = _d(y)
+    d2 = np.zeros_like(x)
+    lib().orc_spline(_p(x), _p(y), len(x), C.c_double(d11), C.c_double(d1n), _p(d2))
+    return d2
+
+
+def bjl(L, x):
+    L = _i(np.broadcast_to(L, np.shape(x)))
+    x = _d(x)
+    out = np.zeros_like(x)
+    lib().orc_bjl(x.size, _p(L), _p(x), _p(out))
+    return out
+
+
+class Bessel:
+    def __init__(self, ls, max_eta_k):
+        self.ls = _i(ls)
+        self.h = lib().orc_bessel_create(len(self.ls), _p(self.ls), C.c_double(max_eta_k))
+        if not self.h:
+            raise RuntimeError("orc_bessel_create failed")
+        self.num_xx = lib().orc_bessel_numxx(self.h)
+
+    def arrays(self):
+        x = np.zeros(self.num_xx)
+        ajl = np.zeros((len(self.ls), self.num_xx))
+        ajlpr = np.zeros((len(self.ls), self.num_xx))
+        lib().orc_bessel_get(self.h, _p(x), _p(ajl), _p(ajlpr))
+        return x, ajl, ajlpr
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_bessel_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def time_steps(taurst, taurend, tau0, maximum_qeta, want_tensors, reion_start, reion_complete, max_n=4000):
+    tau = np.zeros(max_n)
+    dtau = np.zeros(max_n)
+    n = lib().orc_time_steps(C.c_double(taurst), C.c_double(taurend), C.c_double(tau0), C.c_double(maximum_qeta),
+                             int(want_tensors), C.c_double(reion_start), C.c_double(reion_complete), max_n,
+                             _p(tau), _p(dtau))
+    if n < 0:
+        raise RuntimeError("orc_time_steps failed")
+    return tau[:n].copy(), dtau[:n].copy()
+
+
+def source_k(tau0, taurst, maximum_qeta, want_tensors, maximum_l, max_n=4000):
+    k = np.zeros(max_n)
+    n = lib().orc_source_k(C.c_double(tau0), C.c_double(taurst), C.c_double(maximum_qeta), int(want_tensors),
+                           int(maximum_l), max_n, _p(k))
+    if n < 0:
+        raise RuntimeError("orc_source_k failed")
+    return k[:n].copy()
+
+
+def q_grid(tau0, maximum_qeta, maximum_l, max_n=20000):
+    q = np.zeros(max_n)
+    dq = np.zeros(max_n)
+    n = lib().orc_q_grid(C.c_double(tau0), C.c_double(maximum_qeta), int(maximum_l), max_n, _p(q), _p(dq))
+    if n < 0:
+        raise RuntimeError("orc_q_grid failed")
+    return q[:n].copy(), dq[:n].copy()
+
+
+def project(bessel, tau0, taurst, taurend, reion_start, reion_complete, maximum_qeta, maximum_l, want_tensors,
+            k_src, src, max_q=20000):
+    """src: [n_tau][n_src][n_k].  Returns q, dq, Delta[n_q][nl][n_src], triples."""
+    k_src = _d(k_src)
+    src = _d(src)
+    n_src = src.shape[1]
+    nl = len(bessel.ls)
+    q = np.zeros(max_q)
+    dq = np.zeros(max_q)
+    Delta = np.zeros((max_q, nl, n_src))
+    trip = C.c_longlong(0)
+    n = lib().orc_project(C.c_void_p(bessel.h), nl, _p(bessel.ls), C.c_double(tau0), C.c_double(taurst),
+                          C.c_double(taurend), C.c_double(reion_start), C.c_double(reion_complete),
+                          C.c_double(maximum_qeta), int(maximum_l), int(want_tensors), len(k_src), _p(k_src), n_src,
+                          _p(src), max_q, _p(q), _p(dq), _p(Delta), C.byref(trip))
+    if n < 0:
+        raise RuntimeError("orc_project failed")
+    return q[:n].copy(), dq[:n].copy(), Delta[:n].copy(), trip.value
+
+
+def initpower_vec(As=2.1e-9, ns=0.96, nrun=0.0, nrunrun=0.0, r=0.0, nt=0.0, ntrun=0.0, pivot_k=0.05,
+                  tensor_pivot_k=0.05, inflation_consistency=True):
+    return _d([As, ns, nrun, nrunrun, r, nt, ntrun, pivot_k, tensor_pivot_k, float(inflation_consistency)])
+
+
+def scalar_power(ip, k):
+    k = _d(k)
+    out = np.zeros_like(k)
+    lib().orc_scalar_power(_p(_d(ip)), k.size, _p(k), _p(out))
+    return out
+
+
+def tensor_power(ip, k):
+    k = _d(k)
+    out = np.zeros_like(k)
+    lib().orc_tensor_power(_p(_d(ip)), k.size, _p(k), _p(out))
+    return out
+
+
+def calc_cls(q, dq, ls, Delta, ip, ALens=1.0, tensors=False):
+    q = _d(q)
+    dq = _d(dq)
+    ls = _i(ls)
+    Delta = _d(Delta)
+    nX = 4 if tensors else 6
+    iCl = np.zeros((nX, len(ls)))
+    if lib().orc_calc_cls(int(tensors), len(q), _p(q), _p(dq), len(ls), _p(ls), Delta.shape[2], _p(Delta),
+                          _p(_d(ip)), C.c_double(ALens), _p(iCl)) != 0:
+        raise RuntimeError("orc_calc_cls failed")
+    return iCl
+
+
+def load_highl_template(path):
+    """camb/modules.f90:1162-1185: columns L, TT, EE, BB, TE, PP,... -> [4][8001] = TT, EE, TE, PP."""
+    a = np.loadtxt(path)
+    t = np.zeros((4, LMAX_EXTRAP_HIGHL + 1))
+    L = a[:, 0].astype(int)
+    m = L <= LMAX_EXTRAP_HIGHL
+    t[0, L[m]] = a[m, 1]
+    t[1, L[m]] = a[m, 2]
+    t[2, L[m]] = a[m, 4]
+    t[3, L[m]] = a[m, 5]
+    return t
+
+
+def interp_cl(ls, iCl, max_ind=None, template_index=0, tmpl=None):
+    ls = _i(ls)
+    iCl = _d(iCl)
+    if max_ind is None:
+        max_ind = len(ls)
+    out = np.zeros(int(ls[max_ind - 1]) + 1)
+    t = _d(tmpl) if tmpl is not None else None
+    if lib().orc_interp_cl(len(ls), _p(ls), _p(iCl), int(max_ind), int(template_index), _p(t), _p(out)) != 0:
+        raise RuntimeError("orc_interp_cl failed")
+    return out
+
+
+def lens_cls(ls, Max_l, cl_scalar, tmpl):
+    """cl_scalar: [4][Max_l+1] TT,EE,TE,PP(l^4 C_phi) dimensionless; returns ([4][lmax_lensed+1] TT,EE,BB,TE)."""
+    ls = _i(ls)
+    cl_scalar = _d(cl_scalar)
+    assert cl_scalar.shape == (4, Max_l + 1)
+    out = np.zeros((4, Max_l + 1))
+    lml = lib().orc_lens_cls(len(ls), _p(ls), int(Max_l), _p(cl_scalar), _p(_d(tmpl)), _p(out), Max_l + 1)
+    if lml < 0:
+        raise RuntimeError("orc_lens_cls failed")
+    return out[:, : lml + 1].copy()
+
+
+def set_powers(cl_lensed, cl_phi, lmax_computed_cl, cl_lmax, highl, Aphiphi=1.0, cl_tensor=None, lmax_tensor=0,
+               highL_norm=0.0, lmax_out=None):
+    cl_lensed = _d(cl_lensed)
+    cl_phi = _d(cl_phi)
+    highl = _d(highl)
+    cl_lmax = _i(cl_lmax)
+    if lmax_out is None:
+        lmax_out = int(cl_lmax.max())
+    out = np.zeros((5, lmax_out + 1))
+    hn = C.c_double(highL_norm)
+    rms = C.c_double(0)
+    ct = _d(cl_tensor) if cl_tensor is not None else None
+    if lib().orc_set_powers(_p(cl_lensed), cl_lensed.shape[1], _p(cl_phi), _p(ct), ct.shape[1] if ct is not None else 0,
+                            int(lmax_tensor), int(lmax_computed_cl), _p(cl_lmax), _p(highl), highl.shape[1],
+                            C.c_double(Aphiphi), C.byref(hn), _p(out), lmax_out, C.byref(rms)) != 0:
+        raise RuntimeError("orc_set_powers failed")
+    return out, hn.value, rms.value
+
+
+def quadform(M, v):
+    M = _d(M)
+    v = _d(v)
+    return lib().orc_quadform(_p(M), _p(v), len(v))
+
+
+def pliklite(cls, nb, blmin, blmax, weights, invcov, X_data, cal):
+    cls = _d(cls)
+    return lib().orc_pliklite(_p(cls), cls.shape[1], _p(_i(nb)), _p(_i(blmin)), _p(_i(blmax)), _p(_d(weights)),
+                              _p(_d(invcov)), _p(_d(X_data)), C.c_double(cal))
+
+
+def cmblikes_chisq(nmaps, nbins, cl_use_index, like_approx, NoiseM, ChatM, sqrt_fid, inv_cov, binnedC):
+    cui = _i(cl_use_index)
+    return lib().orc_cmblikes_chisq(int(nmaps), int(nbins), len(cui), _p(cui), int(like_approx),
+                                    _p(_d(NoiseM)) if NoiseM is not None else None, _p(_d(ChatM)),
+                                    _p(_d(sqrt_fid)) if sqrt_fid is not None else None, _p(_d(inv_cov)),
+                                    _p(_d(binnedC)))
