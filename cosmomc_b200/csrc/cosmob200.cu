@@ -1,0 +1,950 @@
+// cosmob200 — handle, orchestration and the extern "C" boundary declared in include/cosmob200.h.
+// Everything numerical runs in the hand-written sm_100a kernels of project.cuh / lens.cuh / like.cuh /
+// dgemm.cuh / bessel.cuh; there is no CPU fallback: without a CUDA device cb200_create fails.
+#include "../../include/cosmob200.h"
+#include "common.cuh"
+#include "grids.hpp"
+#include "bessel.cuh"
+#include "dgemm.cuh"
+#include "project.cuh"
+#include "lens.cuh"
+#include "like.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+
+using namespace cb200;
+
+namespace {
+
+constexpr int kTmplL = 8001;
+
+struct KindSet {  // per perturbation type (0 scalar, 1 tensor): multipole set + Bessel table
+  bool active = false;
+  int max_l = 0;
+  double max_eta_k = 0;
+  std::vector<int> ls;
+  SampleGrid bgrid;
+  LinSegs bseg{};
+  int num_xx = 0;
+  DevBuf<int> d_ls;
+  DevBuf<double> d_bx;
+  DevBuf<double2> d_bes;
+  DevBuf<int> d_llo;  // [max_l+1]
+};
+
+struct PointStore {  // resident per-point inputs
+  int cap = 0, NT = 0, NK = 0, NQ = 0;
+  DevBuf<double> thermo, tau, dtau, ksrc, q, dq, src;
+  DevBuf<int> n_tau, n_k, n_q;
+  DevBuf<LinSegs> tseg;
+  std::vector<int> h_nq, h_ntau;  // host mirrors for launch shapes
+  PointView view() const {
+    PointView v;
+    v.NT = NT; v.NK = NK; v.NQ = NQ; v.NSRC = 3;
+    v.thermo = thermo.p; v.n_tau = n_tau.p; v.tau = tau.p; v.dtau = dtau.p; v.tseg = tseg.p;
+    v.n_k = n_k.p; v.ksrc = ksrc.p; v.n_q = n_q.p; v.q = q.p; v.dq = dq.p; v.src = src.p;
+    return v;
+  }
+};
+
+struct LikeEntry {
+  int type = 0;  // 1 plik-lite, 2 cmblikes
+  int cal_index = -1;
+  // plik-lite
+  int nused = 0, lmax_w = 0;
+  DevBuf<int> bin_spec, bin_lo, bin_hi;
+  DevBuf<double> weights, x_data, invcov;
+  // cmblikes
+  int nmaps = 0, ncl = 0, nbins = 0, ncl_used = 0, like_approx = 2;
+  double log_cal_prior = -1;
+  DevBuf<double> Wt_cmb, Wt_pp, offset, noise, chat, sqrt_fid;
+  DevBuf<int> cl_use;
+  bool has_noise = false, has_sqrt_fid = false;
+};
+
+enum Phase { PH_SPLINE = 0, PH_PROJECT, PH_CONTRACT, PH_INTERP, PH_LENS, PH_LIKE, PH_COUNT };
+
+}  // namespace
+
+struct cb200_handle {
+  cb200_config cfg{};
+  cb200_info info{};
+  std::string err;
+  cudaStream_t stream = nullptr;
+  KindSet kind[2];
+  PointStore store[2];
+  bool have_templates = false;
+  DevBuf<double> d_tmpl, d_highl;
+  int n_highl = 0;
+  // lensing tables
+  LensGeom lg{};
+  DevBuf<int> d_jidx, d_lj;
+  DevBuf<double> d_A1, d_M, d_tab, d_apod;
+  std::vector<int> lj;
+  // chunk work buffers
+  int chunk = 0, LS = 0, LL = 0;
+  DevBuf<double> w_coef, w_ddsrc, w_part, w_icl, w_cl, w_cin, w_sc, w_corr, w_lcon, w_initpower, w_alens, w_aphi;
+  DevBuf<double> w_delta;
+  bool keep_transfers = false;
+  int last_chunk_p0 = 0, last_chunk_np = 0;
+  DevBuf<unsigned long long> d_triples;
+  bool count_triples = false;
+  // resident outputs
+  DevBuf<double> r_cl_lensed, r_cls_out, r_derived, r_icl, r_cl;
+  DevBuf<int> r_status;
+  double saved_highl_norm = 0;
+  // likelihoods
+  std::vector<std::unique_ptr<LikeEntry>> likes;
+  DevBuf<double> w_resid, w_T, w_bc, w_bp, w_bigx, w_quad, w_ll, w_total, w_nuis, w_cls_in, w_binned;
+  // timing
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[PH_COUNT];
+  std::vector<cudaEvent_t> ev_pool;
+  long long n_launches = 0;
+
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    CB_CUDA(cudaEventCreate(&e));
+    return e;
+  }
+  struct Scope {
+    cb200_handle* h; int ph; cudaEvent_t a, b;
+    Scope(cb200_handle* h_, int ph_) : h(h_), ph(ph_) {
+      a = h->get_event(); b = h->get_event();
+      cudaEventRecord(a, h->stream);
+    }
+    ~Scope() { cudaEventRecord(b, h->stream); h->ev[ph].push_back({a, b}); }
+  };
+};
+
+namespace {
+
+int fail(cb200_handle* h, const std::string& msg, int code = -1) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CB_API_BEGIN try {
+#define CB_API_END(h)                                               \
+  }                                                                 \
+  catch (const std::exception& e) { return fail((h), e.what()); }   \
+  catch (...) { return fail((h), "unknown error"); }
+
+LinSegs to_linsegs(const SampleGrid& g) {
+  LinSegs s{};
+  if (g.seg.size() > 8) throw std::runtime_error("grid has more than 8 segments");
+  s.n = (int)g.seg.size();
+  s.highest = g.highest;
+  s.npoints = g.npoints;
+  for (int i = 0; i < s.n; i++) {
+    if (g.seg[i].is_log) throw std::runtime_error("log segment in a grid that must be linear");
+    s.seg[i][0] = g.seg[i].lo; s.seg[i][1] = g.seg[i].hi; s.seg[i][2] = g.seg[i].step; s.seg[i][3] = g.seg[i].first;
+  }
+  return s;
+}
+
+// lower sample index used by the running search of InterpolateClArr (camb/modules.f90:969-975)
+std::vector<int> make_llo(const std::vector<int>& ls, int max_l) {
+  std::vector<int> llo_of(max_l + 1, 1);
+  int llo = 1, max_ind = (int)ls.size();
+  for (int il = 2; il <= ls[max_ind - 1] && il <= max_l; il++) {
+    if ((il > ls[llo]) && (llo < max_ind)) llo++;
+    llo_of[il] = llo;
+  }
+  return llo_of;
+}
+
+void build_kind(cb200_handle* h, int k, int max_l, double max_eta_k) {
+  KindSet& K = h->kind[k];
+  K.active = true;
+  K.max_l = max_l;
+  K.max_eta_k = max_eta_k;
+  K.ls = make_l_samples(max_l);
+  if ((int)K.ls.size() > PROJ_LP) throw std::runtime_error("more than 96 sampled multipoles is not supported");
+  make_bessel_x(K.bgrid, max_eta_k);
+  K.bseg = to_linsegs(K.bgrid);
+  K.num_xx = K.bgrid.npoints;
+  K.d_ls.upload(K.ls, h->stream);
+  K.d_bx.upload(K.bgrid.x, h->stream);
+  K.d_bes.alloc((size_t)K.num_xx * PROJ_LP);
+  std::vector<int> llo = make_llo(K.ls, max_l);
+  K.d_llo.upload(llo, h->stream);
+  DevBuf<double> scratch;
+  scratch.alloc((size_t)K.ls.size() * K.num_xx);
+  dim3 blk(64, 4), grd((K.num_xx + 63) / 64, (PROJ_LP + 3) / 4);
+  bessel_values_kernel<<<grd, blk, 0, h->stream>>>(K.num_xx, (int)K.ls.size(), PROJ_LP, K.d_bx.p, K.d_ls.p, K.d_bes.p);
+  CB_LAUNCH_CHECK();
+  bessel_spline_kernel<<<((int)K.ls.size() + 31) / 32, 32, 0, h->stream>>>(K.num_xx, (int)K.ls.size(), PROJ_LP,
+                                                                           K.d_bx.p, K.d_bes.p, scratch.p);
+  CB_LAUNCH_CHECK();
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  h->n_launches += 2;
+}
+
+void build_lensing(cb200_handle* h) {
+  // geometry of the correlation-function integrals (camb/lensing.f90:94-101,153-189)
+  const KindSet& K = h->kind[0];
+  LensGeom& g = h->lg;
+  const int Max_l = K.max_l;
+  int lmax_extrap = Max_l - 100 + 450 + 300;  // HighAccuracyDefault
+  lmax_extrap = std::min(8000, lmax_extrap);
+  g.max_l = Max_l;
+  g.lmax = std::max(lmax_extrap, Max_l);
+  int ix = (int)K.ls.size() - 1;
+  while (K.ls[ix - 1] > Max_l - 100) ix--;
+  g.lmax_lensed = K.ls[ix - 1];
+  int npoints = (int)(Max_l * 2 * 1.0);
+  double dtheta = kPi / npoints;
+  if (Max_l > 3500) dtheta = dtheta / (double)1.3f;
+  const int apw = round_half_away((double)0.003f / dtheta);
+  npoints = (int)(kPi / dtheta);
+  double range_fac = 1;
+  const bool short_range = !h->cfg.accurate_bb;
+  if (short_range) { range_fac = std::max(1., 32 / 1.0); npoints = (int)(npoints / range_fac); }
+  g.npoints = npoints;
+  g.dtheta = dtheta;
+  g.interp_fac = std::max(1, std::min(round_half_away(10 / 1.0), (int)(range_fac * 2) - 1));
+  g.NTH = npoints - 1;
+  g.NTHP = ((g.NTH + 31) / 32) * 32;
+  if (g.NTHP > 192 && short_range) throw std::runtime_error("unexpected theta count");
+  std::vector<int> jidx(g.lmax + 1, -1);
+  h->lj.clear();
+  for (int l = 2; l <= g.lmax; l++)
+    if (l <= 15 || ((l - 15) % g.interp_fac) == g.interp_fac / 2) { jidx[l] = (int)h->lj.size(); h->lj.push_back(l); }
+  g.jmax = (int)h->lj.size();
+  g.NLL = ((g.lmax_lensed - 1 + 3) / 4) * 4;
+  std::vector<double> apod(g.NTHP, 0.0);
+  for (int it = 0; it < g.NTH; it++) {
+    const int i = it + 1;
+    double w = 1;
+    if (short_range && i > npoints - apw * 3) {
+      const int d = i - npoints + apw * 3;
+      // single-precision factor, as the reference's integer**2/real(...) expression (lensing.f90:436)
+      w = (double)std::exp(-(float)(d * d) / (float)(2 * apw * apw));
+    }
+    apod[it] = w;
+  }
+  h->d_jidx.upload(jidx, h->stream);
+  h->d_lj.upload(h->lj, h->stream);
+  h->d_apod.upload(apod, h->stream);
+  h->d_A1.alloc((size_t)(g.lmax - 1) * 2 * g.NTHP);
+  h->d_M.alloc((size_t)4 * g.NTHP * g.NLL);
+  h->d_tab.alloc((size_t)g.jmax * 12 * g.NTHP);
+  h->d_A1.zero(h->stream); h->d_M.zero(h->stream); h->d_tab.zero(h->stream);
+  lens_tables_kernel<<<(g.NTH + 31) / 32, 32, 0, h->stream>>>(g, h->d_jidx.p, h->d_A1.p, h->d_M.p, h->d_tab.p);
+  CB_LAUNCH_CHECK();
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  h->n_launches += 1;
+}
+
+void parallel_for(int n, const std::function<void(int, int)>& fn) {
+  int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+  nt = std::min(nt, std::max(1, n / 64));
+  if (nt <= 1) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> errs(nt);
+  for (int t = 0; t < nt; t++) {
+    int a = (int)((long long)n * t / nt), b = (int)((long long)n * (t + 1) / nt);
+    th.emplace_back([&, a, b, t]() {
+      try { fn(a, b); } catch (...) { errs[t] = std::current_exception(); }
+    });
+  }
+  for (auto& x : th) x.join();
+  for (auto& e : errs) if (e) std::rethrow_exception(e);
+}
+
+void ensure_store(cb200_handle* h, int k) {
+  PointStore& S = h->store[k];
+  if (S.cap) return;
+  S.cap = h->cfg.max_points; S.NT = h->cfg.n_tau_max; S.NK = h->cfg.n_k_max; S.NQ = h->cfg.n_q_max;
+  const size_t P = S.cap;
+  S.thermo.alloc(P * 5); S.tau.alloc(P * S.NT); S.dtau.alloc(P * S.NT); S.ksrc.alloc(P * S.NK);
+  S.q.alloc(P * S.NQ); S.dq.alloc(P * S.NQ); S.n_tau.alloc(P); S.n_k.alloc(P); S.n_q.alloc(P); S.tseg.alloc(P);
+  S.src.alloc(P * S.NT * 3 * S.NK);
+  S.h_nq.assign(P, 0); S.h_ntau.assign(P, 0);
+}
+
+void ensure_work(cb200_handle* h) {
+  if (h->w_icl.p) return;
+  const int C = h->chunk, NT = h->cfg.n_tau_max, NK = h->cfg.n_k_max, NQ = h->cfg.n_q_max;
+  const int NQB = (NQ + PROJ_Q - 1) / PROJ_Q;
+  h->w_coef.alloc((size_t)C * 4 * NK);
+  h->w_ddsrc.alloc((size_t)C * NT * 3 * NK);
+  h->w_part.alloc((size_t)C * NQB * 6 * PROJ_LP);
+  h->w_icl.alloc((size_t)C * 6 * PROJ_LP);
+  h->w_cl.alloc((size_t)C * 6 * h->LS);
+  h->w_cin.alloc((size_t)C * 4 * h->LL);
+  h->w_sc.alloc((size_t)C * 2 * h->lg.NTHP);
+  h->w_corr.alloc((size_t)C * 4 * h->lg.NTHP);
+  h->w_lcon.alloc((size_t)C * 4 * h->lg.NLL);
+  h->w_initpower.alloc((size_t)C * 10);
+  h->w_alens.alloc(C); h->w_aphi.alloc(C);
+  const size_t P = h->cfg.max_points;
+  h->r_cl_lensed.alloc(P * 4 * h->LS);
+  h->r_cls_out.alloc(P * 5 * (h->cfg.lmax_out + 1));
+  h->r_derived.alloc(P * 4);
+  h->r_status.alloc(P);
+  h->r_icl.alloc(P * 6 * PROJ_LP);
+  h->r_cl.alloc(P * 6 * h->LS);
+  h->d_triples.alloc(1);
+  h->d_triples.zero(h->stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+void cb200_default_config(cb200_config* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->device = 0;
+  c->lmax_computed_cl = 2500;
+  c->cmb_lensing = 1;
+  c->use_lensing_potential = 1;
+  c->use_nonlinear_lensing = 1;
+  c->compute_tensors = 0;
+  c->lmax_tensor = 600;
+  c->accurate_bb = 0;
+  c->k_eta_max_scalar = -1;
+  c->accuracy_level = 1;
+  c->lmax_out = 2508;
+  c->highl_norm_first_call = 0;
+  c->max_points = 1024;
+  c->chunk_points = 0;
+  c->n_tau_max = 768; c->n_k_max = 256; c->n_q_max = 3072;
+}
+
+int cb200_create(const cb200_config* cfg, cb200_handle** out) {
+  if (!cfg || !out) return -1;
+  *out = nullptr;
+  std::unique_ptr<cb200_handle> h(new cb200_handle());
+  h->cfg = *cfg;
+  cb200_config& c = h->cfg;
+  try {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      throw std::runtime_error("cosmob200: no CUDA device available (there is no CPU fallback)");
+    CB_CUDA(cudaSetDevice(c.device));
+    CB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (c.accuracy_level != 1) throw std::runtime_error("only accuracy_level = 1 is supported");
+    if (!c.cmb_lensing) throw std::runtime_error("only CMB_lensing = T is supported");
+    if (c.n_tau_max <= 0) c.n_tau_max = 768;
+    if (c.n_k_max <= 0) c.n_k_max = 256;
+    if (c.n_q_max <= 0) c.n_q_max = 3072;
+    if (c.max_points <= 0) c.max_points = 1024;
+    if (c.lmax_out <= 0) c.lmax_out = c.lmax_computed_cl;
+    // CAMBCalc_InitCAMBParams (source/Calculator_CAMB.f90:749-754, 802-820)
+    int max_l = c.lmax_computed_cl + 100 + 50;
+    double max_eta_k = max_l * 2;
+    max_eta_k = std::max(std::min(max_l, 3000) * 2.5 * c.accuracy_level, max_eta_k);
+    if (c.use_lensing_potential || c.use_nonlinear_lensing) max_eta_k = std::max(max_eta_k, 14000 * c.accuracy_level);
+    if (c.k_eta_max_scalar > 0) max_eta_k = c.k_eta_max_scalar;
+    double max_eta_k_tensor = c.lmax_tensor * 5. / 2;
+    if (c.compute_tensors) max_eta_k = std::max(max_eta_k, max_eta_k_tensor);  // CAMBParams_Set, modules.f90:285
+    build_kind(h.get(), 0, max_l, max_eta_k);
+    if (c.compute_tensors) build_kind(h.get(), 1, c.lmax_tensor, max_eta_k_tensor);
+    build_lensing(h.get());
+    if (std::min(c.lmax_computed_cl, c.lmax_out) > h->lg.lmax_lensed)
+      throw std::runtime_error("lmax_computed_cl exceeds lmax_lensed");
+    h->LS = ((max_l + 1 + 3) / 4) * 4;
+    h->LL = ((h->lg.lmax + 1 + 3) / 4) * 4;
+    h->chunk = c.chunk_points > 0 ? c.chunk_points : std::min(c.max_points, 1024);
+    h->chunk = std::min(h->chunk, c.max_points);
+    c.chunk_points = h->chunk;
+    cb200_info& I = h->info;
+    I.max_l = max_l; I.max_eta_k = (int)max_eta_k; I.max_l_tensor = c.lmax_tensor; I.max_eta_k_tensor = (int)max_eta_k_tensor;
+    I.n_lsamp = (int)h->kind[0].ls.size(); I.n_lsamp_tensor = (int)h->kind[1].ls.size();
+    I.num_xx = h->kind[0].num_xx; I.lmax_lensed = h->lg.lmax_lensed; I.lens_lmax = h->lg.lmax;
+    I.lens_npoints = h->lg.npoints; I.lens_jmax = h->lg.jmax;
+    I.n_tau_max = c.n_tau_max; I.n_k_max = c.n_k_max; I.n_q_max = c.n_q_max; I.max_points = c.max_points;
+    I.chunk_points = h->chunk;
+    const char* ct = std::getenv("CB200_COUNT_TRIPLES");
+    h->count_triples = ct && ct[0] == '1';
+    CB_CUDA(cudaFuncSetAttribute(project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "cb200_create: %s\n", e.what());
+    return -1;
+  }
+  *out = h.release();
+  return 0;
+}
+
+void cb200_destroy(cb200_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& v : h->ev) for (auto& p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* cb200_last_error(const cb200_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int cb200_get_info(const cb200_handle* h, cb200_info* info) {
+  if (!h || !info) return -1;
+  *info = h->info;
+  return 0;
+}
+
+int cb200_get_lsamples(const cb200_handle* h, int kind, int* l, int* n) {
+  if (!h || kind < 0 || kind > 1 || !h->kind[kind].active) return -1;
+  const auto& ls = h->kind[kind].ls;
+  if (l) for (size_t i = 0; i < ls.size(); i++) l[i] = ls[i];
+  if (n) *n = (int)ls.size();
+  return 0;
+}
+
+int cb200_set_templates(cb200_handle* h, const double* unl, const double* lensed, int n_l) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  h->d_tmpl.upload(unl, (size_t)4 * kTmplL, h->stream);
+  if (lensed && n_l > 0) { h->d_highl.upload(lensed, (size_t)4 * n_l, h->stream); h->n_highl = n_l; }
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  h->have_templates = true;
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_make_q_grid(const cb200_handle* h, int kind, double tau0, int max_n, double* q, double* dq, int* n) {
+  if (!h || !h->kind[kind].active) return -1;
+  try {
+    SampleGrid g;
+    make_q_grid(g, tau0, h->kind[kind].max_eta_k, h->kind[kind].max_l);
+    *n = g.npoints;
+    if (g.npoints > max_n) return -2;
+    std::copy(g.x.begin(), g.x.end(), q);
+    std::copy(g.dx.begin(), g.dx.end(), dq);
+    return 0;
+  } catch (...) { return -1; }
+}
+
+int cb200_make_time_steps(const cb200_handle* h, int kind, double tau0, double taurst, double taurend, double rs,
+                          double rc, int max_n, double* tau, double* dtau, int* n) {
+  if (!h || !h->kind[kind].active) return -1;
+  try {
+    SampleGrid g;
+    make_time_steps(g, taurst, taurend, tau0, h->kind[kind].max_eta_k, kind == 1, rs, rc);
+    *n = g.npoints;
+    if (g.npoints > max_n) return -2;
+    std::copy(g.x.begin(), g.x.end(), tau);
+    std::copy(g.dx.begin(), g.dx.end(), dtau);
+    return 0;
+  } catch (...) { return -1; }
+}
+
+int cb200_make_source_k(const cb200_handle* h, int kind, double tau0, double taurst, int max_n, double* k, int* n) {
+  if (!h || !h->kind[kind].active) return -1;
+  try {
+    SampleGrid g;
+    make_source_k(g, tau0, taurst, h->kind[kind].max_eta_k, kind == 1, h->kind[kind].max_l);
+    *n = g.npoints;
+    if (g.npoints > max_n) return -2;
+    std::copy(g.x.begin(), g.x.end(), k);
+    return 0;
+  } catch (...) { return -1; }
+}
+
+int cb200_grid_build(int nops, const double* ops, int max_n, double* x, double* dx, int* n, int n_query,
+                     const double* query, int* index_out) {
+  try {
+    SampleGrid g;
+    for (int i = 0; i < nops; i++) {
+      const double* o = ops + 5 * i;
+      if (o[0] == 0) g.add_spacing(o[1], o[2], o[3], o[4] != 0);
+      else g.add_count(o[1], o[2], (int)o[3], o[4] != 0);
+    }
+    g.materialise(true);
+    *n = g.npoints;
+    if (g.npoints > max_n) return -2;
+    std::copy(g.x.begin(), g.x.end(), x);
+    std::copy(g.dx.begin(), g.dx.end(), dx);
+    for (int i = 0; i < n_query; i++) index_out[i] = g.index_of(query[i]);
+    return 0;
+  } catch (...) { return -1; }
+}
+
+int cb200_get_bessel_table(const cb200_handle* hc, int kind, double* x, double* ajl, double* ajlpr) {
+  cb200_handle* h = const_cast<cb200_handle*>(hc);
+  if (!h || !h->kind[kind].active) return -1;
+  CB_API_BEGIN
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  const KindSet& K = h->kind[kind];
+  std::vector<double2> tmp((size_t)K.num_xx * PROJ_LP);
+  CB_CUDA(cudaMemcpy(tmp.data(), K.d_bes.p, tmp.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+  const int nl = (int)K.ls.size();
+  for (int i = 0; i < K.num_xx; i++) {
+    x[i] = K.bgrid.x[i];
+    for (int j = 0; j < nl; j++) {
+      ajl[(size_t)j * K.num_xx + i] = tmp[(size_t)i * PROJ_LP + j].x;
+      ajlpr[(size_t)j * K.num_xx + i] = tmp[(size_t)i * PROJ_LP + j].y;
+    }
+  }
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_upload_sources(cb200_handle* h, int kind, int first, int npts, const double* thermo, const int* n_k,
+                         const double* k, const double* src, int src_is_device) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (kind < 0 || kind > 1 || !h->kind[kind].active) return fail(h, "upload_sources: kind not configured");
+  if (first < 0 || npts <= 0 || first + npts > h->cfg.max_points) return fail(h, "upload_sources: point range exceeds max_points");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  ensure_store(h, kind);
+  PointStore& S = h->store[kind];
+  const KindSet& K = h->kind[kind];
+  std::vector<double> tau((size_t)npts * S.NT, 0.0), dtau((size_t)npts * S.NT, 0.0), q((size_t)npts * S.NQ, 0.0),
+      dq((size_t)npts * S.NQ, 0.0);
+  std::vector<int> ntau(npts), nq(npts);
+  std::vector<LinSegs> tseg(npts);
+  std::string perr;
+  parallel_for(npts, [&](int a, int b) {
+    SampleGrid gt, gq;
+    for (int i = a; i < b; i++) {
+      const double* th = thermo + (size_t)i * 5;
+      make_time_steps(gt, th[1], th[2], th[0], K.max_eta_k, kind == 1, th[3], th[4]);
+      make_q_grid(gq, th[0], K.max_eta_k, K.max_l);
+      if (gt.npoints > S.NT) throw std::runtime_error("n_tau exceeds n_tau_max");
+      if (gq.npoints > S.NQ) throw std::runtime_error("n_q exceeds n_q_max");
+      if (n_k[i] > S.NK || n_k[i] < 4) throw std::runtime_error("n_k out of range");
+      ntau[i] = gt.npoints; nq[i] = gq.npoints;
+      std::copy(gt.x.begin(), gt.x.end(), tau.begin() + (size_t)i * S.NT);
+      std::copy(gt.dx.begin(), gt.dx.end(), dtau.begin() + (size_t)i * S.NT);
+      std::copy(gq.x.begin(), gq.x.end(), q.begin() + (size_t)i * S.NQ);
+      std::copy(gq.dx.begin(), gq.dx.end(), dq.begin() + (size_t)i * S.NQ);
+      tseg[i] = to_linsegs(gt);
+    }
+  });
+  cudaStream_t s = h->stream;
+  const size_t f = first;
+  CB_CUDA(cudaMemcpyAsync(S.thermo.p + f * 5, thermo, sizeof(double) * npts * 5, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(S.tau.p + f * S.NT, tau.data(), sizeof(double) * tau.size(), cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(S.dtau.p + f * S.NT, dtau.data(), sizeof(double) * dtau.size(), cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(S.q.p + f * S.NQ, q.data(), sizeof(double) * q.size(), cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(S.dq.p + f * S.NQ, dq.data(), sizeof(double) * dq.size(), cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(S.ksrc.p + f * S.NK, k, sizeof(double) * (size_t)npts * S.NK, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(S.n_tau.p + f, ntau.data(), sizeof(int) * npts, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(S.n_q.p + f, nq.data(), sizeof(int) * npts, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(S.n_k.p + f, n_k, sizeof(int) * npts, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(S.tseg.p + f, tseg.data(), sizeof(LinSegs) * npts, cudaMemcpyHostToDevice, s));
+  const size_t per = (size_t)S.NT * 3 * S.NK;
+  if (src)
+    CB_CUDA(cudaMemcpyAsync(S.src.p + f * per, src, sizeof(double) * per * npts,
+                            src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  for (int i = 0; i < npts; i++) { S.h_nq[first + i] = nq[i]; S.h_ntau[first + i] = ntau[i]; }
+  CB_CUDA(cudaStreamSynchronize(s));  // host staging vectors go out of scope
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_keep_transfers(cb200_handle* h, int on) {
+  if (!h) return -1;
+  h->keep_transfers = on != 0;
+  return 0;
+}
+
+int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, const double* alens,
+                 const double* aphiphi, double* cls_out, double* derived_out, int* status) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (!h->have_templates) return fail(h, "powers: call cb200_set_templates first");
+  PointStore& S = h->store[0];
+  if (!S.cap || first < 0 || npts <= 0 || first + npts > S.cap) return fail(h, "powers: point range not resident");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  ensure_work(h);
+  cudaStream_t s = h->stream;
+  const KindSet& K = h->kind[0];
+  const LensGeom& g = h->lg;
+  const int nl = (int)K.ls.size();
+  const int NQB = (S.NQ + PROJ_Q - 1) / PROJ_Q;
+  const int lmax_out = h->cfg.lmax_out;
+  if (h->keep_transfers) h->w_delta.alloc((size_t)h->chunk * S.NQ * PROJ_LP * 3);
+
+  for (int c0 = 0; c0 < npts; c0 += h->chunk) {
+    const int np = std::min(h->chunk, npts - c0);
+    const int p0 = first + c0;
+    h->last_chunk_p0 = p0; h->last_chunk_np = np;
+    CB_CUDA(cudaMemcpyAsync(h->w_initpower.p, initpower + (size_t)c0 * 10, sizeof(double) * 10 * np,
+                            cudaMemcpyHostToDevice, s));
+    if (alens) CB_CUDA(cudaMemcpyAsync(h->w_alens.p, alens + c0, sizeof(double) * np, cudaMemcpyHostToDevice, s));
+    if (aphiphi) CB_CUDA(cudaMemcpyAsync(h->w_aphi.p, aphiphi + c0, sizeof(double) * np, cudaMemcpyHostToDevice, s));
+    PointView v = S.view();
+    int nq_max = 0;
+    for (int i = 0; i < np; i++) nq_max = std::max(nq_max, S.h_nq[p0 + i]);
+    const int nqb_used = (nq_max + PROJ_Q - 1) / PROJ_Q;
+    {  // K0
+      cb200_handle::Scope sc(h, PH_SPLINE);
+      spline_setup_kernel<<<(np + 63) / 64, 64, 0, s>>>(v, p0, np, h->w_coef.p);
+      CB_LAUNCH_CHECK();
+      const long long rows = (long long)np * S.NT * 3;
+      source_spline_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(v, p0, np, h->w_coef.p, h->w_ddsrc.p);
+      CB_LAUNCH_CHECK();
+      h->n_launches += 2;
+    }
+    {  // K1
+      cb200_handle::Scope sc(h, PH_PROJECT);
+      ProjParams pp;
+      pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB = NQB; pp.tensors = 0;
+      pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes = K.d_bes.p;
+      pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
+      pp.delta = h->keep_transfers ? h->w_delta.p : nullptr;
+      pp.triples = h->count_triples ? h->d_triples.p : nullptr;
+      pp.bseg = K.bseg;
+      for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
+      constexpr size_t META = sizeof(ProjMeta) * PROJ_NS * PROJ_SLAB * PROJ_Q;
+      constexpr size_t RED = sizeof(double) * (PROJ_NS - 1) * PROJ_Q * 3 * PROJ_LP;
+      const size_t smem = std::max(META, RED) + sizeof(ProjQ) * PROJ_Q;
+      dim3 grid(nqb_used, np);
+      project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB><<<grid, 32 * PROJ_LW * PROJ_NS, smem, s>>>(pp);
+      CB_LAUNCH_CHECK();
+      h->n_launches += 1;
+    }
+    {  // K2
+      cb200_handle::Scope sc(h, PH_CONTRACT);
+      dim3 grid((6 * PROJ_LP + 127) / 128, np);
+      contract_reduce_kernel<<<grid, 128, 0, s>>>(np, p0, S.n_q.p, PROJ_Q, NQB, nl, K.d_ls.p, 0,
+                                                 alens ? h->w_alens.p : nullptr, h->w_part.p, h->w_icl.p);
+      CB_LAUNCH_CHECK();
+      h->n_launches += 1;
+    }
+    {  // K3
+      cb200_handle::Scope sc(h, PH_INTERP);
+      InterpParams ip;
+      ip.np = np; ip.nl = nl; ip.max_l = K.max_l; ip.LS = h->LS; ip.nspec = 6; ip.templated = 1;
+      ip.icl = h->w_icl.p; ip.ls = K.d_ls.p; ip.llo_of_l = K.d_llo.p; ip.tmpl = h->d_tmpl.p; ip.cl = h->w_cl.p;
+      interp_cls_kernel<<<np, 192, 0, s>>>(ip, PROJ_LP);
+      CB_LAUNCH_CHECK();
+      h->n_launches += 1;
+    }
+    {  // K4
+      cb200_handle::Scope sc(h, PH_LENS);
+      dim3 gp((g.lmax + 1 + 127) / 128, np);
+      lens_prep_kernel<<<gp, 128, 0, s>>>(np, g, h->LS, h->LL, h->w_cl.p, h->d_tmpl.p, h->w_cin.p);
+      CB_LAUNCH_CHECK();
+      // (1) sigma^2 | Cg2 = Cphil3[2..lmax] x A1
+      dgemm(s, false, false, np, 2 * g.NTHP, g.lmax - 1, 1.0, h->w_cin.p + 2, 4 * h->LL, h->d_A1.p, 2 * g.NTHP,
+            h->w_sc.p, 2 * g.NTHP, &h->n_launches);
+      LensCorrParams cp;
+      cp.np = np; cp.LL = h->LL; cp.g = g; cp.sc = h->w_sc.p; cp.cin = h->w_cin.p; cp.tab = h->d_tab.p;
+      cp.lj = h->d_lj.p; cp.apod = h->d_apod.p; cp.corr = h->w_corr.p;
+      const size_t csm = sizeof(double) * LENS_PB * 3 * g.jmax;
+      lens_corr_kernel<<<(np + LENS_PB - 1) / LENS_PB, g.NTHP, csm, s>>>(cp);
+      CB_LAUNCH_CHECK();
+      // (3) four correlation -> multipole transforms
+      const size_t ms = (size_t)g.NTHP * g.NLL;
+      for (int k4 = 0; k4 < 4; k4++)
+        dgemm(s, false, false, np, g.lmax_lensed - 1, g.NTHP, 1.0, h->w_corr.p + (size_t)k4 * g.NTHP, 4 * g.NTHP,
+              h->d_M.p + k4 * ms, g.NLL, h->w_lcon.p + (size_t)k4 * g.NLL, 4 * g.NLL, &h->n_launches);
+      FinishParams fp;
+      fp.np = np; fp.LS = h->LS; fp.NLL = g.NLL; fp.lmax_out = lmax_out; fp.lmax_computed_cl = h->cfg.lmax_computed_cl;
+      fp.lmax_lensed = g.lmax_lensed; fp.n_highl = h->n_highl; fp.lmax_tensor = 0; fp.have_tensor = 0; fp.LST = 0;
+      fp.dtheta = g.dtheta; fp.cl = h->w_cl.p; fp.lcon = h->w_lcon.p; fp.cl_tensor = nullptr; fp.tensor_shared = 0;
+      fp.highl = h->d_highl.p; fp.aphiphi = aphiphi ? h->w_aphi.p : nullptr;
+      fp.cl_lensed = h->r_cl_lensed.p + (size_t)p0 * 4 * h->LS;
+      fp.cls_out = h->r_cls_out.p + (size_t)p0 * 5 * (lmax_out + 1);
+      fp.saved_highl_norm = h->cfg.highl_norm_first_call ? h->saved_highl_norm : 0.0;
+      const int lspan = std::max(h->LS, lmax_out + 1);
+      dim3 gf((lspan + 127) / 128, np);
+      lens_finish_kernel<<<gf, 128, 0, s>>>(fp);
+      CB_LAUNCH_CHECK();
+      derived_status_kernel<<<np, 32, 0, s>>>(np, h->LS, lmax_out, K.max_l, h->w_cl.p, fp.cls_out,
+                                              h->r_derived.p + (size_t)p0 * 4, h->r_status.p + p0);
+      CB_LAUNCH_CHECK();
+      h->n_launches += 4;
+    }
+    // keep intermediates resident for parity read-backs
+    CB_CUDA(cudaMemcpyAsync(h->r_icl.p + (size_t)p0 * 6 * PROJ_LP, h->w_icl.p, sizeof(double) * np * 6 * PROJ_LP,
+                            cudaMemcpyDeviceToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(h->r_cl.p + (size_t)p0 * 6 * h->LS, h->w_cl.p, sizeof(double) * np * 6 * h->LS,
+                            cudaMemcpyDeviceToDevice, s));
+  }
+  if (cls_out)
+    CB_CUDA(cudaMemcpyAsync(cls_out, h->r_cls_out.p + (size_t)first * 5 * (lmax_out + 1),
+                            sizeof(double) * npts * 5 * (lmax_out + 1), cudaMemcpyDeviceToHost, s));
+  if (derived_out)
+    CB_CUDA(cudaMemcpyAsync(derived_out, h->r_derived.p + (size_t)first * 4, sizeof(double) * npts * 4,
+                            cudaMemcpyDeviceToHost, s));
+  if (status)
+    CB_CUDA(cudaMemcpyAsync(status, h->r_status.p + first, sizeof(int) * npts, cudaMemcpyDeviceToHost, s));
+  if (cls_out || derived_out || status) CB_CUDA(cudaStreamSynchronize(s));
+  if (h->cfg.highl_norm_first_call && h->saved_highl_norm == 0 && h->n_highl > 0) {
+    // reference SAVE semantics: the first evaluated point fixes the tail normalisation for the whole run
+    const int lmx = std::min(h->cfg.lmax_computed_cl, lmax_out);
+    double tt = 0;
+    std::vector<double> hl(1);
+    CB_CUDA(cudaMemcpy(&tt, h->r_cls_out.p + (size_t)first * 5 * (lmax_out + 1) + lmx, sizeof(double), cudaMemcpyDeviceToHost));
+    CB_CUDA(cudaMemcpy(hl.data(), h->d_highl.p + lmx, sizeof(double), cudaMemcpyDeviceToHost));
+    h->saved_highl_norm = tt / hl[0];
+  }
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_debug_fetch(cb200_handle* h, int what, int point, int max_n, double* out, int* n) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  const PointStore& S = h->store[0];
+  const KindSet& K = h->kind[0];
+  const int nl = (int)K.ls.size();
+  auto fetch = [&](const double* d, size_t cnt) {
+    if ((long long)cnt > max_n) throw std::runtime_error("debug_fetch: buffer too small");
+    CB_CUDA(cudaMemcpy(out, d, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+    *n = (int)cnt;
+  };
+  switch (what) {
+    case 0: {
+      std::vector<double> t((size_t)6 * PROJ_LP);
+      CB_CUDA(cudaMemcpy(t.data(), h->r_icl.p + (size_t)point * 6 * PROJ_LP, sizeof(double) * t.size(), cudaMemcpyDeviceToHost));
+      if (6 * nl > max_n) return fail(h, "debug_fetch: buffer too small");
+      for (int X = 0; X < 6; X++) for (int j = 0; j < nl; j++) out[X * nl + j] = t[(size_t)X * PROJ_LP + j];
+      *n = 6 * nl;
+      break;
+    }
+    case 1: {
+      std::vector<double> t((size_t)6 * h->LS);
+      CB_CUDA(cudaMemcpy(t.data(), h->r_cl.p + (size_t)point * 6 * h->LS, sizeof(double) * t.size(), cudaMemcpyDeviceToHost));
+      const int w = K.max_l + 1;
+      if (6 * w > max_n) return fail(h, "debug_fetch: buffer too small");
+      for (int X = 0; X < 6; X++) for (int l = 0; l < w; l++) out[X * w + l] = t[(size_t)X * h->LS + l];
+      *n = 6 * w;
+      break;
+    }
+    case 2: {
+      std::vector<double> t((size_t)4 * h->LS);
+      CB_CUDA(cudaMemcpy(t.data(), h->r_cl_lensed.p + (size_t)point * 4 * h->LS, sizeof(double) * t.size(), cudaMemcpyDeviceToHost));
+      const int w = K.max_l + 1;
+      if (4 * w > max_n) return fail(h, "debug_fetch: buffer too small");
+      for (int X = 0; X < 4; X++) for (int l = 0; l < w; l++) out[X * w + l] = (l <= h->lg.lmax_lensed) ? t[(size_t)X * h->LS + l] : 0.0;
+      *n = 4 * w;
+      break;
+    }
+    case 3: {
+      if (!h->keep_transfers || !h->w_delta.p) return fail(h, "debug_fetch: transfers not kept");
+      // valid for points of the last processed chunk only
+      const int local = point - h->last_chunk_p0;
+      if (local < 0 || local >= h->last_chunk_np) return fail(h, "debug_fetch: point not in the last chunk");
+      fetch(h->w_delta.p + (size_t)local * S.NQ * PROJ_LP * 3, (size_t)S.h_nq[point] * PROJ_LP * 3);
+      break;
+    }
+    case 4: fetch(S.q.p + (size_t)point * S.NQ, S.h_nq[point]); break;
+    case 5: fetch(S.dq.p + (size_t)point * S.NQ, S.h_nq[point]); break;
+    case 6: fetch(S.tau.p + (size_t)point * S.NT, S.h_ntau[point]); break;
+    case 7: fetch(S.dtau.p + (size_t)point * S.NT, S.h_ntau[point]); break;
+    default: return fail(h, "debug_fetch: unknown selector");
+  }
+  return 0;
+  CB_API_END(h)
+}
+
+// ---------------------------------------------------------------------------------------------- likelihoods
+int cb200_like_add_pliklite(cb200_handle* h, const int* nb, int nbins_tab, const int* blmin, const int* blmax,
+                            const double* weights, int lmax_w, const double* invcov, const double* x_data,
+                            int cal_index, int* like_id) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  std::unique_ptr<LikeEntry> L(new LikeEntry());
+  L->type = 1; L->cal_index = cal_index; L->lmax_w = lmax_w;
+  std::vector<int> spec, lo, hi;
+  for (int i = 0; i < 3; i++) {
+    if (nb[i] > nbins_tab) return fail(h, "pliklite: nb exceeds bin table");
+    for (int j = 0; j < nb[i]; j++) {
+      if (blmax[j] > std::min(lmax_w, h->cfg.lmax_out)) return fail(h, "pliklite: bin exceeds lmax_out / weights");
+      spec.push_back(i); lo.push_back(blmin[j]); hi.push_back(blmax[j]);
+    }
+  }
+  L->nused = (int)spec.size();
+  L->bin_spec.upload(spec, h->stream); L->bin_lo.upload(lo, h->stream); L->bin_hi.upload(hi, h->stream);
+  L->weights.upload(weights, (size_t)lmax_w + 1, h->stream);
+  L->x_data.upload(x_data, L->nused, h->stream);
+  L->invcov.upload(invcov, (size_t)L->nused * L->nused, h->stream);
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  if (like_id) *like_id = (int)h->likes.size();
+  h->likes.push_back(std::move(L));
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_like_add_cmblikes(cb200_handle* h, int nmaps, int nbins, int ncl_used, const int* cl_use_index,
+                            int like_approx, int lmax_w, const double* W, const double* offset, const double* noise,
+                            const double* chat, const double* sqrt_fid, const double* invcov, double log_cal_prior,
+                            int cal_index, int* like_id) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  if (nmaps > CMBL_MAXMAPS) return fail(h, "cmblikes: too many maps");
+  if (lmax_w > h->cfg.lmax_out) return fail(h, "cmblikes: window lmax exceeds lmax_out");
+  if (like_approx == 1 && !sqrt_fid) return fail(h, "cmblikes: HL needs sqrt_fid");
+  std::unique_ptr<LikeEntry> L(new LikeEntry());
+  L->type = 2; L->cal_index = cal_index; L->lmax_w = lmax_w; L->nmaps = nmaps; L->ncl = nmaps * (nmaps + 1) / 2;
+  L->nbins = nbins; L->ncl_used = ncl_used; L->like_approx = like_approx; L->log_cal_prior = log_cal_prior;
+  const int nb = nbins * L->ncl, LO = h->cfg.lmax_out + 1;
+  // transpose the windows into GEMM B operands: Wt_cmb [(X,l)][nb] for X = TT,TE,EE,BB and Wt_pp [l][nb]
+  std::vector<double> wc((size_t)4 * LO * nb, 0.0), wp((size_t)LO * nb, 0.0);
+  for (int b = 0; b < nb; b++)
+    for (int X = 0; X < 5; X++)
+      for (int l = 0; l <= lmax_w; l++) {
+        const double v = W[((size_t)b * 5 + X) * (lmax_w + 1) + l];
+        if (X < 4) wc[((size_t)X * LO + l) * nb + b] = v;
+        else wp[(size_t)l * nb + b] = v;
+      }
+  L->Wt_cmb.upload(wc, h->stream); L->Wt_pp.upload(wp, h->stream);
+  L->offset.upload(offset, nb, h->stream);
+  const size_t nm = (size_t)nbins * nmaps * nmaps;
+  if (noise) { L->noise.upload(noise, nm, h->stream); L->has_noise = true; }
+  L->chat.upload(chat, nm, h->stream);
+  if (sqrt_fid) { L->sqrt_fid.upload(sqrt_fid, nm, h->stream); L->has_sqrt_fid = true; }
+  L->cl_use.upload(cl_use_index, ncl_used, h->stream);
+  const size_t nx = (size_t)nbins * ncl_used;
+  L->invcov.upload(invcov, nx * nx, h->stream);
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  if (like_id) *like_id = (int)h->likes.size();
+  h->likes.push_back(std::move(L));
+  return 0;
+  CB_API_END(h)
+}
+
+static int loglike_device(cb200_handle* h, int npts, const double* d_cls, const int* d_status, const double* nuisance,
+                          int n_nuis, double* loglikes, double* total, int* status) {
+  cudaStream_t s = h->stream;
+  const int nlike = (int)h->likes.size();
+  if (nlike == 0) return fail(h, "loglike: no likelihood registered");
+  const int LO = h->cfg.lmax_out + 1;
+  h->w_ll.alloc((size_t)npts * nlike);
+  h->w_total.alloc(npts);
+  h->w_quad.alloc(npts);
+  h->w_nuis.alloc((size_t)npts * std::max(1, n_nuis));
+  if (n_nuis > 0) CB_CUDA(cudaMemcpyAsync(h->w_nuis.p, nuisance, sizeof(double) * npts * n_nuis, cudaMemcpyHostToDevice, s));
+  {
+    cb200_handle::Scope sc(h, PH_LIKE);
+    for (int li = 0; li < nlike; li++) {
+      LikeEntry& L = *h->likes[li];
+      if (L.cal_index >= n_nuis) return fail(h, "loglike: calibration index outside the nuisance vector");
+      if (L.type == 1) {
+        h->w_resid.alloc((size_t)npts * L.nused);
+        h->w_T.alloc((size_t)npts * L.nused);
+        PlikBinParams bp;
+        bp.np = npts; bp.nused = L.nused; bp.lmax_out = h->cfg.lmax_out; bp.n_nuis = n_nuis; bp.cal_index = L.cal_index;
+        bp.cls = d_cls; bp.bin_spec = L.bin_spec.p; bp.bin_lo = L.bin_lo.p; bp.bin_hi = L.bin_hi.p;
+        bp.weights = L.weights.p; bp.x_data = L.x_data.p; bp.nuis = h->w_nuis.p; bp.resid = h->w_resid.p;
+        dim3 grid((L.nused + 127) / 128, npts);
+        plik_bin_kernel<<<grid, 128, 0, s>>>(bp);
+        CB_LAUNCH_CHECK();
+        dgemm(s, false, false, npts, L.nused, L.nused, 1.0, h->w_resid.p, L.nused, L.invcov.p, L.nused, h->w_T.p,
+              L.nused, &h->n_launches);
+        rowdot_kernel<<<(npts + 3) / 4, 128, 0, s>>>(npts, L.nused, h->w_T.p, h->w_resid.p, 0.5, h->w_ll.p + li, nlike, 0);
+        CB_LAUNCH_CHECK();
+        h->n_launches += 2;
+      } else if (L.type == 2) {
+        const int nb = L.nbins * L.ncl, nx = L.nbins * L.ncl_used;
+        h->w_bc.alloc((size_t)npts * nb); h->w_bp.alloc((size_t)npts * nb);
+        h->w_bigx.alloc((size_t)npts * nx); h->w_T.alloc((size_t)npts * std::max(nx, 1));
+        h->w_binned.alloc((size_t)npts * nb);
+        dgemm(s, false, false, npts, nb, 4 * LO, 1.0, d_cls, 5 * LO, L.Wt_cmb.p, nb, h->w_bc.p, nb, &h->n_launches);
+        dgemm(s, false, false, npts, nb, LO, 1.0, d_cls + (size_t)4 * LO, 5 * LO, L.Wt_pp.p, nb, h->w_bp.p, nb,
+              &h->n_launches);
+        CmbLikesBinParams cp;
+        cp.np = npts; cp.nmaps = L.nmaps; cp.ncl = L.ncl; cp.nbins = L.nbins; cp.ncl_used = L.ncl_used;
+        cp.like_approx = L.like_approx; cp.n_nuis = n_nuis; cp.cal_index = L.cal_index;
+        cp.bc = h->w_bc.p; cp.bp = h->w_bp.p; cp.offset = L.offset.p; cp.noise = L.has_noise ? L.noise.p : nullptr;
+        cp.chat = L.chat.p; cp.sqrt_fid = L.has_sqrt_fid ? L.sqrt_fid.p : nullptr; cp.cl_use = L.cl_use.p;
+        cp.nuis = h->w_nuis.p; cp.bigx = h->w_bigx.p; cp.binned_out = h->w_binned.p;
+        dim3 grid((L.nbins + 31) / 32, npts);
+        cmblikes_bin_kernel<<<grid, 32, 0, s>>>(cp);
+        CB_LAUNCH_CHECK();
+        dgemm(s, false, false, npts, nx, nx, 1.0, h->w_bigx.p, nx, L.invcov.p, nx, h->w_T.p, nx, &h->n_launches);
+        rowdot_kernel<<<(npts + 3) / 4, 128, 0, s>>>(npts, nx, h->w_T.p, h->w_bigx.p, 1.0, h->w_quad.p, 1, 0);
+        CB_LAUNCH_CHECK();
+        cmblikes_final_kernel<<<(npts + 127) / 128, 128, 0, s>>>(npts, h->w_quad.p, h->w_nuis.p, n_nuis, L.cal_index,
+                                                                 L.log_cal_prior, h->w_ll.p + li, nlike);
+        CB_LAUNCH_CHECK();
+        h->n_launches += 3;
+      }
+    }
+    total_kernel<<<(npts + 127) / 128, 128, 0, s>>>(npts, nlike, h->w_ll.p, d_status, h->w_total.p);
+    CB_LAUNCH_CHECK();
+    h->n_launches += 1;
+  }
+  if (loglikes) CB_CUDA(cudaMemcpyAsync(loglikes, h->w_ll.p, sizeof(double) * npts * nlike, cudaMemcpyDeviceToHost, s));
+  if (total) CB_CUDA(cudaMemcpyAsync(total, h->w_total.p, sizeof(double) * npts, cudaMemcpyDeviceToHost, s));
+  if (status && d_status) CB_CUDA(cudaMemcpyAsync(status, d_status, sizeof(int) * npts, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  if (status && !d_status) for (int i = 0; i < npts; i++) status[i] = 0;
+  return 0;
+}
+
+int cb200_loglike_batch(cb200_handle* h, int first, int npts, const double* nuisance, int n_nuis, double* loglikes,
+                        double* total, int* status) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (!h->r_cls_out.p || first < 0 || first + npts > h->cfg.max_points) return fail(h, "loglike_batch: no resident Cls");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  return loglike_device(h, npts, h->r_cls_out.p + (size_t)first * 5 * (h->cfg.lmax_out + 1), h->r_status.p + first,
+                        nuisance, n_nuis, loglikes, total, status);
+  CB_API_END(h)
+}
+
+int cb200_loglike_cls(cb200_handle* h, int npts, const double* cls, const double* nuisance, int n_nuis,
+                      double* loglikes, double* total, int* status) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)npts * 5 * (h->cfg.lmax_out + 1);
+  h->w_cls_in.alloc(n);
+  CB_CUDA(cudaMemcpyAsync(h->w_cls_in.p, cls, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  return loglike_device(h, npts, h->w_cls_in.p, nullptr, nuisance, n_nuis, loglikes, total, status);
+  CB_API_END(h)
+}
+
+int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset) {
+  if (!h || !t) return -1;
+  CB_API_BEGIN
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  float ms[PH_COUNT];
+  for (int p = 0; p < PH_COUNT; p++) {
+    ms[p] = 0;
+    for (auto& e : h->ev[p]) {
+      float x = 0;
+      cudaEventElapsedTime(&x, e.first, e.second);
+      ms[p] += x;
+    }
+  }
+  t->ms_spline = ms[PH_SPLINE]; t->ms_project = ms[PH_PROJECT]; t->ms_contract = ms[PH_CONTRACT];
+  t->ms_interp = ms[PH_INTERP]; t->ms_lens = ms[PH_LENS]; t->ms_like = ms[PH_LIKE];
+  t->ms_total = 0;
+  for (int p = 0; p < PH_COUNT; p++) t->ms_total += ms[p];
+  t->n_launches = h->n_launches;
+  unsigned long long tr = 0;
+  if (h->d_triples.p) CB_CUDA(cudaMemcpy(&tr, h->d_triples.p, sizeof(tr), cudaMemcpyDeviceToHost));
+  t->proj_triples = (long long)tr;
+  if (reset) {
+    for (int p = 0; p < PH_COUNT; p++) {
+      for (auto& e : h->ev[p]) { h->ev_pool.push_back(e.first); h->ev_pool.push_back(e.second); }
+      h->ev[p].clear();
+    }
+    h->n_launches = 0;
+    if (h->d_triples.p) h->d_triples.zero(h->stream);
+  }
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_sync(cb200_handle* h) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+  CB_API_END(h)
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+"""ctypes binding of libcosmob200.so (the C ABI declared in include/cosmob200.h).
+
+This is the shim GetDist-side Python and the tests drive; it is the Python analogue of the Fortran
+ISO_C_BINDING glue in cosmomc_b200/fortran/Calculator_B200.f90 (precedent in the reference: pycamb binds
+camblib.so's `__handles_MOD_*` symbols through ctypes, camb/camb_python.f90 + camb/pycamb/camb/baseconfig.py).
+
+There is no CPU fallback: importing works anywhere (so the symbol table can be checked), but creating a
+handle without a CUDA device raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcosmob200.so")
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+# every symbol include/cosmob200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "cb200_default_config", "cb200_create", "cb200_destroy", "cb200_last_error", "cb200_get_info",
+    "cb200_get_lsamples", "cb200_set_templates", "cb200_make_q_grid", "cb200_make_time_steps",
+    "cb200_make_source_k", "cb200_grid_build", "cb200_get_bessel_table", "cb200_upload_sources", "cb200_powers",
+    "cb200_debug_fetch", "cb200_keep_transfers", "cb200_like_add_pliklite", "cb200_like_add_cmblikes",
+    "cb200_loglike_batch", "cb200_loglike_cls", "cb200_get_timing", "cb200_sync",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("lmax_computed_cl", C.c_int), ("cmb_lensing", C.c_int),
+                ("use_lensing_potential", C.c_int), ("use_nonlinear_lensing", C.c_int), ("compute_tensors", C.c_int),
+                ("lmax_tensor", C.c_int), ("accurate_bb", C.c_int), ("k_eta_max_scalar", C.c_double),
+                ("accuracy_level", C.c_double), ("lmax_out", C.c_int), ("highl_norm_first_call", C.c_int),
+                ("max_points", C.c_int), ("chunk_points", C.c_int), ("n_tau_max", C.c_int), ("n_k_max", C.c_int),
+                ("n_q_max", C.c_int)]
+
+
+class Info(C.Structure):
+    _fields_ = [(n, C.c_int) for n in
+                ["max_l", "max_eta_k", "max_l_tensor", "max_eta_k_tensor", "n_lsamp", "n_lsamp_tensor", "num_xx",
+                 "lmax_lensed", "lens_lmax", "lens_npoints", "lens_jmax", "n_tau_max", "n_k_max", "n_q_max",
+                 "max_points", "chunk_points"]]
+
+
+class Timing(C.Structure):
+    _fields_ = [("ms_spline", C.c_float), ("ms_project", C.c_float), ("ms_contract", C.c_float),
+                ("ms_interp", C.c_float), ("ms_lens", C.c_float), ("ms_like", C.c_float), ("ms_total", C.c_float),
+                ("n_launches", C.c_longlong), ("proj_triples", C.c_longlong)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library; raises with a clear message if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("cosmomc_b200: %s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.cb200_last_error.restype = C.c_char_p
+    L.cb200_last_error.argtypes = [C.c_void_p]
+    L.cb200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    L.cb200_destroy.argtypes = [C.c_void_p]
+    L.cb200_destroy.restype = None
+    L.cb200_default_config.argtypes = [C.POINTER(Config)]
+    L.cb200_default_config.restype = None
+    L.cb200_get_info.argtypes = [C.c_void_p, C.POINTER(Info)]
+    L.cb200_get_lsamples.argtypes = [C.c_void_p, C.c_int, c_ip, c_ip]
+    L.cb200_set_templates.argtypes = [C.c_void_p, c_dp, c_dp, C.c_int]
+    L.cb200_make_q_grid.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, c_dp, c_dp, c_ip]
+    L.cb200_make_time_steps.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                        C.c_double, C.c_int, c_dp, c_dp, c_ip]
+    L.cb200_make_source_k.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, c_dp, c_ip]
+    L.cb200_grid_build.argtypes = [C.c_int, c_dp, C.c_int, c_dp, c_dp, c_ip, C.c_int, c_dp, c_ip]
+    L.cb200_get_bessel_table.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_dp]
+    L.cb200_upload_sources.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_dp, C.c_void_p, C.c_int]
+    L.cb200_powers.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip]
+    L.cb200_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_ip]
+    L.cb200_keep_transfers.argtypes = [C.c_void_p, C.c_int]
+    L.cb200_like_add_pliklite.argtypes = [C.c_void_p, c_ip, C.c_int, c_ip, c_ip, c_dp, C.c_int, c_dp, c_dp, C.c_int,
+                                          c_ip]
+    L.cb200_like_add_cmblikes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_ip, C.c_int, C.c_int, c_dp, c_dp,
+                                          c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_int, c_ip]
+    L.cb200_loglike_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_ip]
+    L.cb200_loglike_cls.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int, c_dp, c_dp, c_ip]
+    L.cb200_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing), C.c_int]
+    L.cb200_sync.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _pd(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def _pi(a):
+    return None if a is None else a.ctypes.data_as(c_ip)
+
+
+class CB200Error(RuntimeError):
+    pass
+
+
+def grid_build(ops, query=None, max_n=200000):
+    """Product-side grid builder (csrc/grids.hpp); no GPU needed."""
+    L = load()
+    o = _d(ops).reshape(-1, 5)
+    x = np.zeros(max_n)
+    dx = np.zeros(max_n)
+    n = C.c_int(0)
+    qv = _d(query if query is not None else [])
+    idx = np.zeros(max(1, len(qv)), dtype=np.int32)
+    rc = L.cb200_grid_build(len(o), _pd(o), max_n, _pd(x), _pd(dx), C.byref(n), len(qv), _pd(qv), _pi(idx))
+    if rc != 0:
+        raise CB200Error("cb200_grid_build failed (%d)" % rc)
+    return x[:n.value].copy(), dx[:n.value].copy(), idx[:len(qv)].copy()
+
+
+class Handle:
+    """Owns one cb200_handle (device tables, resident sources, likelihood data)."""
+
+    def __init__(self, **kw):
+        L = load()
+        self.L = L
+        cfg = Config()
+        L.cb200_default_config(C.byref(cfg))
+        for k, v in kw.items():
+            if not hasattr(cfg, k):
+                raise TypeError("unknown config field " + k)
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = L.cb200_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0 or not self.h:
+            raise CB200Error("cb200_create failed (no CUDA device or bad config); there is no CPU fallback")
+        self.info = Info()
+        L.cb200_get_info(self.h, C.byref(self.info))
+        self.n_like = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.cb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise CB200Error("%s failed (%d): %s" % (what, rc, self.L.cb200_last_error(self.h).decode()))
+
+    # ---- tables / grids
+    def lsamples(self, kind=0):
+        l = np.zeros(128, dtype=np.int32)
+        n = C.c_int(0)
+        self._check(self.L.cb200_get_lsamples(self.h, kind, _pi(l), C.byref(n)), "get_lsamples")
+        return l[:n.value].copy()
+
+    def set_templates(self, highl_unlensed, highl_lensed):
+        u = _d(highl_unlensed)
+        assert u.shape == (4, 8001)
+        le = _d(highl_lensed)
+        self._check(self.L.cb200_set_templates(self.h, _pd(u), _pd(le), le.shape[1]), "set_templates")
+
+    def q_grid(self, tau0, kind=0):
+        q = np.zeros(self.info.n_q_max * 4)
+        dq = np.zeros_like(q)
+        n = C.c_int(0)
+        self._check(self.L.cb200_make_q_grid(self.h, kind, tau0, len(q), _pd(q), _pd(dq), C.byref(n)), "make_q_grid")
+        return q[:n.value].copy(), dq[:n.value].copy()
+
+    def time_steps(self, tau0, taurst, taurend, reion_start, reion_complete, kind=0):
+        t = np.zeros(8192)
+        dt = np.zeros_like(t)
+        n = C.c_int(0)
+        self._check(self.L.cb200_make_time_steps(self.h, kind, tau0, taurst, taurend, reion_start, reion_complete,
+                                                 len(t), _pd(t), _pd(dt), C.byref(n)), "make_time_steps")
+        return t[:n.value].copy(), dt[:n.value].copy()
+
+    def source_k(self, tau0, taurst, kind=0):
+        k = np.zeros(8192)
+        n = C.c_int(0)
+        self._check(self.L.cb200_make_source_k(self.h, kind, tau0, taurst, len(k), _pd(k), C.byref(n)), "make_source_k")
+        return k[:n.value].copy()
+
+    def bessel_table(self, kind=0):
+        nl = self.info.n_lsamp if kind == 0 else self.info.n_lsamp_tensor
+        x = np.zeros(self.info.num_xx)
+        ajl = np.zeros((nl, self.info.num_xx))
+        ajlpr = np.zeros_like(ajl)
+        self._check(self.L.cb200_get_bessel_table(self.h, kind, _pd(x), _pd(ajl), _pd(ajlpr)), "get_bessel_table")
+        return x, ajl, ajlpr
+
+    # ---- calculator
+    def upload_sources(self, thermo, n_k, k, src, first=0, kind=0, src_device_ptr=None):
+        thermo = _d(thermo).reshape(-1, 5)
+        npts = len(thermo)
+        n_k = _i(n_k)
+        k = _d(k)
+        assert k.shape == (npts, self.info.n_k_max), (k.shape, self.info.n_k_max)
+        if src_device_ptr is not None:
+            ptr, isdev = C.c_void_p(src_device_ptr), 1
+        elif src is None:
+            ptr, isdev = None, 0
+        else:
+            src = _d(src)
+            assert src.shape == (npts, self.info.n_tau_max, 3, self.info.n_k_max), src.shape
+            self._keep = src
+            ptr, isdev = C.c_void_p(src.ctypes.data), 0
+        self._check(self.L.cb200_upload_sources(self.h, kind, first, npts, _pd(thermo), _pi(n_k), _pd(k), ptr, isdev),
+                    "upload_sources")
+
+    def powers(self, initpower, alens=None, aphiphi=None, first=0, want_cls=True, want_derived=True):
+        ip = _d(initpower).reshape(-1, 10)
+        npts = len(ip)
+        al = _d(alens) if alens is not None else None
+        ap = _d(aphiphi) if aphiphi is not None else None
+        lo = self.cfg.lmax_out + 1
+        cls = np.zeros((npts, 5, lo)) if want_cls else None
+        der = np.zeros((npts, 4)) if want_derived else None
+        st = np.zeros(npts, dtype=np.int32)
+        self._check(self.L.cb200_powers(self.h, first, npts, _pd(ip), _pd(al), _pd(ap), _pd(cls), _pd(der), _pi(st)),
+                    "powers")
+        return cls, der, st
+
+    def powers_resident(self, initpower, alens=None, aphiphi=None, first=0):
+        """Run the semi-slow step leaving every output on the device (no D2H)."""
+        ip = _d(initpower).reshape(-1, 10)
+        al = _d(alens) if alens is not None else None
+        ap = _d(aphiphi) if aphiphi is not None else None
+        self._check(self.L.cb200_powers(self.h, first, len(ip), _pd(ip), _pd(al), _pd(ap), None, None, None), "powers")
+
+    def keep_transfers(self, on=True):
+        self.L.cb200_keep_transfers(self.h, int(on))
+
+    def debug_fetch(self, what, point=0, max_n=None):
+        if max_n is None:
+            max_n = 3 * 96 * self.info.n_q_max + 6 * (self.info.max_l + 8)
+        out = np.zeros(max_n)
+        n = C.c_int(0)
+        self._check(self.L.cb200_debug_fetch(self.h, what, point, max_n, _pd(out), C.byref(n)), "debug_fetch")
+        return out[:n.value].copy()
+
+    # ---- likelihoods
+    def add_pliklite(self, nb, blmin, blmax, weights, invcov, x_data, cal_index=0):
+        nb = _i(nb)
+        blmin = _i(blmin)
+        blmax = _i(blmax)
+        w = _d(weights)
+        ic = _d(invcov)
+        xd = _d(x_data)
+        lid = C.c_int(-1)
+        self._check(self.L.cb200_like_add_pliklite(self.h, _pi(nb), len(blmin), _pi(blmin), _pi(blmax), _pd(w),
+                                                   len(w) - 1, _pd(ic), _pd(xd), cal_index, C.byref(lid)),
+                    "like_add_pliklite")
+        self.n_like += 1
+        return lid.value
+
+    def add_cmblikes(self, nmaps, nbins, cl_use_index, like_approx, W, offset, chat, invcov, noise=None,
+                     sqrt_fid=None, log_cal_prior=-1.0, cal_index=-1):
+        cui = _i(cl_use_index)
+        W = _d(W)
+        ncl = nmaps * (nmaps + 1) // 2
+        assert W.shape[0] == nbins and W.shape[1] == ncl and W.shape[2] == 5
+        lid = C.c_int(-1)
+        self._check(self.L.cb200_like_add_cmblikes(
+            self.h, nmaps, nbins, len(cui), _pi(cui), like_approx, W.shape[3] - 1, _pd(W), _pd(_d(offset)),
+            _pd(_d(noise)) if noise is not None else None, _pd(_d(chat)),
+            _pd(_d(sqrt_fid)) if sqrt_fid is not None else None, _pd(_d(invcov)), log_cal_prior, cal_index,
+            C.byref(lid)), "like_add_cmblikes")
+        self.n_like += 1
+        return lid.value
+
+    def loglike_batch(self, npts, nuisance, first=0):
+        nu = _d(nuisance).reshape(npts, -1)
+        ll = np.zeros((npts, self.n_like))
+        tot = np.zeros(npts)
+        st = np.zeros(npts, dtype=np.int32)
+        self._check(self.L.cb200_loglike_batch(self.h, first, npts, _pd(nu), nu.shape[1], _pd(ll), _pd(tot), _pi(st)),
+                    "loglike_batch")
+        return ll, tot, st
+
+    def loglike_cls(self, cls, nuisance):
+        cls = _d(cls)
+        npts = cls.shape[0]
+        assert cls.shape[1:] == (5, self.cfg.lmax_out + 1)
+        nu = _d(nuisance).reshape(npts, -1)
+        ll = np.zeros((npts, self.n_like))
+        tot = np.zeros(npts)
+        st = np.zeros(npts, dtype=np.int32)
+        self._check(self.L.cb200_loglike_cls(self.h, npts, _pd(cls), _pd(nu), nu.shape[1], _pd(ll), _pd(tot), _pi(st)),
+                    "loglike_cls")
+        return ll, tot, st
+
+    def timing(self, reset=True):
+        t = Timing()
+        self._check(self.L.cb200_get_timing(self.h, C.byref(t), int(reset)), "get_timing")
+        return {n: getattr(t, n) for n, _ in Timing._fields_}
+
+    def sync(self):
+        self._check(self.L.cb200_sync(self.h), "sync")

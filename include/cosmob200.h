@@ -1,0 +1,163 @@
+/* cosmob200 — C ABI of the B200-native theory + likelihood path behind CosmoMC's calculator /
+ * likelihood plug-in surface.  Plain pointers and sizes only; the library owns device memory, the caller
+ * owns every host buffer.  All arrays are C-contiguous, point-major.  One handle per host thread; there are
+ * no globals (the reference's CAMB state is global and thread-unsafe, camb/cmbmain.f90:7-8).
+ *
+ * Return value of every entry point: 0 = OK, >0 = soft error (CAMB-style: the caller maps it to `error`
+ * and rejects the point, source/Calculator_CAMB.f90:205-211), <0 = usage / CUDA error (cb200_last_error()).
+ * The library never exits or aborts the process.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef COSMOB200_H
+#define COSMOB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_VERSION 1
+#define CB200_LOGZERO 1e30 /* source/settings.f90:114 */
+
+typedef struct cb200_handle cb200_handle;
+
+/* Mirrors what CAMBCalc_InitCAMBParams derives from CosmoSettings (source/Calculator_CAMB.f90:729-836). */
+typedef struct cb200_config {
+  int device;                /* CUDA device ordinal */
+  int lmax_computed_cl;      /* CosmoSettings%lmax_computed_cl (batch3: 2500) */
+  int cmb_lensing;           /* CosmoSettings%CMB_Lensing */
+  int use_lensing_potential; /* CosmoSettings%use_lensing_potential */
+  int use_nonlinear_lensing; /* CosmoSettings%use_nonlinear_lensing */
+  int compute_tensors;       /* CosmoSettings%compute_tensors */
+  int lmax_tensor;           /* CosmoSettings%lmax_tensor (600) */
+  int accurate_bb;           /* CAMB_Calculator%accurate_BB */
+  double k_eta_max_scalar;   /* CAMB_Calculator%k_eta_max_scalar, <=0: default rule */
+  double accuracy_level;     /* AccuracyLevel (only 1 supported) */
+  int lmax_out;              /* CosmoSettings%lmax: highest l of the returned Cls (>= lmax_computed_cl ok) */
+  int highl_norm_first_call; /* 1: keep the reference's SAVEd highL_norm (Calculator_CAMB.f90:358,396);
+                                0 (default): renormalise the l>lmax_computed tail per point */
+  int max_points;            /* capacity of resident source storage (points) */
+  int chunk_points;          /* points processed per internal pass (work-buffer size); 0 = auto */
+  int n_tau_max, n_k_max, n_q_max; /* capacities per point; 0 = defaults 768 / 256 / 3072 */
+} cb200_config;
+
+typedef struct cb200_info {
+  int max_l, max_eta_k;       /* CAMB Max_l, Max_eta_k after InitCAMBParams */
+  int max_l_tensor, max_eta_k_tensor;
+  int n_lsamp, n_lsamp_tensor; /* l-sample counts (camb/modules.f90:791-950) */
+  int num_xx;                  /* Bessel abscissae (camb/bessels.f90:64-77) */
+  int lmax_lensed;             /* camb/lensing.f90:153-157 */
+  int lens_lmax;               /* lmax of the lensing sums (lmax_extrap, camb/lensing.f90:96-101) */
+  int lens_npoints;            /* theta samples actually integrated (camb/lensing.f90:163-177) */
+  int lens_jmax;               /* sampled l in the correlation sums (camb/lensing.f90:183-189) */
+  int n_tau_max, n_k_max, n_q_max, max_points, chunk_points;
+} cb200_info;
+
+void cb200_default_config(cb200_config* cfg);
+int cb200_create(const cb200_config* cfg, cb200_handle** out);
+void cb200_destroy(cb200_handle* h);
+const char* cb200_last_error(const cb200_handle* h);
+int cb200_get_info(const cb200_handle* h, cb200_info* info);
+/* l-sample set (replaces lSamp from initlval, camb/modules.f90:791). kind: 0 scalar, 1 tensor */
+int cb200_get_lsamples(const cb200_handle* h, int kind, int* l, int* n);
+
+/* Fiducial templates read by the reference at run time:
+ *   highl_unlensed [4][8001] TT,EE,TE,PP   camb/modules.f90:1162-1185 (HighLExtrapTemplate_lenspotentialCls.dat)
+ *   highl_lensed   [4][n_l]  TT,EE,BB,TE   source/Calculator_CAMB.f90:966-990 (HighL_lensedCls.dat, muK^2) */
+int cb200_set_templates(cb200_handle* h, const double* highl_unlensed, const double* highl_lensed, int n_l);
+
+/* ---- host grid helpers (bit-exact restatement of the reference's Ranges-based grids) -------------------
+ * kind: 0 scalar, 1 tensor.  Each returns the number of samples in *n (arrays sized max_n). */
+int cb200_make_q_grid(const cb200_handle* h, int kind, double tau0, int max_n, double* q, double* dq, int* n);
+    /* camb/cmbmain.f90:1221-1293 SetkValuesForInt */
+int cb200_make_time_steps(const cb200_handle* h, int kind, double tau0, double taurst, double taurend,
+                          double reion_tau_start, double reion_tau_complete, int max_n, double* tau,
+                          double* dtau, int* n); /* camb/modules.f90:2994-3027 SetTimeSteps */
+int cb200_make_source_k(const cb200_handle* h, int kind, double tau0, double taurst, int max_n, double* k,
+                        int* n);                 /* camb/cmbmain.f90:794-849 SetkValuesForSources */
+/* Generic grid builder for tests: ops[i] = {kind(0 spacing,1 count), start, end, step_or_count, is_log} */
+int cb200_grid_build(int nops, const double* ops, int max_n, double* x, double* dx, int* n, int n_query,
+                     const double* query, int* index_out);
+/* Bessel table read-back (camb/bessels.f90:50-120): x [num_xx], ajl/ajlpr [n_lsamp][num_xx] */
+int cb200_get_bessel_table(const cb200_handle* h, int kind, double* x, double* ajl, double* ajlpr);
+
+/* ---- calculator: slow step ------------------------------------------------------------------------------
+ * Replaces the part of CAMBCalc_GetNewTransferData after the source ODEs (source/Calculator_CAMB.f90:179-218
+ * -> camb/cmbmain.f90:238-263).  Inputs per point (what CAMB holds in globals after DoSourcek):
+ *   thermo [npts][5] = tau0, taurst, taurend, reion_tau_start (<=0: none), reion_tau_complete
+ *   n_k [npts], k [npts][n_k_max]                     Evolve_q%points
+ *   src  [npts][n_tau][n_src=3][n_k] packed per point with strides (n_tau_max, 3, n_k_max)  == Src(k,s,tau)
+ * The time-step grid and q grid are rebuilt inside from `thermo` exactly as the reference does.
+ * `first` = index of the first point slot to fill (resident storage), kind 0 scalar / 1 tensor.
+ * src_is_device != 0: `src` is a device pointer (used by the HBM-resident benchmark leg). */
+int cb200_upload_sources(cb200_handle* h, int kind, int first, int npts, const double* thermo, const int* n_k,
+                         const double* k, const double* src, int src_is_device);
+
+/* ---- calculator: semi-slow step -------------------------------------------------------------------------
+ * Replaces CAMBCalc_GetNewPowerData (source/Calculator_CAMB.f90:220-275): k-contraction, l-interpolation,
+ * lensing, unit conversion for points [first, first+npts).
+ *   initpower [npts][10] = As(absolute), ns, nrun, nrunrun, r, nt, ntrun, pivot_k, tensor_pivot_k,
+ *                          inflation_consistency      (CAMBCalc_SetCAMBInitPower, :839-877)
+ *   alens [npts] (ALens), aphiphi [npts] (Aphiphi; NULL = 1)
+ *   cls_out [npts][5][lmax_out+1]  TT,TE,EE,BB,PP in CosmoMC units (NULL: keep on device only)
+ *   derived_out [npts][4] rms deflection (arcmin), tensor ratio_02, ratio_BB, AT  (NULL ok)
+ *   status [npts] 0 ok / >0 rejected (NaN or negative TT/EE/BB, :239-256) */
+int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, const double* alens,
+                 const double* aphiphi, double* cls_out, double* derived_out, int* status);
+
+/* Intermediate read-backs for parity tests (device -> host copies of the last cb200_powers call):
+ *   what: 0 iCl [6][n_lsamp], 1 Cl_scalar [6][max_l+1], 2 Cl_lensed [4][max_l+1] (dimensionless),
+ *         3 transfers Delta [n_q][n_lsamp_pad][3] (only if cb200_keep_transfers(h,1)), 4 q, 5 dq, 6 tau, 7 dtau */
+int cb200_debug_fetch(cb200_handle* h, int what, int point, int max_n, double* out, int* n);
+int cb200_keep_transfers(cb200_handle* h, int on);
+
+/* ---- likelihoods ----------------------------------------------------------------------------------------
+ * Each cb200_like_add_* takes the dense arrays the reference's ReadIni resolves a .dataset to (parsing is
+ * host-side, cosmomc_b200/datasets.py or the Fortran ReadIni) and returns like_id = position in the list
+ * (TLikelihoodList order, source/GeneralTypes.f90:129-146). */
+
+/* native plik-lite (source/CMB.f90:208-329): nb[3] bins used for TT,TE,EE (first nb[i] bins of the common table),
+ * blmin/blmax absolute l per bin, weights [lmax_w+1] indexed by l and already x 2pi/(l(l+1)),
+ * invcov [nused][nused], x_data [nused].  nuisance: calPlanck. */
+int cb200_like_add_pliklite(cb200_handle* h, const int* nb, int nbins_tab, const int* blmin, const int* blmax,
+                            const double* weights, int lmax_w, const double* invcov, const double* x_data,
+                            int cal_index /* position of calPlanck in the nuisance vector, -1 none */,
+                            int* like_id);
+
+/* binned CMBLikes (source/CMBlikes.f90:1165-1256), dense form:
+ *   binned[bin][c] = sum_{X,l} W[bin][c][X][l] * Cl_X(l)/cal_X - offset[bin][c]   (X over TT,TE,EE,BB,PP;
+ *   cal_X = calPlanck^2 for CMB spectra, 1 for PP; window + linear-correction windows folded into W,
+ *   FiducialCorrection into offset; CMBlikes.f90:981-995)
+ *   then per bin: C(+noise) -> gaussian (C-Chat) or HL transform -> vecp[cl_use] -> bigX; chi2 = X^T invcov X
+ *   (+ (ln cal / prior)^2 when log_cal_prior>0).   like_approx: 1 HL, 2 gaussian.
+ *   W [nbins][ncl][5][lmax_w+1]; noise/chat/sqrt_fid [nbins][nmaps][nmaps] (noise, sqrt_fid may be NULL). */
+int cb200_like_add_cmblikes(cb200_handle* h, int nmaps, int nbins, int ncl_used, const int* cl_use_index,
+                            int like_approx, int lmax_w, const double* W, const double* offset,
+                            const double* noise, const double* chat, const double* sqrt_fid,
+                            const double* invcov, double log_cal_prior,
+                            int cal_index /* position of the calibration parameter in the nuisance vector, -1 none */,
+                            int* like_id);
+
+/* -lnL of every registered CMB likelihood for points [first, first+npts) using the Cls resident on the device
+ * from the last cb200_powers (replaces TheoryLike_LogLikeWithTheorySet, source/calclike.f90:357-389).
+ *   nuisance [npts][n_nuis_total] in registration order; loglikes [npts][n_like]; total [npts] */
+int cb200_loglike_batch(cb200_handle* h, int first, int npts, const double* nuisance, int n_nuis,
+                        double* loglikes, double* total, int* status);
+
+/* same for host-supplied Cls (cls [npts][5][lmax_out+1]); used by the ctypes shim / importance sampling */
+int cb200_loglike_cls(cb200_handle* h, int npts, const double* cls, const double* nuisance, int n_nuis,
+                      double* loglikes, double* total, int* status);
+
+/* ---- timing / counters (DebugMsgs timings of camb/cmbmain.f90:152-165,265-269, lensing.f90:516) ------- */
+typedef struct cb200_timing {
+  float ms_spline, ms_project, ms_contract, ms_interp, ms_lens, ms_like, ms_total;
+  long long n_launches;   /* kernels launched by this library since the last reset */
+  long long proj_triples; /* (q,l,tau) triples integrated by the last projection (if counting enabled) */
+} cb200_timing;
+int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset);
+int cb200_sync(cb200_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
