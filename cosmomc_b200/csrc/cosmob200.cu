@@ -104,6 +104,7 @@ struct cb200_handle {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[PH_COUNT];
   std::vector<cudaEvent_t> ev_pool;
   long long n_launches = 0;
+  cudaEvent_t t_a = nullptr, t_b = nullptr;
 
   cudaEvent_t get_event() {
     if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
@@ -934,6 +935,96 @@ int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset) {
     h->n_launches = 0;
     if (h->d_triples.p) h->d_triples.zero(h->stream);
   }
+  return 0;
+  CB_API_END(h)
+}
+
+// ---- FP64 peak micro-kernels -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double seed, double* out) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double seed, double* out) {
+  double c[8][2];
+  for (int i = 0; i < 8; i++) c[i][0] = c[i][1] = seed;
+  const double a = 0.5 + threadIdx.x * 1e-6, b = 1e-3;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) dmma_m8n8k4(c[k][0], c[k][1], a, b);
+  }
+  double s = 0;
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  if (s == 123.456) out[0] = s;
+}
+
+int cb200_measure_fp64_peaks(cb200_handle* h, double* dfma_tflops, double* dmma_tflops) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  cudaDeviceProp prop;
+  CB_CUDA(cudaGetDeviceProperties(&prop, h->cfg.device));
+  DevBuf<double> out;
+  out.alloc(1);
+  const int blocks = prop.multiProcessorCount * 8, iters = 20000;
+  cudaEvent_t a = h->get_event(), b = h->get_event();
+  float ms = 0;
+  double best_f = 0, best_m = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(a, h->stream);
+    dfma_peak_kernel<<<blocks, 256, 0, h->stream>>>(iters, 1.0, out.p);
+    cudaEventRecord(b, h->stream);
+    CB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&ms, a, b);
+    best_f = std::max(best_f, 2.0 * 8 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12);
+    cudaEventRecord(a, h->stream);
+    dmma_peak_kernel<<<blocks, 256, 0, h->stream>>>(iters / 4, 1.0, out.p);
+    cudaEventRecord(b, h->stream);
+    CB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&ms, a, b);
+    best_m = std::max(best_m, 2.0 * 256 * 8 * (iters / 4) * 8.0 * blocks / (ms * 1e-3) / 1e12);
+  }
+  h->ev_pool.push_back(a); h->ev_pool.push_back(b);
+  if (dfma_tflops) *dfma_tflops = best_f;
+  if (dmma_tflops) *dmma_tflops = best_m;
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_set_option(cb200_handle* h, const char* name, double value) {
+  if (!h || !name) return -1;
+  std::string n(name);
+  if (n == "count_triples") h->count_triples = value != 0;
+  else if (n == "keep_transfers") h->keep_transfers = value != 0;
+  else return fail(h, "set_option: unknown option " + n);
+  return 0;
+}
+
+int cb200_timer_start(cb200_handle* h) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  if (!h->t_a) { h->t_a = h->get_event(); h->t_b = h->get_event(); }
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  CB_CUDA(cudaEventRecord(h->t_a, h->stream));
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_timer_stop(cb200_handle* h, float* ms) {
+  if (!h || !h->t_a) return -1;
+  CB_API_BEGIN
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  CB_CUDA(cudaEventRecord(h->t_b, h->stream));
+  CB_CUDA(cudaEventSynchronize(h->t_b));
+  float x = 0;
+  CB_CUDA(cudaEventElapsedTime(&x, h->t_a, h->t_b));
+  if (ms) *ms = x;
   return 0;
   CB_API_END(h)
 }

@@ -23,7 +23,8 @@ EXPORTS = [
     "cb200_get_lsamples", "cb200_set_templates", "cb200_make_q_grid", "cb200_make_time_steps",
     "cb200_make_source_k", "cb200_grid_build", "cb200_get_bessel_table", "cb200_upload_sources", "cb200_powers",
     "cb200_debug_fetch", "cb200_keep_transfers", "cb200_like_add_pliklite", "cb200_like_add_cmblikes",
-    "cb200_loglike_batch", "cb200_loglike_cls", "cb200_get_timing", "cb200_sync",
+    "cb200_loglike_batch", "cb200_loglike_cls", "cb200_get_timing", "cb200_sync", "cb200_set_option",
+    "cb200_timer_start", "cb200_timer_stop", "cb200_measure_fp64_peaks",
 ]
 
 
@@ -89,6 +90,10 @@ def load():
     L.cb200_loglike_cls.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int, c_dp, c_dp, c_ip]
     L.cb200_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing), C.c_int]
     L.cb200_sync.argtypes = [C.c_void_p]
+    L.cb200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    L.cb200_timer_start.argtypes = [C.c_void_p]
+    L.cb200_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.cb200_measure_fp64_peaks.argtypes = [C.c_void_p, c_dp, c_dp]
     _lib = L
     return L
 
@@ -207,7 +212,7 @@ class Handle:
         return x, ajl, ajlpr
 
     # ---- calculator
-    def upload_sources(self, thermo, n_k, k, src, first=0, kind=0, src_device_ptr=None):
+    def upload_sources(self, thermo, n_k, k, src, first=0, kind=0, src_device_ptr=None, src_host_ptr=None):
         thermo = _d(thermo).reshape(-1, 5)
         npts = len(thermo)
         n_k = _i(n_k)
@@ -215,6 +220,8 @@ class Handle:
         assert k.shape == (npts, self.info.n_k_max), (k.shape, self.info.n_k_max)
         if src_device_ptr is not None:
             ptr, isdev = C.c_void_p(src_device_ptr), 1
+        elif src_host_ptr is not None:  # caller-owned (e.g. pinned) host buffer with the padded layout
+            ptr, isdev = C.c_void_p(src_host_ptr), 0
         elif src is None:
             ptr, isdev = None, 0
         else:
@@ -314,3 +321,20 @@ class Handle:
 
     def sync(self):
         self._check(self.L.cb200_sync(self.h), "sync")
+
+    def set_option(self, name, value):
+        self._check(self.L.cb200_set_option(self.h, name.encode(), float(value)), "set_option")
+
+    def timer_start(self):
+        self._check(self.L.cb200_timer_start(self.h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._check(self.L.cb200_timer_stop(self.h, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    def measure_fp64_peaks(self):
+        a = C.c_double(0)
+        b = C.c_double(0)
+        self._check(self.L.cb200_measure_fp64_peaks(self.h, C.byref(a), C.byref(b)), "measure_fp64_peaks")
+        return a.value, b.value

@@ -156,6 +156,14 @@ typedef struct cb200_timing {
 } cb200_timing;
 int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset);
 int cb200_sync(cb200_handle* h);
+/* options: "count_triples" (0/1), "keep_transfers" (0/1) */
+int cb200_set_option(cb200_handle* h, const char* name, double value);
+/* CUDA-event stopwatch on the library's stream (device-side timing of whole calls) */
+int cb200_timer_start(cb200_handle* h);
+int cb200_timer_stop(cb200_handle* h, float* ms);
+/* measured FP64 peaks of this GPU (TFLOP/s): vector DFMA and tensor-pipe DMMA micro-kernels; the driver-written
+ * MEASURED_PEAKS.json holds only HBM and bf16 numbers, so the FP64 roofline denominators are measured here. */
+int cb200_measure_fp64_peaks(cb200_handle* h, double* dfma_tflops, double* dmma_tflops);
 
 #ifdef __cplusplus
 }
