@@ -7,6 +7,7 @@
 #include "bessel.cuh"
 #include "dgemm.cuh"
 #include "project.cuh"
+#include "project2.cuh"
 #include "lens.cuh"
 #include "like.cuh"
 
@@ -33,6 +34,7 @@ struct KindSet {  // per perturbation type (0 scalar, 1 tensor): multipole set +
   DevBuf<int> d_ls;
   DevBuf<double> d_bx;
   DevBuf<double2> d_bes;
+  DevBuf<double2> d_bes3;  // [chunk][row][32] layout for the windowed projection
   DevBuf<int> d_llo;  // [max_l+1]
 };
 
@@ -92,7 +94,9 @@ struct cb200_handle {
   bool keep_transfers = false;
   int last_chunk_p0 = 0, last_chunk_np = 0;
   DevBuf<unsigned long long> d_triples;
-  bool count_triples = false;
+  bool count_triples = false, ring_stats = false;
+  int proj_kernel = 2;
+  DevBuf<unsigned long long> d_ring_stats;
   // resident outputs
   DevBuf<double> r_cl_lensed, r_cls_out, r_derived, r_icl, r_cl;
   DevBuf<int> r_status;
@@ -182,8 +186,11 @@ void build_kind(cb200_handle* h, int k, int max_l, double max_eta_k) {
   bessel_spline_kernel<<<((int)K.ls.size() + 31) / 32, 32, 0, h->stream>>>(K.num_xx, (int)K.ls.size(), PROJ_LP,
                                                                            K.d_bx.p, K.d_bes.p, scratch.p);
   CB_LAUNCH_CHECK();
+  K.d_bes3.alloc((size_t)PROJ_LW * K.num_xx * 32);
+  bessel_relayout_kernel<<<K.num_xx, PROJ_LP, 0, h->stream>>>(K.num_xx, K.d_bes.p, K.d_bes3.p);
+  CB_LAUNCH_CHECK();
   CB_CUDA(cudaStreamSynchronize(h->stream));
-  h->n_launches += 2;
+  h->n_launches += 3;
 }
 
 void build_lensing(cb200_handle* h) {
@@ -272,7 +279,7 @@ void ensure_store(cb200_handle* h, int k) {
 void ensure_work(cb200_handle* h) {
   if (h->w_icl.p) return;
   const int C = h->chunk, NT = h->cfg.n_tau_max, NK = h->cfg.n_k_max, NQ = h->cfg.n_q_max;
-  const int NQB = (NQ + PROJ_Q - 1) / PROJ_Q;
+  const int NQB = (NQ + PROJ_Q - 1) / PROJ_Q;  // v1 needs the larger partial buffer
   h->w_coef.alloc((size_t)C * 4 * NK);
   h->w_ddsrc.alloc((size_t)C * NT * 3 * NK);
   h->w_part.alloc((size_t)C * NQB * 6 * PROJ_LP);
@@ -293,6 +300,8 @@ void ensure_work(cb200_handle* h) {
   h->r_cl.alloc(P * 6 * h->LS);
   h->d_triples.alloc(1);
   h->d_triples.zero(h->stream);
+  h->d_ring_stats.alloc(4);
+  h->d_ring_stats.zero(h->stream);
 }
 
 }  // namespace
@@ -366,6 +375,9 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
     h->count_triples = ct && ct[0] == '1';
     CB_CUDA(cudaFuncSetAttribute(project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(project2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
+    const char* pk = std::getenv("CB200_PROJ_KERNEL");
+    if (pk && pk[0] == '1') h->proj_kernel = 1;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "cb200_create: %s\n", e.what());
     return -1;
@@ -588,28 +600,45 @@ int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, 
       CB_LAUNCH_CHECK();
       h->n_launches += 2;
     }
+    int q_per_block = PROJ_Q, nqb_total = NQB;
     {  // K1
       cb200_handle::Scope sc(h, PH_PROJECT);
-      ProjParams pp;
-      pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB = NQB; pp.tensors = 0;
-      pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes = K.d_bes.p;
-      pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
-      pp.delta = h->keep_transfers ? h->w_delta.p : nullptr;
-      pp.triples = h->count_triples ? h->d_triples.p : nullptr;
-      pp.bseg = K.bseg;
-      for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
-      constexpr size_t META = sizeof(ProjMeta) * PROJ_NS * PROJ_SLAB * PROJ_Q;
-      constexpr size_t RED = sizeof(double) * (PROJ_NS - 1) * PROJ_Q * 3 * PROJ_LP;
-      const size_t smem = std::max(META, RED) + sizeof(ProjQ) * PROJ_Q;
-      dim3 grid(nqb_used, np);
-      project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB><<<grid, 32 * PROJ_LW * PROJ_NS, smem, s>>>(pp);
+      if (h->proj_kernel == 1) {
+        ProjParams pp;
+        pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB = NQB; pp.tensors = 0;
+        pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes = K.d_bes.p;
+        pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
+        pp.delta = h->keep_transfers ? h->w_delta.p : nullptr;
+        pp.triples = h->count_triples ? h->d_triples.p : nullptr;
+        pp.bseg = K.bseg;
+        for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
+        constexpr size_t META = sizeof(ProjMeta) * PROJ_NS * PROJ_SLAB * PROJ_Q;
+        constexpr size_t RED = sizeof(double) * (PROJ_NS - 1) * PROJ_Q * 3 * PROJ_LP;
+        const size_t smem = std::max(META, RED) + sizeof(ProjQ) * PROJ_Q;
+        dim3 grid(nqb_used, np);
+        project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB><<<grid, 32 * PROJ_LW * PROJ_NS, smem, s>>>(pp);
+      } else {
+        q_per_block = W2_QC;
+        nqb_total = (S.NQ + W2_QC - 1) / W2_QC;
+        Proj2Params pp;
+        pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB2 = nqb_total; pp.tensors = 0;
+        pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes3 = K.d_bes3.p;
+        pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
+        pp.delta = h->keep_transfers ? h->w_delta.p : nullptr;
+        pp.triples = h->count_triples ? h->d_triples.p : nullptr;
+        pp.ring_stats = h->ring_stats ? h->d_ring_stats.p : nullptr;
+        pp.bseg = K.bseg;
+        for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
+        dim3 grid((nq_max + W2_QC - 1) / W2_QC, (nl + 31) / 32, np);
+        project2_kernel<<<grid, 32 * W2_NW, W2_SMEM, s>>>(pp);
+      }
       CB_LAUNCH_CHECK();
       h->n_launches += 1;
     }
     {  // K2
       cb200_handle::Scope sc(h, PH_CONTRACT);
       dim3 grid((6 * PROJ_LP + 127) / 128, np);
-      contract_reduce_kernel<<<grid, 128, 0, s>>>(np, p0, S.n_q.p, PROJ_Q, NQB, nl, K.d_ls.p, 0,
+      contract_reduce_kernel<<<grid, 128, 0, s>>>(np, p0, S.n_q.p, q_per_block, nqb_total, nl, K.d_ls.p, 0,
                                                  alens ? h->w_alens.p : nullptr, h->w_part.p, h->w_icl.p);
       CB_LAUNCH_CHECK();
       h->n_launches += 1;
@@ -927,6 +956,10 @@ int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset) {
   unsigned long long tr = 0;
   if (h->d_triples.p) CB_CUDA(cudaMemcpy(&tr, h->d_triples.p, sizeof(tr), cudaMemcpyDeviceToHost));
   t->proj_triples = (long long)tr;
+  unsigned long long rs[4] = {0, 0, 0, 0};
+  if (h->d_ring_stats.p) CB_CUDA(cudaMemcpy(rs, h->d_ring_stats.p, sizeof(rs), cudaMemcpyDeviceToHost));
+  t->ring_slabs = (long long)rs[0]; t->ring_direct = (long long)rs[1]; t->ring_rows = (long long)rs[2];
+  t->ring_pairs = (long long)rs[3];
   if (reset) {
     for (int p = 0; p < PH_COUNT; p++) {
       for (auto& e : h->ev[p]) { h->ev_pool.push_back(e.first); h->ev_pool.push_back(e.second); }
@@ -934,6 +967,7 @@ int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset) {
     }
     h->n_launches = 0;
     if (h->d_triples.p) h->d_triples.zero(h->stream);
+    if (h->d_ring_stats.p) h->d_ring_stats.zero(h->stream);
   }
   return 0;
   CB_API_END(h)
@@ -1001,6 +1035,8 @@ int cb200_set_option(cb200_handle* h, const char* name, double value) {
   std::string n(name);
   if (n == "count_triples") h->count_triples = value != 0;
   else if (n == "keep_transfers") h->keep_transfers = value != 0;
+  else if (n == "ring_stats") h->ring_stats = value != 0;
+  else if (n == "proj_kernel") h->proj_kernel = (value == 1) ? 1 : 2;
   else return fail(h, "set_option: unknown option " + n);
   return 0;
 }

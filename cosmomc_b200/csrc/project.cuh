@@ -269,7 +269,8 @@ __global__ void __launch_bounds__(32 * PROJ_LW * NS, 1) project_kernel(const Pro
   const int n_hi = s_nhi;
 
   // ---- sweep over conformal time ----
-  for (int n_base = 2; n_base <= n_hi; n_base += NS * SLAB) {
+  // starts at n = 1: IndexOf(TimeSteps, tmin) can truncate to 1; Source_q(1,:) = 0 there (cmbmain.f90:1380)
+  for (int n_base = 1; n_base <= n_hi; n_base += NS * SLAB) {
     __syncthreads();
     for (int idx = tid; idx < NS * SLAB * Q; idx += NTHR) {
       const int qq = idx % Q, r = idx / Q;
@@ -290,9 +291,12 @@ __global__ void __launch_bounds__(32 * PROJ_LW * NS, 1) project_kernel(const Pro
         const double* S = src + (size_t)(n - 1) * tau_stride;
         const double* D = dds + (size_t)(n - 1) * tau_stride;
         m.a = a; m.fac = fac; m.i0 = bi - 1;
-        m.s0 = interp_source(S, D, c) * dt;
-        m.s1 = interp_source(S + row_stride, D + row_stride, c) * dt;
-        m.s2 = interp_source(S + 2 * row_stride, D + 2 * row_stride, c) * dt;
+        m.s0 = m.s1 = m.s2 = 0;
+        if (n >= 2) {
+          m.s0 = interp_source(S, D, c) * dt;
+          m.s1 = interp_source(S + row_stride, D + row_stride, c) * dt;
+          m.s2 = interp_source(S + 2 * row_stride, D + 2 * row_stride, c) * dt;
+        }
       } else {
         m.a = 0; m.fac = 0; m.s0 = m.s1 = m.s2 = 0; m.i0 = 0;
       }

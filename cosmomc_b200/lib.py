@@ -47,7 +47,8 @@ class Info(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("ms_spline", C.c_float), ("ms_project", C.c_float), ("ms_contract", C.c_float),
                 ("ms_interp", C.c_float), ("ms_lens", C.c_float), ("ms_like", C.c_float), ("ms_total", C.c_float),
-                ("n_launches", C.c_longlong), ("proj_triples", C.c_longlong)]
+                ("n_launches", C.c_longlong), ("proj_triples", C.c_longlong), ("ring_slabs", C.c_longlong),
+                ("ring_direct", C.c_longlong), ("ring_rows", C.c_longlong), ("ring_pairs", C.c_longlong)]
 
 
 _lib = None

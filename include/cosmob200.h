@@ -153,10 +153,11 @@ typedef struct cb200_timing {
   float ms_spline, ms_project, ms_contract, ms_interp, ms_lens, ms_like, ms_total;
   long long n_launches;   /* kernels launched by this library since the last reset */
   long long proj_triples; /* (q,l,tau) triples integrated by the last projection (if counting enabled) */
+  long long ring_slabs, ring_direct, ring_rows, ring_pairs; /* windowed projection statistics (option "ring_stats") */
 } cb200_timing;
 int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset);
 int cb200_sync(cb200_handle* h);
-/* options: "count_triples" (0/1), "keep_transfers" (0/1) */
+/* options: "count_triples" (0/1), "keep_transfers" (0/1), "ring_stats" (0/1), "proj_kernel" (1 = L2-gather v1, 2 = windowed) */
 int cb200_set_option(cb200_handle* h, const char* name, double value);
 /* CUDA-event stopwatch on the library's stream (device-side timing of whole calls) */
 int cb200_timer_start(cb200_handle* h);

