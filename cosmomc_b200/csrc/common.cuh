@@ -74,6 +74,26 @@ __device__ __forceinline__ int lin_index_of(const LinSegs& g, double v) {
   return 1;
 }
 
+// same lookup, also returning the two grid values bracketing v, rebuilt arithmetically exactly as the grid was
+// materialised (lo + step*j without FMA; the last sample of a stretch is the next stretch's lo): no table load.
+__device__ __forceinline__ int lin_locate(const LinSegs& g, double v, double& x0, double& x1) {
+#pragma unroll 1
+  for (int r = 0; r < g.n; r++) {
+    const double lo = g.seg[r][0], hi = g.seg[r][1];
+    if (v < hi && v >= lo) {
+      const double step = g.seg[r][2];
+      const int first = (int)g.seg[r][3];
+      const int j = (int)(__ddiv_rn(__dsub_rn(v, lo), step));
+      const int nseg = ((r + 1 < g.n) ? (int)g.seg[r + 1][3] : g.npoints) - first;
+      x0 = __dadd_rn(lo, __dmul_rn(step, (double)j));
+      x1 = (j + 1 < nseg) ? __dadd_rn(lo, __dmul_rn(step, (double)(j + 1))) : hi;
+      return first + j;
+    }
+  }
+  x0 = x1 = g.highest;
+  return g.npoints;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -300,7 +300,7 @@ void ensure_work(cb200_handle* h) {
   h->r_cl.alloc(P * 6 * h->LS);
   h->d_triples.alloc(1);
   h->d_triples.zero(h->stream);
-  h->d_ring_stats.alloc(4);
+  h->d_ring_stats.alloc(16);
   h->d_ring_stats.zero(h->stream);
 }
 
@@ -375,7 +375,8 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
     h->count_triples = ct && ct[0] == '1';
     CB_CUDA(cudaFuncSetAttribute(project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CB_CUDA(cudaFuncSetAttribute(project2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
+    CB_CUDA(cudaFuncSetAttribute(project2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
+    CB_CUDA(cudaFuncSetAttribute(project2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
     const char* pk = std::getenv("CB200_PROJ_KERNEL");
     if (pk && pk[0] == '1') h->proj_kernel = 1;
   } catch (const std::exception& e) {
@@ -630,7 +631,8 @@ int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, 
         pp.bseg = K.bseg;
         for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
         dim3 grid((nq_max + W2_QC - 1) / W2_QC, (nl + 31) / 32, np);
-        project2_kernel<<<grid, 32 * W2_NW, W2_SMEM, s>>>(pp);
+        if (h->count_triples || h->ring_stats) project2_kernel<true><<<grid, 32 * W2_NW, W2_SMEM, s>>>(pp);
+        else project2_kernel<false><<<grid, 32 * W2_NW, W2_SMEM, s>>>(pp);
       }
       CB_LAUNCH_CHECK();
       h->n_launches += 1;
@@ -956,8 +958,9 @@ int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset) {
   unsigned long long tr = 0;
   if (h->d_triples.p) CB_CUDA(cudaMemcpy(&tr, h->d_triples.p, sizeof(tr), cudaMemcpyDeviceToHost));
   t->proj_triples = (long long)tr;
-  unsigned long long rs[4] = {0, 0, 0, 0};
+  unsigned long long rs[16] = {0};
   if (h->d_ring_stats.p) CB_CUDA(cudaMemcpy(rs, h->d_ring_stats.p, sizeof(rs), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 6; i++) t->phase_cycles[i] = (long long)rs[4 + i];
   t->ring_slabs = (long long)rs[0]; t->ring_direct = (long long)rs[1]; t->ring_rows = (long long)rs[2];
   t->ring_pairs = (long long)rs[3];
   if (reset) {

@@ -20,18 +20,38 @@
 
 namespace cb200 {
 
-constexpr int W2_NW = 8;                 // warps per CTA
-constexpr int W2_QW = 8;                 // wavenumbers per warp
-constexpr int W2_S = 4;                  // time samples per slab
+#ifndef CB200_W2_QW
+#define CB200_W2_QW 4
+#endif
+#ifndef CB200_W2_S
+#define CB200_W2_S 8
+#endif
+#ifndef CB200_W2_NW
+#define CB200_W2_NW 8
+#endif
+#ifndef CB200_W2_R
+#define CB200_W2_R 176
+#endif
+#ifndef CB200_W2_MINB
+#define CB200_W2_MINB 2
+#endif
+constexpr int W2_NW = CB200_W2_NW;       // warps per CTA
+constexpr int W2_QW = CB200_W2_QW;       // wavenumbers per warp
+constexpr int W2_S = CB200_W2_S;         // time samples per slab
 constexpr int W2_QC = W2_NW * W2_QW;     // wavenumbers per CTA
-constexpr int W2_R = 184;                // ring capacity in table rows
-static_assert(W2_QW * W2_S == 32, "one (q, tau) pair per lane");
+constexpr int W2_R = CB200_W2_R;         // ring capacity in table rows (+1 mirror row)
+constexpr int W2_NP = W2_QW * W2_S;      // (q, tau) pairs per warp per slab, one per lane
+static_assert(W2_NP <= 32, "at most one (q, tau) pair per lane");
 
+// Per-warp, per-slab metadata of the 32 (q, tau) pairs, structure-of-arrays so that the broadcast reads of the
+// inner loop are as narrow as possible: a warp-wide shared load costs one LSU wavefront per 4 bytes per lane
+// even when every lane reads the same address (ncu: 4 wavefronts per broadcast LDS.128), so bytes matter.
 struct __align__(16) ProjMeta2 {
-  double a, fac;
-  double s0, s1;
-  double s2;
-  int off0, off1;  // ring mode: element offsets (double2 units) of rows i0, i0+1 in the ring; direct mode: i0, -
+  double2 af[32];   // a = (x_{i+1}-x)/h ; fac = h^2 a / 6
+  double2 s01[32];  // k-interpolated sources x dtau (temperature, E)
+  double s2[32];    // lensing-potential source x dtau
+  int off[32];      // byte offset of node row i0 in the ring
+  int i0[32];       // table row (-1: pair not visited)
 };
 
 struct ProjQ2 {
@@ -66,12 +86,13 @@ __device__ __forceinline__ double interp_source2(const double* __restrict__ S, c
   return c.a0 * S[c.klo - 1] + c.b0 * S[c.klo] + (c.a03h * D[c.klo - 1] + c.b03h * D[c.klo]) * c.ho2o6;
 }
 
-__global__ void __launch_bounds__(32 * W2_NW, 2) project2_kernel(const Proj2Params p) {
-  constexpr int NW = W2_NW, QW = W2_QW, S = W2_S, QC = W2_QC, R = W2_R;
+template <bool COUNT>
+__global__ void __launch_bounds__(32 * W2_NW, CB200_W2_MINB) project2_kernel(const Proj2Params p) {
+  constexpr int NW = W2_NW, QW = W2_QW, S = W2_S, QC = W2_QC, R = W2_R, NP = W2_NP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* ring = reinterpret_cast<double2*>(smem_raw);                                  // [R][32]
-  ProjMeta2* meta = reinterpret_cast<ProjMeta2*>(smem_raw + sizeof(double2) * R * 32);   // [NW][32]
-  ProjQ2* qc = reinterpret_cast<ProjQ2*>(smem_raw + sizeof(double2) * R * 32 + sizeof(ProjMeta2) * NW * 32);
+  double2* ring = reinterpret_cast<double2*>(smem_raw);                                        // [R+1][32], slot R mirrors slot 0
+  ProjMeta2* meta = reinterpret_cast<ProjMeta2*>(smem_raw + sizeof(double2) * (R + 1) * 32);   // [NW]
+  ProjQ2* qc = reinterpret_cast<ProjQ2*>(smem_raw + sizeof(double2) * (R + 1) * 32 + sizeof(ProjMeta2) * NW);
   __shared__ int s_wmin[2][NW], s_wmax[2][NW], s_wn1[NW][QW], s_wn2[NW][QW];
   __shared__ int s_nlo, s_nhi, s_rlo, s_rhi;
 
@@ -190,45 +211,71 @@ __global__ void __launch_bounds__(32 * W2_NW, 2) project2_kernel(const Proj2Para
 #pragma unroll
   for (int qq = 0; qq < QW; qq++) acc[qq][0] = acc[qq][1] = acc[qq][2] = 0.0;
   unsigned long long my_triples = 0, st_slabs = 0, st_direct = 0, st_rows = 0, st_pairs = 0;
+  long long ck_pro = 0, ck_pre = 0, ck_bar = 0, ck_ring = 0, ck_cmp = 0, ck_fin = 0, ck_t0 = clock64(), ck_t;
+#define CK(var) do { if (COUNT) { ck_t = clock64(); var += ck_t - ck_t0; ck_t0 = ck_t; } } while (0)
 
   __syncthreads();
   const int n_lo = s_nlo, n_hi = s_nhi;
 
-  // ---- sweep over conformal time in slabs of S samples ----
-  ProjMeta2* wmeta = meta + warp * 32;
-  int par = 0;
-  for (int n_base = n_lo; n_base <= n_hi; n_base += S, par ^= 1) {
-    // (1) one (q, tau) pair per lane
-    int i0 = -1;
-    {
-      const int qq = lane / S, n = n_base + (lane % S);
-      const ProjQ2& c = wq[qq];
-      ProjMeta2 m;
-      m.a = 0; m.fac = 0; m.s0 = m.s1 = m.s2 = 0; m.off0 = -1; m.off1 = 0;
-      if (c.valid && n <= c.steps && n >= s_wn1[warp][qq] && n <= s_wn2[warp][qq]) {
-        const double t = tau[n - 1];
-        const double x = fabs(__dmul_rn(c.q, __dsub_rn(tau0, t)));
-        int bi = lin_index_of(p.bseg, x);
-        bi = min(bi, p.num_xx - 1);
-        const double x1 = p.bx[bi], x0 = p.bx[bi - 1];
-        double fac = __dsub_rn(x1, x0);
-        const double a = __ddiv_rn(__dsub_rn(x1, x), fac);
-        fac = __ddiv_rn(__dmul_rn(__dmul_rn(fac, fac), a), 6.0);
-        const double dt = dtau[n - 1];
-        const double* Sp = src + (size_t)(n - 1) * tau_stride;
-        const double* Dp = dds + (size_t)(n - 1) * tau_stride;
-        m.a = a; m.fac = fac;
-        if (n >= 2) {  // Source_q(1,:) is forced to zero (IntegrationVars_Init, cmbmain.f90:1380)
-          m.s0 = interp_source2(Sp, Dp, c) * dt;
-          m.s1 = interp_source2(Sp + row_stride, Dp + row_stride, c) * dt;
-          m.s2 = interp_source2(Sp + 2 * row_stride, Dp + 2 * row_stride, c) * dt;
-        }
-        i0 = bi - 1;
-        m.off0 = i0;
-        m.off1 = i0 % R;
+  // ---- sweep over conformal time in slabs of S samples, software-pipelined ----
+  // The per-pair metadata of slab k+1 (table row, spline weights, k-interpolated dtau-weighted sources) needs
+  // 14 global values per lane; they are fetched BEFORE the accumulation of slab k and consumed after it, so
+  // their L2/HBM latency hides behind the FP64 work instead of stalling every warp at the slab barrier.
+  ProjMeta2& wm = meta[warp];
+  const unsigned char* ring_bytes = reinterpret_cast<const unsigned char*>(ring) + lane * 16;
+  const int pq = lane % QW, pn = lane / QW;            // this lane's pair within a slab
+  const ProjQ2& pc = wq[pq];
+  const bool lane_has_pair = (lane < NP) && pc.valid;
+  const int pw1 = lane_has_pair ? max(s_wn1[warp][pq], 1) : 0x7fffffff;
+  const int pw2 = lane_has_pair ? min(s_wn2[warp][pq], pc.steps) : 0;
+
+  double f_tau = 0, f_dtau = 0, f_s[3][4];
+  bool f_valid = false;
+  auto prefetch = [&](int nb) {   // issue the loads of slab starting at nb
+    const int n = nb + pn;
+    f_valid = (n >= pw1) && (n <= pw2);
+    if (f_valid) {
+      f_tau = __ldg(tau + n - 1);
+      f_dtau = __ldg(dtau + n - 1);
+      const double* Sp = src + (size_t)(n - 1) * tau_stride + (pc.klo - 1);
+      const double* Dp = dds + (size_t)(n - 1) * tau_stride + (pc.klo - 1);
+#pragma unroll
+      for (int sI = 0; sI < 3; sI++) {
+        f_s[sI][0] = __ldg(Sp + sI * row_stride);
+        f_s[sI][1] = __ldg(Sp + sI * row_stride + 1);
+        f_s[sI][2] = __ldg(Dp + sI * row_stride);
+        f_s[sI][3] = __ldg(Dp + sI * row_stride + 1);
       }
-      wmeta[lane] = m;
     }
+  };
+  unsigned vmask = 0;
+  auto finish = [&](int nb, int par) {   // turn the prefetched values into the slab's metadata
+    const int n = nb + pn;
+    int i0 = -1;
+    double ma = 0, mfac = 0, ms0 = 0, ms1 = 0, ms2 = 0;
+    int moff = 0;
+    if (f_valid) {
+      const double x = fabs(__dmul_rn(pc.q, __dsub_rn(tau0, f_tau)));
+      double x0, x1;
+      int bi = lin_locate(p.bseg, x, x0, x1);
+      if (bi > p.num_xx - 1) { bi = p.num_xx - 1; x0 = p.bx[bi - 1]; x1 = p.bx[bi]; }
+      double fac = __dsub_rn(x1, x0);
+      ma = __ddiv_rn(__dsub_rn(x1, x), fac);
+      mfac = __ddiv_rn(__dmul_rn(__dmul_rn(fac, fac), ma), 6.0);
+      if (n >= 2) {  // Source_q(1,:) is forced to zero (IntegrationVars_Init, cmbmain.f90:1380)
+        ms0 = (pc.a0 * f_s[0][0] + pc.b0 * f_s[0][1] + (pc.a03h * f_s[0][2] + pc.b03h * f_s[0][3]) * pc.ho2o6) * f_dtau;
+        ms1 = (pc.a0 * f_s[1][0] + pc.b0 * f_s[1][1] + (pc.a03h * f_s[1][2] + pc.b03h * f_s[1][3]) * pc.ho2o6) * f_dtau;
+        ms2 = (pc.a0 * f_s[2][0] + pc.b0 * f_s[2][1] + (pc.a03h * f_s[2][2] + pc.b03h * f_s[2][3]) * pc.ho2o6) * f_dtau;
+      }
+      i0 = bi - 1;
+      moff = (i0 % R) * 512;
+    }
+    wm.af[lane] = make_double2(ma, mfac);
+    wm.s01[lane] = make_double2(ms0, ms1);
+    wm.s2[lane] = ms2;
+    wm.off[lane] = moff;
+    wm.i0[lane] = i0;
+    vmask = __ballot_sync(0xffffffffu, i0 >= 0);
     int rmin = (i0 >= 0) ? i0 : 0x7fffffff, rmax = (i0 >= 0) ? i0 + 1 : -1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -236,14 +283,23 @@ __global__ void __launch_bounds__(32 * W2_NW, 2) project2_kernel(const Proj2Para
       rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
     }
     if (lane == 0) { s_wmin[par][warp] = rmin; s_wmax[par][warp] = rmax; }
-    __syncthreads();  // previous slab fully consumed by every warp; window bounds visible
+  };
+
+  int par = 0;
+  if (n_lo <= n_hi) { prefetch(n_lo); finish(n_lo, 0); }
+  CK(ck_pro);
+  for (int n_base = n_lo; n_base <= n_hi; n_base += S, par ^= 1) {
+    const unsigned vm = vmask;                 // pairs of THIS slab (metadata already in wm)
+    if (n_base + S <= n_hi) prefetch(n_base + S);
+    CK(ck_pre);
+    __syncthreads();  // previous slab fully consumed by every warp; this slab's window bounds visible
+    CK(ck_bar);
     int lo = 0x7fffffff, hi = -1;
 #pragma unroll
     for (int w = 0; w < NW; w++) { lo = min(lo, s_wmin[par][w]); hi = max(hi, s_wmax[par][w]); }
-    if (hi < 0) continue;  // nothing active in this slab (CTA-uniform)
     const bool direct = (hi - lo + 1) > R;
-    if (!direct) {
-      // (2) slide the ring: fetch the rows of [lo, hi] that are not resident
+    if (hi >= 0 && !direct) {
+      // slide the ring: fetch the rows of [lo, hi] that are not resident
       int rlo = s_rlo, rhi = s_rhi;
       int la, lb, la2 = 1, lb2 = 0;
       if (rlo > rhi || hi < rlo - 1 || lo > rhi + 1) { la = lo; lb = hi; rlo = lo; rhi = hi; }
@@ -255,60 +311,93 @@ __global__ void __launch_bounds__(32 * W2_NW, 2) project2_kernel(const Proj2Para
         else { rhi = nhi; rlo = max(nlo, nhi - R + 1); }
       }
       for (int e = tid; e < (lb - la + 1) * 32; e += 32 * NW) {
-        const int row = la + (e >> 5), ll = e & 31;
-        cp_async16(&ring[(row % R) * 32 + ll], &bes[(size_t)row * 32 + ll]);
+        const int row = la + (e >> 5), ll = e & 31, slot = row % R;
+        cp_async16(&ring[slot * 32 + ll], &bes[(size_t)row * 32 + ll]);
+        if (slot == 0) cp_async16(&ring[R * 32 + ll], &bes[(size_t)row * 32 + ll]);
       }
       for (int e = tid; e < (lb2 - la2 + 1) * 32; e += 32 * NW) {
-        const int row = la2 + (e >> 5), ll = e & 31;
-        cp_async16(&ring[(row % R) * 32 + ll], &bes[(size_t)row * 32 + ll]);
+        const int row = la2 + (e >> 5), ll = e & 31, slot = row % R;
+        cp_async16(&ring[slot * 32 + ll], &bes[(size_t)row * 32 + ll]);
+        if (slot == 0) cp_async16(&ring[R * 32 + ll], &bes[(size_t)row * 32 + ll]);
       }
-      if (p.ring_stats && tid == 0) st_rows += max(0, lb - la + 1) + max(0, lb2 - la2 + 1);
+      if (COUNT && p.ring_stats && tid == 0) st_rows += max(0, lb - la + 1) + max(0, lb2 - la2 + 1);
       cp_async_wait_all();
       __syncthreads();
       if (tid == 0) { s_rlo = rlo; s_rhi = rhi; }
     }
-    if (p.ring_stats && tid == 0) { st_slabs++; st_direct += direct ? 1 : 0; }
+    if (COUNT && p.ring_stats && tid == 0 && hi >= 0) { st_slabs++; st_direct += direct ? 1 : 0; }
+    CK(ck_ring);
 
-    // (3) accumulate: 32 (q, tau) pairs per warp, lanes = multipoles
+    // accumulate: S groups (one time sample each) of QW wavenumbers; lanes = multipoles.  Within a group the
+    // QW accumulator sets are independent, so the FP64 chains of different pairs overlap.
+#ifndef CB200_W2_SKIP_COMPUTE
 #pragma unroll
-    for (int pr = 0; pr < 32; pr++) {
-      const int qq = pr / S, n = n_base + (pr % S);
-      const double2* m2 = reinterpret_cast<const double2*>(&wmeta[pr]);
-      const double2 s2i = m2[2];
-      const int r0 = __double2loint(s2i.y);
-      if (r0 < 0) continue;  // warp-uniform
-      const bool act = (n >= n1[qq]) && (n <= n2[qq]);
-      const double2 af = m2[0], s01 = m2[1];
-      double2 nd0, nd1;
-      if (!direct) {
-        const int sl0 = __double2hiint(s2i.y);
-        const int sl1 = (sl0 + 1 == R) ? 0 : sl0 + 1;
-        nd0 = ring[sl0 * 32 + lane];
-        nd1 = ring[sl1 * 32 + lane];
-      } else {
-        nd0 = __ldg(&bes[(size_t)r0 * 32 + lane]);
-        nd1 = __ldg(&bes[(size_t)(r0 + 1) * 32 + lane]);
+    for (int nn = 0; nn < S; nn++) {
+      if (((vm >> (nn * QW)) & ((1u << QW) - 1u)) == 0u) continue;  // warp-uniform
+      const int n = n_base + nn;
+      // stage 1: all loads of the group (metadata broadcasts + two table nodes per pair)
+      double2 AF[QW], N0[QW], N1[QW], S01[QW];
+      double S2[QW];
+#pragma unroll
+      for (int qq = 0; qq < QW; qq++) {
+        const int pr = nn * QW + qq;
+        AF[qq] = wm.af[pr];
+        S01[qq] = wm.s01[pr];
+        S2[qq] = wm.s2[pr];
+        if (!direct) {
+          const unsigned char* rp = ring_bytes + wm.off[pr];
+          N0[qq] = *reinterpret_cast<const double2*>(rp);
+          N1[qq] = *reinterpret_cast<const double2*>(rp + 512);
+        } else {
+          const int r0 = max(wm.i0[pr], 0);
+          N0[qq] = __ldg(&bes[(size_t)r0 * 32 + lane]);
+          N1[qq] = __ldg(&bes[(size_t)(r0 + 1) * 32 + lane]);
+        }
       }
-      const double a2 = af.x;
-      const double J = a2 * nd0.x + (1 - a2) * (nd1.x - ((a2 + 1) * nd0.y + (2 - a2) * nd1.y) * af.y);
-      if (act) {
-        acc[qq][0] += s01.x * J;
-        acc[qq][1] += s01.y * J;
-        acc[qq][2] += s2i.x * J;
-        if (p.triples) my_triples++;
+      // stage 2: cubic-spline value of j_l between the two nodes (cmbmain.f90:1515-1516), weights expanded so
+      // the dependent FP64 chain after the table loads is three deep:  J = (a j0 + b j1) + (g0 p0 + g1 p1)
+      double Jv[QW];
+#pragma unroll
+      for (int qq = 0; qq < QW; qq++) {
+        const double a2 = AF[qq].x, b2 = 1 - a2, t = -(b2 * AF[qq].y);
+        const double g0 = t * (a2 + 1), g1 = t * (2 - a2);
+        const double v = (a2 * N0[qq].x + b2 * N1[qq].x) + (g0 * N0[qq].y + g1 * N1[qq].y);
+        const bool act = (n >= n1[qq]) && (n <= n2[qq]);
+        Jv[qq] = act ? v : 0.0;
+        if (COUNT) {
+          if (p.triples && act) my_triples++;
+          if (p.ring_stats && lane == 0 && ((vm >> (nn * QW + qq)) & 1u)) st_pairs++;
+        }
       }
-      if (p.ring_stats && lane == 0) st_pairs++;
+      // stage 3: the three source accumulations
+#pragma unroll
+      for (int qq = 0; qq < QW; qq++) {
+        acc[qq][0] += S01[qq].x * Jv[qq];
+        acc[qq][1] += S01[qq].y * Jv[qq];
+        acc[qq][2] += S2[qq] * Jv[qq];
+      }
     }
+#endif
+    CK(ck_cmp);
+    // metadata of the next slab (its loads were issued before the barrier above)
+    __syncwarp();
+    if (n_base + S <= n_hi) finish(n_base + S, par ^ 1);
+    CK(ck_fin);
   }
 
-  if (p.triples) {
+  if (COUNT && p.triples) {
     unsigned long long t = my_triples;
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     if (lane == 0 && t) atomicAdd(p.triples, t);
   }
-  if (p.ring_stats) {
+  if (COUNT && p.ring_stats) {
     if (tid == 0) { atomicAdd(p.ring_stats + 0, st_slabs); atomicAdd(p.ring_stats + 1, st_direct); atomicAdd(p.ring_stats + 2, st_rows); }
     if (lane == 0) atomicAdd(p.ring_stats + 3, st_pairs);
+    if (lane == 0) {
+      atomicAdd(p.ring_stats + 4, (unsigned long long)ck_pro); atomicAdd(p.ring_stats + 5, (unsigned long long)ck_pre);
+      atomicAdd(p.ring_stats + 6, (unsigned long long)ck_bar); atomicAdd(p.ring_stats + 7, (unsigned long long)ck_ring);
+      atomicAdd(p.ring_stats + 8, (unsigned long long)ck_cmp); atomicAdd(p.ring_stats + 9, (unsigned long long)ck_fin);
+    }
   }
 
   // ---- Limber value of the lensing source and the partial k-contraction over this warp's wavenumbers ----
@@ -367,7 +456,7 @@ __global__ void __launch_bounds__(32 * W2_NW, 2) project2_kernel(const Proj2Para
   }
 }
 
-constexpr size_t W2_SMEM = sizeof(double2) * W2_R * 32 + sizeof(ProjMeta2) * W2_NW * 32 + sizeof(ProjQ2) * W2_QC;
+constexpr size_t W2_SMEM = sizeof(double2) * (W2_R + 1) * 32 + sizeof(ProjMeta2) * W2_NW + sizeof(ProjQ2) * W2_QC;
 
 // re-layout of the node table for the windowed kernel: [row][PROJ_LP] -> [chunk][row][32]
 __global__ void bessel_relayout_kernel(int num_xx, const double2* __restrict__ bes, double2* __restrict__ bes3) {

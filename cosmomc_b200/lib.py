@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcosmob200.so")
+LIB_PATH = os.environ.get("CB200_LIB", os.path.join(_HERE, "libcosmob200.so"))  # CB200_LIB: dev override for kernel-tuning builds
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
@@ -48,7 +48,8 @@ class Timing(C.Structure):
     _fields_ = [("ms_spline", C.c_float), ("ms_project", C.c_float), ("ms_contract", C.c_float),
                 ("ms_interp", C.c_float), ("ms_lens", C.c_float), ("ms_like", C.c_float), ("ms_total", C.c_float),
                 ("n_launches", C.c_longlong), ("proj_triples", C.c_longlong), ("ring_slabs", C.c_longlong),
-                ("ring_direct", C.c_longlong), ("ring_rows", C.c_longlong), ("ring_pairs", C.c_longlong)]
+                ("ring_direct", C.c_longlong), ("ring_rows", C.c_longlong), ("ring_pairs", C.c_longlong),
+                ("phase_cycles", C.c_longlong * 6)]
 
 
 _lib = None
@@ -318,7 +319,9 @@ class Handle:
     def timing(self, reset=True):
         t = Timing()
         self._check(self.L.cb200_get_timing(self.h, C.byref(t), int(reset)), "get_timing")
-        return {n: getattr(t, n) for n, _ in Timing._fields_}
+        d = {n: getattr(t, n) for n, _ in Timing._fields_}
+        d["phase_cycles"] = list(t.phase_cycles)
+        return d
 
     def sync(self):
         self._check(self.L.cb200_sync(self.h), "sync")

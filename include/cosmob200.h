@@ -154,6 +154,7 @@ typedef struct cb200_timing {
   long long n_launches;   /* kernels launched by this library since the last reset */
   long long proj_triples; /* (q,l,tau) triples integrated by the last projection (if counting enabled) */
   long long ring_slabs, ring_direct, ring_rows, ring_pairs; /* windowed projection statistics (option "ring_stats") */
+  long long phase_cycles[6]; /* per-warp clock64 sums: prologue, prefetch, barrier wait, ring fill, accumulate, metadata */
 } cb200_timing;
 int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset);
 int cb200_sync(cb200_handle* h);

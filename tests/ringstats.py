@@ -19,10 +19,13 @@ for pk in (2, 1):
     h.powers_resident(ip, al)
     t = h.timing(reset=True)
     print("kernel v%d:" % pk, {k_: (round(v, 3) if isinstance(v, float) else v) for k_, v in t.items()})
+    pc = np.array(t["phase_cycles"], dtype=float)
+    if pc.sum() > 0:
+        print("  PHASES prologue/prefetch/barrier/ring/accumulate/metadata %%: %s" % np.round(100 * pc / pc.sum(), 1))
     if pk == 2 and t["ring_slabs"]:
         print("  direct frac %.4f rows/slab %.1f pairs/row %.2f triples/pair %.1f" % (t["ring_direct"] / t["ring_slabs"], t["ring_rows"] / t["ring_slabs"], t["ring_pairs"] / max(1, t["ring_rows"]), t["proj_triples"] / max(1, t["ring_pairs"])))
     h.set_option("ring_stats", 0); h.set_option("count_triples", 0)
     h.powers_resident(ip, al); h.timing(reset=True)
     h.powers_resident(ip, al)
     t = h.timing(reset=True)
-    print("  clean timing: project %.2f ms for %d points -> %.1f us/point" % (t["ms_project"], n, 1e3 * t["ms_project"] / n))
+    print("  CLEAN timing: project %.2f ms for %d points -> %.1f us/point" % (t["ms_project"], n, 1e3 * t["ms_project"] / n))
