@@ -60,6 +60,7 @@ struct LinSegs {
   double highest;
   int npoints;
   double seg[8][4];
+  double inv_step[8];  // 1/step, for interpolation weights only (never for index arithmetic)
 };
 
 // 1-based index of the last sample <= v, with the reference's arithmetic (camb/utils.F90:81-111):
@@ -76,7 +77,7 @@ __device__ __forceinline__ int lin_index_of(const LinSegs& g, double v) {
 
 // same lookup, also returning the two grid values bracketing v, rebuilt arithmetically exactly as the grid was
 // materialised (lo + step*j without FMA; the last sample of a stretch is the next stretch's lo): no table load.
-__device__ __forceinline__ int lin_locate(const LinSegs& g, double v, double& x0, double& x1) {
+__device__ __forceinline__ int lin_locate(const LinSegs& g, double v, double& x0, double& x1, double& inv_h) {
 #pragma unroll 1
   for (int r = 0; r < g.n; r++) {
     const double lo = g.seg[r][0], hi = g.seg[r][1];
@@ -87,10 +88,12 @@ __device__ __forceinline__ int lin_locate(const LinSegs& g, double v, double& x0
       const int nseg = ((r + 1 < g.n) ? (int)g.seg[r + 1][3] : g.npoints) - first;
       x0 = __dadd_rn(lo, __dmul_rn(step, (double)j));
       x1 = (j + 1 < nseg) ? __dadd_rn(lo, __dmul_rn(step, (double)(j + 1))) : hi;
+      inv_h = g.inv_step[r];
       return first + j;
     }
   }
   x0 = x1 = g.highest;
+  inv_h = 0;
   return g.npoints;
 }
 

@@ -8,6 +8,7 @@
 #include "dgemm.cuh"
 #include "project.cuh"
 #include "project2.cuh"
+#include "project3.cuh"
 #include "lens.cuh"
 #include "like.cuh"
 
@@ -95,7 +96,7 @@ struct cb200_handle {
   int last_chunk_p0 = 0, last_chunk_np = 0;
   DevBuf<unsigned long long> d_triples;
   bool count_triples = false, ring_stats = false;
-  int proj_kernel = 2;
+  int proj_kernel = 3;
   DevBuf<unsigned long long> d_ring_stats;
   // resident outputs
   DevBuf<double> r_cl_lensed, r_cls_out, r_derived, r_icl, r_cl;
@@ -148,6 +149,7 @@ LinSegs to_linsegs(const SampleGrid& g) {
   for (int i = 0; i < s.n; i++) {
     if (g.seg[i].is_log) throw std::runtime_error("log segment in a grid that must be linear");
     s.seg[i][0] = g.seg[i].lo; s.seg[i][1] = g.seg[i].hi; s.seg[i][2] = g.seg[i].step; s.seg[i][3] = g.seg[i].first;
+    s.inv_step[i] = 1.0 / g.seg[i].step;
   }
   return s;
 }
@@ -377,8 +379,10 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CB_CUDA(cudaFuncSetAttribute(project2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
     CB_CUDA(cudaFuncSetAttribute(project2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
+    CB_CUDA(cudaFuncSetAttribute(project3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
+    CB_CUDA(cudaFuncSetAttribute(project3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
     const char* pk = std::getenv("CB200_PROJ_KERNEL");
-    if (pk && pk[0] == '1') h->proj_kernel = 1;
+    if (pk && pk[0] >= '1' && pk[0] <= '3') h->proj_kernel = pk[0] - '0';
   } catch (const std::exception& e) {
     std::fprintf(stderr, "cb200_create: %s\n", e.what());
     return -1;
@@ -618,6 +622,21 @@ int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, 
         const size_t smem = std::max(META, RED) + sizeof(ProjQ) * PROJ_Q;
         dim3 grid(nqb_used, np);
         project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB><<<grid, 32 * PROJ_LW * PROJ_NS, smem, s>>>(pp);
+      } else if (h->proj_kernel == 3) {
+        q_per_block = W3_QC;
+        nqb_total = (S.NQ + W3_QC - 1) / W3_QC;
+        Proj3Params pp;
+        pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB = nqb_total; pp.tensors = 0;
+        pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes3 = K.d_bes3.p;
+        pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
+        pp.delta = h->keep_transfers ? h->w_delta.p : nullptr;
+        pp.triples = h->count_triples ? h->d_triples.p : nullptr;
+        pp.ring_stats = h->ring_stats ? h->d_ring_stats.p : nullptr;
+        pp.bseg = K.bseg;
+        for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
+        dim3 grid((nq_max + W3_QC - 1) / W3_QC, (nl + 31) / 32, np);
+        if (h->count_triples || h->ring_stats) project3_kernel<true><<<grid, 32 * W3_NW, W3_SMEM, s>>>(pp);
+        else project3_kernel<false><<<grid, 32 * W3_NW, W3_SMEM, s>>>(pp);
       } else {
         q_per_block = W2_QC;
         nqb_total = (S.NQ + W2_QC - 1) / W2_QC;
@@ -1039,7 +1058,7 @@ int cb200_set_option(cb200_handle* h, const char* name, double value) {
   if (n == "count_triples") h->count_triples = value != 0;
   else if (n == "keep_transfers") h->keep_transfers = value != 0;
   else if (n == "ring_stats") h->ring_stats = value != 0;
-  else if (n == "proj_kernel") h->proj_kernel = (value == 1) ? 1 : 2;
+  else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 3) ? (int)value : 3;
   else return fail(h, "set_option: unknown option " + n);
   return 0;
 }

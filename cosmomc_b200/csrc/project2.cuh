@@ -256,12 +256,13 @@ __global__ void __launch_bounds__(32 * W2_NW, CB200_W2_MINB) project2_kernel(con
     int moff = 0;
     if (f_valid) {
       const double x = fabs(__dmul_rn(pc.q, __dsub_rn(tau0, f_tau)));
-      double x0, x1;
-      int bi = lin_locate(p.bseg, x, x0, x1);
-      if (bi > p.num_xx - 1) { bi = p.num_xx - 1; x0 = p.bx[bi - 1]; x1 = p.bx[bi]; }
-      double fac = __dsub_rn(x1, x0);
-      ma = __ddiv_rn(__dsub_rn(x1, x), fac);
-      mfac = __ddiv_rn(__dmul_rn(__dmul_rn(fac, fac), ma), 6.0);
+      double x0, x1, inv_h;
+      int bi = lin_locate(p.bseg, x, x0, x1, inv_h);
+      if (bi > p.num_xx - 1) { bi = p.num_xx - 1; x0 = p.bx[bi - 1]; x1 = p.bx[bi]; inv_h = 1.0 / (x1 - x0); }
+      // interpolation weights (values, not indices): reciprocal multiplies instead of the reference's divisions
+      const double fac = x1 - x0;
+      ma = (x1 - x) * inv_h;
+      mfac = fac * fac * ma * (1.0 / 6.0);
       if (n >= 2) {  // Source_q(1,:) is forced to zero (IntegrationVars_Init, cmbmain.f90:1380)
         ms0 = (pc.a0 * f_s[0][0] + pc.b0 * f_s[0][1] + (pc.a03h * f_s[0][2] + pc.b03h * f_s[0][3]) * pc.ho2o6) * f_dtau;
         ms1 = (pc.a0 * f_s[1][0] + pc.b0 * f_s[1][1] + (pc.a03h * f_s[1][2] + pc.b03h * f_s[1][3]) * pc.ho2o6) * f_dtau;

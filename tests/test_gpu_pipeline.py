@@ -138,7 +138,7 @@ def test_triple_count_matches_oracle(setup):
     """The instrumented unit-of-work count is an integer artefact: identical in both kernels."""
     h, orc = setup["h"], setup["orc"]
     want = sum(o["triples"] for o in orc)
-    for pk in (1, 2):
+    for pk in (1, 2, 3):
         h.set_option("proj_kernel", pk)
         h.set_option("count_triples", 1)
         h.timing(reset=True)
@@ -146,15 +146,16 @@ def test_triple_count_matches_oracle(setup):
         t = h.timing()
         h.set_option("count_triples", 0)
         assert t["proj_triples"] == want, (pk, t["proj_triples"], want)
-    h.set_option("proj_kernel", 2)
+    h.set_option("proj_kernel", 3)
 
 
-def test_l2_gather_kernel_agrees(setup):
-    """The first-generation projection kernel (direct L2 gathers) stays available as a cross-check."""
+@pytest.mark.parametrize("pk", [1, 2])
+def test_earlier_projection_kernels_agree(setup, pk):
+    """The earlier projection kernels (1: direct L2 gathers, 2: windowed, warp-per-pair) stay as cross-checks."""
     h, orc = setup["h"], setup["orc"]
-    h.set_option("proj_kernel", 1)
+    h.set_option("proj_kernel", pk)
     cls, derived, status = h.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
-    h.set_option("proj_kernel", 2)
+    h.set_option("proj_kernel", 3)
     for i in range(NPTS):
         o = orc[i]["cls_out"]
         for X in (0, 2, 4):
