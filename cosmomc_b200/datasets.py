@@ -1,0 +1,347 @@
+"""Host-side data preparation: CosmoMC .ini / .dataset / .paramnames readers and the resolution of a binned
+`CMBlikes` data set into the dense arrays the C ABI takes (cb200_like_add_cmblikes).
+
+Mirrors the reference's file handling for this path so that the same files configure the B200 likelihoods:
+  * ini dialect: source/IniObjects.f90:466-473 (DEFAULT(file) lower priority, INCLUDE(file)), key = value, '#' comments,
+    relative file names resolved against the ini file's directory (ReadRelativeFileName)
+  * .paramnames: source/ObjectParamNames.f90:82-86  ("name  latex  #comment", trailing '*' = derived)
+  * CMBlikes data set: source/CMBlikes.f90:371-859 (CMBLikes_ReadIni, ReadClArr, ReadBinWindows, ReadCovmat)
+The numerical evaluation is NOT here (it runs on the GPU); this module only builds arrays at set-up time.
+"""
+import os
+import re
+
+import numpy as np
+
+FIELDS = ["T", "E", "B", "P"]
+# theory spectrum slot of the device Cls array [TT, TE, EE, BB, PP] for a pair of theory fields (sorted)
+SPEC_SLOT = {(0, 0): 0, (0, 1): 1, (1, 1): 2, (2, 2): 3, (3, 3): 4}
+
+
+class IniFile:
+    def __init__(self, path=None):
+        self.params = {}
+        self.order = []
+        self.dir = "."
+        if path is not None:
+            self.dir = os.path.dirname(os.path.abspath(path))
+            self._read(path, override=True)
+
+    def _read(self, path, override):
+        defaults = []
+        with open(path) as f:
+            for raw in f:
+                line = raw.strip()
+                if not line or line.startswith("#") or line.startswith(";"):
+                    continue
+                m = re.match(r"^(DEFAULT|INCLUDE)\((.*)\)\s*$", line)
+                if m:
+                    fn = m.group(2).strip()
+                    if not os.path.isabs(fn):
+                        fn = os.path.join(os.path.dirname(os.path.abspath(path)), fn)
+                    if m.group(1) == "INCLUDE":
+                        self._read(fn, override=True)
+                    else:
+                        defaults.append(fn)
+                    continue
+                if "=" not in line:
+                    continue
+                k, v = line.split("=", 1)
+                k = k.strip()
+                v = v.split("#")[0].strip() if not v.strip().startswith("#") else ""
+                if override or k not in self.params:
+                    if k not in self.params:
+                        self.order.append(k)
+                    self.params[k] = v
+        for fn in defaults:  # DEFAULT files never override what is already set
+            self._read(fn, override=False)
+
+    def has(self, key):
+        return key in self.params and self.params[key] != ""
+
+    def string(self, key, default=None):
+        if self.has(key):
+            return self.params[key]
+        if default is None:
+            raise KeyError("ini key not found: " + key)
+        return default
+
+    def int(self, key, default=None):
+        return int(self.string(key, None if default is None else str(default)))
+
+    def float(self, key, default=None):
+        return float(self.string(key, None if default is None else str(default)))
+
+    def bool(self, key, default=False):
+        v = self.string(key, "T" if default else "F").strip().upper()
+        return v in ("T", "TRUE", ".TRUE.", "1", "YES")
+
+    def split(self, key, default=None):
+        if self.has(key):
+            return self.params[key].split()
+        if default is None:
+            raise KeyError("ini key not found: " + key)
+        return list(default)
+
+    def relative_file(self, key):
+        fn = self.string(key)
+        fn = fn.replace("%DATASETDIR%", os.environ.get("DATASETDIR", self.dir + os.sep))
+        return fn if os.path.isabs(fn) else os.path.join(self.dir, fn)
+
+
+def read_paramnames(path):
+    """-> list of (name, latex, is_derived)"""
+    out = []
+    with open(path) as f:
+        for raw in f:
+            line = raw.split("#")[0].strip()
+            if not line:
+                continue
+            parts = line.split(None, 1)
+            name = parts[0]
+            derived = name.endswith("*")
+            out.append((name.rstrip("*"), parts[1].strip() if len(parts) > 1 else "", derived))
+    return out
+
+
+def _top_comment(path):
+    last = None
+    with open(path) as f:
+        for line in f:
+            s = line.strip()
+            if s.startswith("#"):
+                last = s[1:].strip()
+            elif s:
+                break
+    return last
+
+
+class CMBLikesPlan:
+    """Dense form of a binned CMBlikes data set (gaussian or HL), ready for cb200_like_add_cmblikes."""
+
+    def __init__(self, dataset_path, overrides=None):
+        ini = IniFile(dataset_path)
+        if overrides:
+            ini.params.update(overrides)
+        self.name = os.path.basename(dataset_path)
+        self._read(ini)
+
+    # -- naming helpers (CMBlikes.f90:196-330)
+    def _pair_to_maps(self, s):
+        if len(s) == 2 and not self.has_map_names:
+            return self.map_names.index(s[0]), self.map_names.index(s[1])
+        if "x" not in s:
+            raise ValueError("CMBlikes: invalid spectrum name " + s)
+        a, b = s.split("x", 1)
+        return self.map_names.index(a), self.map_names.index(b)
+
+    def _pair_to_used(self, index, s):
+        i1, i2 = self._pair_to_maps(s)
+        i1, i2 = index[i1], index[i2]
+        return (i2, i1) if i2 > i1 else (i1, i2)
+
+    def _element_index(self, i1, i2):
+        if i1 < 0 or i2 < 0:
+            return -1
+        return i1 * (i1 + 1) // 2 + i2  # lower-triangle row-major, i1 >= i2 (MatrixToElements order)
+
+    def _used_name(self, i, j):
+        a, b = self.used_map_order[i], self.used_map_order[j]
+        return a + "x" + b if self.has_map_names else a + b
+
+    def _cols_from_order(self, names):
+        cols = -np.ones(self.ncl, dtype=int)
+        ix = 0
+        for i in range(self.nmaps):
+            for j in range(i + 1):
+                nm = self._used_name(i, j)
+                if nm not in names and i != j:
+                    nm = self._used_name(j, i)
+                if nm in names:
+                    cols[ix] = names.index(nm)
+                ix += 1
+        return cols
+
+    def _read_cl_arr(self, ini, stem):
+        fn = ini.relative_file(stem + "_file")
+        order = ini.string(stem + "_order", "")
+        names = ("L " + order).split() if order else (_top_comment(fn) or "").split()
+        if not names:
+            raise ValueError("no column order for " + fn)
+        cols = self._cols_from_order(names)
+        data = np.loadtxt(fn)
+        cl = np.zeros((self.ncl, self.nbins_used))
+        Ls = data[:, 0].astype(int) - (1 if self.binned else 0)
+        for r, L in enumerate(Ls):
+            if self.bin_min <= L <= self.bin_max:
+                for ix in range(self.ncl):
+                    if cols[ix] != -1:
+                        cl[ix, L - self.bin_min] = data[r, cols[ix]]
+        if Ls[-1] < self.bin_max:
+            raise ValueError("C_l file does not reach the last used bin: " + fn)
+        return cl
+
+    def _read_windows(self, ini, stem):
+        in_cl = ini.split(stem + "_in_order")
+        out_cl = ini.split(stem + "_out_order", in_cl)
+        cols_in = [self._pair_to_used(self.map_required_index, s) for s in in_cl]
+        cols_out = [self._element_index(*self._pair_to_used(self.map_used_index, s)) for s in out_cl]
+        if len(cols_in) != len(cols_out):
+            raise ValueError("_in_order and _out_order differ in length")
+        nL = self.pcl_lmax - self.pcl_lmin + 1
+        W = np.zeros((len(cols_in), self.nbins_used, nL))
+        pattern = ini.relative_file(stem + "_files")
+        for b in range(self.nbins_used):
+            win = np.loadtxt(pattern.replace("%u", str(b + 1 + self.bin_min)))
+            for row in win:
+                L = int(row[0])
+                if self.pcl_lmin <= L <= self.pcl_lmax:
+                    W[:, b, L - self.pcl_lmin] = row[1:1 + len(cols_in)]
+        return cols_in, cols_out, W
+
+    def _read(self, ini):
+        self.map_names = ini.split("map_names", [])
+        self.has_map_names = len(self.map_names) > 0
+        if self.has_map_names:
+            mf = ini.split("map_fields")
+            self.map_fields = [FIELDS.index(f) for f in mf]
+        else:
+            self.map_names = list(FIELDS)
+            self.map_fields = list(range(4))
+        fields_use = ini.split("fields_use", [])
+        if fields_use:
+            use_field = [FIELDS[i] in fields_use for i in range(4)]
+        else:
+            if not self.has_map_names:
+                raise ValueError("CMBlikes: need fields_use or map_names")
+            use_field = [True] * 4
+        maps_use = ini.split("maps_use", [])
+        if maps_use:
+            self.use_map = [m in maps_use for m in self.map_names]
+        else:
+            self.use_map = [use_field[self.map_fields[i]] for i in range(len(self.map_names))]
+        self.require_map = list(self.use_map)
+        req = ini.split("maps_required" if self.has_map_names else "fields_required", [])
+        for m in req:
+            self.require_map[self.map_names.index(m)] = True
+        self.like_approx = {"gaussian": 2, "HL": 1}[ini.string("like_approx", "gaussian")]
+        self.nmaps = int(np.count_nonzero(self.use_map))
+        self.nmaps_required = int(np.count_nonzero(self.require_map))
+        self.required_order = [i for i, r in enumerate(self.require_map) if r]
+        self.map_required_index = -np.ones(len(self.map_names), dtype=int)
+        for k, i in enumerate(self.required_order):
+            self.map_required_index[i] = k
+        self.map_used_index = -np.ones(len(self.map_names), dtype=int)
+        self.used_map_order = []
+        for i, nm in enumerate(self.map_names):
+            if self.use_map[i]:
+                self.map_used_index[i] = len(self.used_map_order)
+                self.used_map_order.append(nm)
+        self.ncl = self.nmaps * (self.nmaps + 1) // 2
+        self.pcl_lmax = ini.int("cl_lmax")
+        self.pcl_lmin = ini.int("cl_lmin")
+        self.binned = ini.bool("binned", True)
+        if not self.binned:
+            raise NotImplementedError("only binned CMBlikes data sets are supported")
+        self.nbins = ini.int("nbins")
+        self.bin_min = ini.int("use_min", 1) - 1
+        self.bin_max = ini.int("use_max", self.nbins) - 1
+        self.nbins_used = self.bin_max - self.bin_min + 1
+        win_in, win_out, winW = self._read_windows(ini, "bin_window")
+        self.bandpowers = self._read_cl_arr(ini, "cl_hat")
+        cl_fid = self._read_cl_arr(ini, "cl_fiducial") if self.like_approx == 1 else None
+        includes_noise = ini.bool("cl_hat_includes_noise", False)
+        cl_noise = None
+        if self.like_approx != 2 or includes_noise:
+            cl_noise = self._read_cl_arr(ini, "cl_noise")
+            if not includes_noise:
+                self.bandpowers = self.bandpowers + cl_noise
+            elif self.like_approx == 2:
+                self.bandpowers = self.bandpowers - cl_noise
+        if cl_fid is not None and not ini.bool("cl_fiducial_includes_noise", False):
+            cl_fid = cl_fid + cl_noise
+
+        def to_matrix(x):
+            M = np.zeros((self.nmaps, self.nmaps))
+            ix = 0
+            for i in range(self.nmaps):
+                for j in range(i + 1):
+                    M[i, j] = M[j, i] = x[ix]
+                    ix += 1
+            return M
+
+        def sqrtm(M):
+            w, V = np.linalg.eigh(M)
+            return (V * np.sqrt(w)) @ V.T
+
+        nb = self.nbins_used
+        self.chat = np.array([to_matrix(self.bandpowers[:, b]) for b in range(nb)])
+        self.noise = np.array([to_matrix(cl_noise[:, b]) for b in range(nb)]) if cl_noise is not None and self.like_approx != 2 else None
+        self.sqrt_fid = np.array([sqrtm(to_matrix(cl_fid[:, b])) for b in range(nb)]) if cl_fid is not None else None
+
+        # covariance (ReadCovmat, CMBlikes.f90:752-859)
+        covmat_cl = ini.split("covmat_cl")
+        cl_in_index = [self._element_index(*self._pair_to_used(self.map_used_index, s)) for s in covmat_cl]
+        used = [(k, ix) for k, ix in enumerate(cl_in_index) if ix >= 0]
+        self.ncl_used = len(used)
+        self.cl_use_index = np.array([ix for _, ix in used], dtype=np.int32)
+        cov_cl_used = np.array([k for k, _ in used], dtype=int)
+        full_cov = np.loadtxt(ini.relative_file("covmat_fiducial"))
+        scale = ini.float("covmat_scale", 1.0)
+        num_in = len(cl_in_index)
+        n = nb * self.ncl_used
+        cov = np.zeros((n, n))
+        for bx in range(nb):
+            for by in range(nb):
+                cov[bx * self.ncl_used:(bx + 1) * self.ncl_used, by * self.ncl_used:(by + 1) * self.ncl_used] = \
+                    scale * full_cov[np.ix_((bx + self.bin_min) * num_in + cov_cl_used, (by + self.bin_min) * num_in + cov_cl_used)]
+        self.cov = cov
+        inv = np.linalg.inv(cov)
+        self.invcov = 0.5 * (inv + inv.T)
+
+        # windows -> dense W[bin][cl][spec][l] on the device Cls layout [TT,TE,EE,BB,PP], l = 0..pcl_lmax
+        self.lmax_w = self.pcl_lmax
+        W = np.zeros((nb, self.ncl, 5, self.lmax_w + 1))
+        offset = np.zeros((nb, self.ncl))
+
+        def add(cols_in, cols_out, Wt):
+            for k, ((i, j), out) in enumerate(zip(cols_in, cols_out)):
+                if out < 0:
+                    continue
+                f = tuple(sorted((self.map_fields[self.required_order[i]], self.map_fields[self.required_order[j]])))
+                if f not in SPEC_SLOT:
+                    continue  # spectrum the theory never allocates (e.g. TB): contributes zero, CMBlikes.f90:1318
+                W[:, out, SPEC_SLOT[f], self.pcl_lmin:self.pcl_lmax + 1] += Wt[k]
+
+        add(win_in, win_out, winW)
+        if ini.has("linear_correction_fiducial_file"):
+            fid_corr = self._read_cl_arr(ini, "linear_correction_fiducial")  # [ncl][nbins]
+            cin, cout, cW = self._read_windows(ini, "linear_correction_bin_window")
+            add(cin, cout, cW)
+            offset += fid_corr.T
+        self.W, self.offset = W, offset
+
+        # calibration / nuisance parameters (CMBlikes.f90:560-590)
+        self.nuisance_names = []
+        self.calibration_param = None
+        if ini.has("nuisance_params"):
+            self.nuisance_names = [n for n, _, _ in read_paramnames(ini.relative_file("nuisance_params"))]
+            if ini.has("calibration_paramname"):
+                self.calibration_param = ini.string("calibration_paramname")
+        elif ini.has("calibration_param"):
+            self.nuisance_names = [n for n, _, _ in read_paramnames(ini.relative_file("calibration_param"))]
+            self.calibration_param = self.nuisance_names[0]
+        self.log_cal_prior = ini.float("log_calibration_prior", -1.0) if self.calibration_param else -1.0
+        if ini.float("aberration_coeff", 0.0) != 0.0:
+            raise NotImplementedError("aberration_coeff != 0 is not folded into the dense windows yet")
+
+    def register(self, handle, cal_index):
+        return handle.add_cmblikes(self.nmaps, self.nbins_used, self.cl_use_index, self.like_approx, self.W, self.offset,
+                                   self.chat, self.invcov, noise=self.noise, sqrt_fid=self.sqrt_fid,
+                                   log_cal_prior=self.log_cal_prior, cal_index=cal_index)
+
+    def binned_theory(self, cls, cal=1.0):
+        """numpy evaluation of the dense form (for host-side checks): cls [5][>=lmax_w+1]."""
+        c = np.array(cls[:, :self.lmax_w + 1], dtype=float)
+        c[:4] = c[:4] / cal ** 2
+        return np.einsum("bcxl,xl->bc", self.W, c) - self.offset

@@ -1,0 +1,203 @@
+    !Calculator_B200: CosmoMC calculator plug-in that keeps CAMB for the Boltzmann source ODEs and hands everything
+    !after them (source spline, line-of-sight projection, k-contraction, l-interpolation, lensing, unit conversion)
+    !to the B200 library through the ISO_C_BINDING interfaces below (include/cosmob200.h).
+    !
+    !Drop-in pattern: same as source/Calculator_PICO.f90:18-27 (extend CAMB_Calculator, override the two slow-step
+    !procedures), selected with  cosmology_calculator = B200  by the branch shown in INTEGRATION.md
+    !(source/CosmologyConfig.f90:40-52).
+    !
+    !NOT compiled in this repository's CI: neither the build container nor the GPU box has a Fortran compiler
+    !(SURVEY section 0).  It is written against the reference's module interfaces as they stand at
+    !source/Calculator_CAMB.f90:179-275 and camb/cmbmain.f90:90-121,198-263.
+
+    module Calculator_B200
+    use, intrinsic :: iso_c_binding
+    use CosmologyTypes
+    use CosmoTheory
+    use CAMB, only : CAMB_GetTransfers, CAMBParams, CAMB_SetDefParams
+    use Calculator_CAMB
+    use settings
+    implicit none
+    private
+
+    !-- mirror of cb200_config (include/cosmob200.h)
+    type, bind(C) :: cb200_config
+        integer(c_int) :: device, lmax_computed_cl, cmb_lensing, use_lensing_potential, use_nonlinear_lensing
+        integer(c_int) :: compute_tensors, lmax_tensor, accurate_bb
+        real(c_double) :: k_eta_max_scalar, accuracy_level
+        integer(c_int) :: lmax_out, highl_norm_first_call, max_points, chunk_points, n_tau_max, n_k_max, n_q_max
+    end type cb200_config
+
+    interface
+    subroutine cb200_default_config(cfg) bind(C, name='cb200_default_config')
+    import :: cb200_config
+    type(cb200_config), intent(out) :: cfg
+    end subroutine
+    integer(c_int) function cb200_create(cfg, h) bind(C, name='cb200_create')
+    import :: cb200_config, c_ptr, c_int
+    type(cb200_config), intent(in) :: cfg
+    type(c_ptr), intent(out) :: h
+    end function
+    subroutine cb200_destroy(h) bind(C, name='cb200_destroy')
+    import :: c_ptr
+    type(c_ptr), value :: h
+    end subroutine
+    integer(c_int) function cb200_set_templates(h, unlensed, lensed, n_l) bind(C, name='cb200_set_templates')
+    import :: c_ptr, c_int, c_double
+    type(c_ptr), value :: h
+    real(c_double), intent(in) :: unlensed(*), lensed(*)
+    integer(c_int), value :: n_l
+    end function
+    integer(c_int) function cb200_upload_sources(h, kind, first, npts, thermo, n_k, k, src, src_is_device) &
+        bind(C, name='cb200_upload_sources')
+    import :: c_ptr, c_int, c_double
+    type(c_ptr), value :: h
+    integer(c_int), value :: kind, first, npts, src_is_device
+    real(c_double), intent(in) :: thermo(*), k(*), src(*)
+    integer(c_int), intent(in) :: n_k(*)
+    end function
+    integer(c_int) function cb200_powers(h, first, npts, initpower, alens, aphiphi, cls_out, derived_out, status) &
+        bind(C, name='cb200_powers')
+    import :: c_ptr, c_int, c_double
+    type(c_ptr), value :: h
+    integer(c_int), value :: first, npts
+    real(c_double), intent(in) :: initpower(*), alens(*), aphiphi(*)
+    real(c_double), intent(out) :: cls_out(*), derived_out(*)
+    integer(c_int), intent(out) :: status(*)
+    end function
+    end interface
+
+    Type, extends(CAMB_Calculator) :: B200_Calculator
+        type(c_ptr) :: handle = c_null_ptr
+        integer :: n_tau_max = 768, n_k_max = 256
+    contains
+    procedure :: InitForLikelihoods => B200_InitForLikelihoods
+    procedure :: GetNewTransferData => B200_GetNewTransferData
+    procedure :: GetNewPowerData => B200_GetNewPowerData
+    procedure :: VersionTraceOutput => B200_VersionTraceOutput
+    end type B200_Calculator
+
+    public B200_Calculator
+    contains
+
+    subroutine B200_InitForLikelihoods(this)
+    !Called once after the likelihoods fixed CosmoSettings (source/Calculator_CAMB.f90:926-946)
+    class(B200_Calculator) :: this
+    type(cb200_config) :: cfg
+    real(c_double), allocatable :: unl(:,:), lens(:,:)
+    integer L
+
+    call this%CAMB_Calculator%InitForLikelihoods()
+    call cb200_default_config(cfg)
+    cfg%lmax_computed_cl = CosmoSettings%lmax_computed_cl
+    cfg%cmb_lensing = merge(1, 0, CosmoSettings%CMB_Lensing)
+    cfg%use_lensing_potential = merge(1, 0, CosmoSettings%use_lensing_potential)
+    cfg%use_nonlinear_lensing = merge(1, 0, CosmoSettings%use_nonlinear_lensing)
+    cfg%compute_tensors = merge(1, 0, CosmoSettings%compute_tensors)
+    cfg%lmax_tensor = CosmoSettings%lmax_tensor
+    cfg%accurate_bb = merge(1, 0, this%accurate_BB)
+    cfg%k_eta_max_scalar = this%k_eta_max_scalar
+    cfg%accuracy_level = AccuracyLevel
+    cfg%lmax_out = CosmoSettings%lmax
+    cfg%highl_norm_first_call = 1          !keep the reference's SAVEd highL_norm behaviour bit for bit
+    cfg%max_points = 1
+    cfg%n_tau_max = this%n_tau_max
+    cfg%n_k_max = this%n_k_max
+    if (cb200_create(cfg, this%handle) /= 0) call MpiStop('B200: cb200_create failed (no CUDA device?)')
+    !templates: camb/modules.f90:1162-1185 (highL_CL_template) and source/Calculator_CAMB.f90:966-990
+    allocate(unl(0:8000,4), lens(0:CosmoSettings%lmax,4))
+    unl = 0; lens = 0
+    call CheckLoadedHighLTemplate
+    do L = lmin, 8000
+        unl(L,1:4) = highL_CL_template(L, C_Temp:C_Phi)
+    end do
+    if (allocated(this%highL_lensedCL_template)) then
+        do L = 2, CosmoSettings%lmax
+            lens(L,1:4) = this%highL_lensedCL_template(L,1:4)
+        end do
+    end if
+    if (cb200_set_templates(this%handle, unl, lens, CosmoSettings%lmax+1) /= 0) call MpiStop('B200: templates')
+    end subroutine B200_InitForLikelihoods
+
+    subroutine B200_GetNewTransferData(this, CMB, Info, Theory, error)
+    !Slow step (source/Calculator_CAMB.f90:179-218): CAMB evolves the sources, then the library takes over.
+    !Requires the small CAMB patch of INTEGRATION.md section 3 (`cmbmain_sources_only`), which stops cmbmain after the
+    !DoSourcek loop (camb/cmbmain.f90:198-202) and exposes Src, Evolve_q, taurst, taurend, ReionHist.
+    use CAMBmain, only : Src, Evolve_q, SourceNum
+    use ThermoData, only : taurst, taurend
+    use ModelParams, only : CP
+    class(B200_Calculator) :: this
+    class(CMBParams) CMB
+    class(TTheoryIntermediateCache), pointer :: Info
+    class(TCosmoTheoryPredictions) :: Theory
+    integer error
+    type(CAMBParams) P
+    real(c_double) :: thermo(5)
+    real(c_double), allocatable :: k(:), srcbuf(:,:,:)
+    integer(c_int) :: nk(1)
+    integer nt
+
+    select type (Info)
+    class is (CAMBTransferCache)
+        call this%CMBToCAMB(CMB, P)
+        P%OnlyTransfers = .true.
+        call CAMB_GetTransfers(P, Info%Transfers, error)   !with cmbmain_sources_only = .true.
+        if (error /= 0) return
+        thermo = [CP%tau0, taurst, taurend, &
+            merge(CP%ReionHist%tau_start, -1._dl, CP%Reion%Reionization), CP%ReionHist%tau_complete]
+        nt = size(Src, 3)
+        allocate(k(this%n_k_max), srcbuf(this%n_k_max, 3, this%n_tau_max))
+        k = 0; srcbuf = 0
+        nk(1) = Evolve_q%npoints
+        k(1:nk(1)) = Evolve_q%points(1:nk(1))
+        srcbuf(1:nk(1), 1:SourceNum, 1:nt) = Src(1:nk(1), 1:SourceNum, 1:nt)   !Src(k,s,tau) == C [tau][s][k]
+        if (cb200_upload_sources(this%handle, 0_c_int, 0_c_int, 1_c_int, thermo, nk, k, srcbuf, 0_c_int) /= 0) error = 1
+        if (error == 0) call this%SetDerived(Theory)
+    end select
+    end subroutine B200_GetNewTransferData
+
+    subroutine B200_GetNewPowerData(this, CMB, Info, Theory, error)
+    !Semi-slow step (source/Calculator_CAMB.f90:220-275 + SetPowersFromCAMB :349-463) on the GPU
+    class(B200_Calculator) :: this
+    class(CMBParams) :: CMB
+    class(TTheoryIntermediateCache), pointer :: Info
+    class(TCosmoTheoryPredictions) :: Theory
+    integer error
+    real(c_double) :: ip(10), alens(1), aphi(1), derived(4)
+    real(c_double), allocatable :: cls(:,:)
+    integer(c_int) :: st(1)
+    integer lmx
+
+    lmx = CosmoSettings%lmax
+    allocate(cls(0:lmx, 5))
+    ip = [cl_norm*CMB%InitPower(As_index), CMB%InitPower(ns_index), CMB%InitPower(nrun_index), &
+        CMB%InitPower(nrunrun_index), CMB%InitPower(amp_ratio_index), CMB%InitPower(nt_index), &
+        CMB%InitPower(ntrun_index), CosmoSettings%pivot_k, CosmoSettings%tensor_pivot_k, &
+        merge(1._dl, 0._dl, CosmoSettings%inflation_consistency)]
+    alens = CMB%ALens
+    aphi = CMB%InitPower(Aphiphi_index)
+    if (cb200_powers(this%handle, 0_c_int, 1_c_int, ip, alens, aphi, cls, derived, st) /= 0) then
+        error = 1
+        return
+    end if
+    error = st(1)
+    if (error /= 0) return
+    !order of cls columns: TT, TE, EE, BB, PP  ->  Theory%Cls(i,j)%CL   (source/CosmoTheory.f90:23-52)
+    if (allocated(Theory%Cls(1,1)%CL)) Theory%Cls(1,1)%CL(2:) = cls(2:ubound(Theory%Cls(1,1)%CL,1), 1)
+    if (allocated(Theory%Cls(2,1)%CL)) Theory%Cls(2,1)%CL(2:) = cls(2:ubound(Theory%Cls(2,1)%CL,1), 2)
+    if (allocated(Theory%Cls(2,2)%CL)) Theory%Cls(2,2)%CL(2:) = cls(2:ubound(Theory%Cls(2,2)%CL,1), 3)
+    if (allocated(Theory%Cls(3,3)%CL)) Theory%Cls(3,3)%CL(2:) = cls(2:ubound(Theory%Cls(3,3)%CL,1), 4)
+    if (allocated(Theory%Cls(CL_Phi,CL_Phi)%CL)) &
+        Theory%Cls(CL_Phi,CL_Phi)%CL(2:) = cls(2:ubound(Theory%Cls(CL_Phi,CL_Phi)%CL,1), 5)
+    Theory%Lensing_rms_deflect = derived(1)
+    end subroutine B200_GetNewPowerData
+
+    subroutine B200_VersionTraceOutput(this, ReadValues)
+    use IniObjects
+    class(B200_Calculator) :: this
+    class(TNameValueList) :: ReadValues
+    call this%CAMB_Calculator%VersionTraceOutput(ReadValues)
+    call ReadValues%Add('Compiled_B200_projection', 'cosmob200 v1')
+    end subroutine B200_VersionTraceOutput
+
+    end module Calculator_B200

@@ -188,3 +188,25 @@ def test_pliklite_loglike(setup):
     ref = o.pliklite(np.stack([gold[0, 0], gold[0, 1], gold[0, 2]]), data["nb"], data["blmin"], data["blmax"],
                      data["weights"], data["invcov"], data["x_data"], 1.00061)
     assert abs(ll2[0, 0] - ref) < 1e-7 * max(1.0, abs(ref))
+
+
+def test_lensing2018_real_data_golden_chi2(setup):
+    """Real Planck lensing 2018 data through the GPU binned-CMBLikes path (DMMA binning GEMM + quadratic form):
+    -lnL at the golden best-fit C_l must be the reference port's chi2/2 = 8.850226451078813/2 (|Delta lnL| < 1e-8)."""
+    import os
+    from cosmomc_b200 import lib
+    from cosmomc_b200.datasets import CMBLikesPlan
+    T = setup["T"]
+    plan = CMBLikesPlan(os.path.join(H.ROOT, "tests", "golden", "data", "planck_lensing_2018",
+                                     "smicadx12_Dec5_ftl_mv2_ndclpp_p_teb_consext8.dataset"))
+    h = lib.Handle(max_points=4, lmax_out=H.LMAX_OUT)
+    plan.register(h, cal_index=0)
+    gold = np.zeros((3, 5, H.LMAX_OUT + 1))
+    gold[:] = T["theory_cl"].T
+    cal = np.array([[1.00061], [1.0], [0.998]])
+    ll, tot, st = h.loglike_cls(gold, cal)
+    assert abs(ll[0, 0] - 8.850226451078813 / 2) < 1e-8
+    for i in range(3):
+        b = plan.binned_theory(gold[i], cal=cal[i, 0])
+        x = (b - plan.chat.reshape(9, 1)).ravel()
+        assert abs(ll[i, 0] - 0.5 * (x @ plan.invcov @ x)) < 1e-8
