@@ -11,6 +11,8 @@
 #include "project3.cuh"
 #include "lens.cuh"
 #include "like.cuh"
+#include "background.cuh"
+#include "sn.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -55,8 +57,18 @@ struct PointStore {  // resident per-point inputs
 };
 
 struct LikeEntry {
-  int type = 0;  // 1 plik-lite, 2 cmblikes
+  int type = 0;  // 1 plik-lite, 2 cmblikes, 3 BAO / MGS, 4 HST, 5 supernovae (JLA / Pantheon)
   int cal_index = -1;
+  // background likelihoods: segment of the handle's redshift list
+  int z_off = 0, nz = 0;
+  BaoParams bao{};
+  DevBuf<double> bao_invcov, bao_prob;
+  double hst_H0 = 0, hst_err = 1, hst_zeff = 0, hst_ang = 0;
+  // supernovae
+  SnData sn{};
+  DevBuf<double> sn_cols, sn_A1, sn_A2, sn_cov[6], sn_vinv;
+  int sn_ia = -1, sn_ib = -1, sn_ld = 0, sn_nr = 0;
+  double sn_sum_vinv = 0;
   // plik-lite
   int nused = 0, lmax_w = 0;
   DevBuf<int> bin_spec, bin_lo, bin_hi;
@@ -69,7 +81,7 @@ struct LikeEntry {
   bool has_noise = false, has_sqrt_fid = false;
 };
 
-enum Phase { PH_SPLINE = 0, PH_PROJECT, PH_CONTRACT, PH_INTERP, PH_LENS, PH_LIKE, PH_COUNT };
+enum Phase { PH_SPLINE = 0, PH_PROJECT, PH_CONTRACT, PH_INTERP, PH_LENS, PH_LIKE, PH_BG, PH_COUNT };
 
 }  // namespace
 
@@ -105,6 +117,14 @@ struct cb200_handle {
   // likelihoods
   std::vector<std::unique_ptr<LikeEntry>> likes;
   DevBuf<double> w_resid, w_T, w_bc, w_bp, w_bigx, w_quad, w_ll, w_total, w_nuis, w_cls_in, w_binned;
+  // background: massive-neutrino table, resident bg vectors, redshift list of the registered likelihoods
+  DevBuf<double> d_nu_r1, d_nu_dr1, r_bg, d_bgz, w_da, w_hz, w_snW, w_bg_in, w_bg_z, w_bg_out;
+  DevBuf<int> w_snbad;
+  double nu_dlnam = 0;
+  std::vector<double> bg_z;
+  bool bg_z_dirty = false;
+  int n_bg_likes = 0, n_cmb_likes = 0;
+  BgTables bg_tables() const { return BgTables{d_nu_r1.p, d_nu_dr1.p, nu_dlnam}; }
   // timing
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[PH_COUNT];
   std::vector<cudaEvent_t> ev_pool;
@@ -348,6 +368,22 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
     if (c.n_q_max <= 0) c.n_q_max = 3072;
     if (c.max_points <= 0) c.max_points = 1024;
     if (c.lmax_out <= 0) c.lmax_out = c.lmax_computed_cl;
+    {  // massive-neutrino density table of the background functions (camb/modules.f90:1532-1610)
+      std::vector<double> r1, dr1;
+      build_nu_table(r1, dr1, h->nu_dlnam);
+      h->d_nu_r1.upload(r1, h->stream);
+      h->d_nu_dr1.upload(dr1, h->stream);
+      CB_CUDA(cudaStreamSynchronize(h->stream));
+      CB_CUDA(cudaFuncSetAttribute(sn_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM));
+    }
+    h->chunk = c.chunk_points > 0 ? c.chunk_points : std::min(c.max_points, 1024);
+    h->chunk = std::min(h->chunk, c.max_points);
+    c.chunk_points = h->chunk;
+    h->info.max_points = c.max_points; h->info.chunk_points = h->chunk;
+    if (c.lmax_computed_cl <= 0) {  // background-only handle (parameterization = background; no CMB theory)
+      *out = h.release();
+      return 0;
+    }
     // CAMBCalc_InitCAMBParams (source/Calculator_CAMB.f90:749-754, 802-820)
     int max_l = c.lmax_computed_cl + 100 + 50;
     double max_eta_k = max_l * 2;
@@ -363,9 +399,6 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
       throw std::runtime_error("lmax_computed_cl exceeds lmax_lensed");
     h->LS = ((max_l + 1 + 3) / 4) * 4;
     h->LL = ((h->lg.lmax + 1 + 3) / 4) * 4;
-    h->chunk = c.chunk_points > 0 ? c.chunk_points : std::min(c.max_points, 1024);
-    h->chunk = std::min(h->chunk, c.max_points);
-    c.chunk_points = h->chunk;
     cb200_info& I = h->info;
     I.max_l = max_l; I.max_eta_k = (int)max_eta_k; I.max_l_tensor = c.lmax_tensor; I.max_eta_k_tensor = (int)max_eta_k_tensor;
     I.n_lsamp = (int)h->kind[0].ls.size(); I.n_lsamp_tensor = (int)h->kind[1].ls.size();
@@ -820,6 +853,7 @@ int cb200_like_add_pliklite(cb200_handle* h, const int* nb, int nbins_tab, const
   CB_CUDA(cudaStreamSynchronize(h->stream));
   if (like_id) *like_id = (int)h->likes.size();
   h->likes.push_back(std::move(L));
+  h->n_cmb_likes++;
   return 0;
   CB_API_END(h)
 }
@@ -859,21 +893,209 @@ int cb200_like_add_cmblikes(cb200_handle* h, int nmaps, int nbins, int ncl_used,
   CB_CUDA(cudaStreamSynchronize(h->stream));
   if (like_id) *like_id = (int)h->likes.size();
   h->likes.push_back(std::move(L));
+  h->n_cmb_likes++;
   return 0;
   CB_API_END(h)
 }
 
-static int loglike_device(cb200_handle* h, int npts, const double* d_cls, const int* d_status, const double* nuisance,
-                          int n_nuis, double* loglikes, double* total, int* status) {
+// ---------------------------------------------------------------------------------- background + its likelihoods
+int cb200_set_background(cb200_handle* h, int first, int npts, const double* bg) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (first < 0 || npts <= 0 || first + npts > h->cfg.max_points) return fail(h, "set_background: point range exceeds max_points");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  h->r_bg.alloc((size_t)h->cfg.max_points * NBG);
+  CB_CUDA(cudaMemcpyAsync(h->r_bg.p + (size_t)first * NBG, bg, sizeof(double) * npts * NBG, cudaMemcpyHostToDevice, h->stream));
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_background(cb200_handle* h, int npts, const double* bg, int nz, const double* z, double* DA, double* H,
+                     double* scalars) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (npts <= 0 || nz < 0) return fail(h, "background: bad sizes");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->stream;
+  h->w_bg_in.alloc((size_t)npts * NBG);
+  CB_CUDA(cudaMemcpyAsync(h->w_bg_in.p, bg, sizeof(double) * npts * NBG, cudaMemcpyHostToDevice, s));
+  cb200_handle::Scope sc(h, PH_BG);
+  if (nz > 0) {
+    h->w_bg_z.alloc(nz);
+    h->w_bg_out.alloc((size_t)2 * npts * nz);
+    CB_CUDA(cudaMemcpyAsync(h->w_bg_z.p, z, sizeof(double) * nz, cudaMemcpyHostToDevice, s));
+    const long long nthr = (long long)npts * nz;
+    bg_distance_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, s>>>(npts, nz, h->w_bg_in.p, h->w_bg_z.p, h->bg_tables(),
+                                                                     DA ? h->w_bg_out.p : nullptr,
+                                                                     H ? h->w_bg_out.p + (size_t)npts * nz : nullptr);
+    CB_LAUNCH_CHECK();
+    h->n_launches += 1;
+    if (DA) CB_CUDA(cudaMemcpyAsync(DA, h->w_bg_out.p, sizeof(double) * npts * nz, cudaMemcpyDeviceToHost, s));
+    if (H) CB_CUDA(cudaMemcpyAsync(H, h->w_bg_out.p + (size_t)npts * nz, sizeof(double) * npts * nz, cudaMemcpyDeviceToHost, s));
+  }
+  if (scalars) {
+    h->w_quad.alloc((size_t)npts * 3);
+    bg_scalars_kernel<<<(npts + 31) / 32, 96, 0, s>>>(npts, h->w_bg_in.p, h->bg_tables(), h->w_quad.p);
+    CB_LAUNCH_CHECK();
+    h->n_launches += 1;
+    CB_CUDA(cudaMemcpyAsync(scalars, h->w_quad.p, sizeof(double) * npts * 3, cudaMemcpyDeviceToHost, s));
+  }
+  CB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+  CB_API_END(h)
+}
+
+static int add_bg_z(cb200_handle* h, const double* z, int n) {
+  const int off = (int)h->bg_z.size();
+  h->bg_z.insert(h->bg_z.end(), z, z + n);
+  h->bg_z_dirty = true;
+  return off;
+}
+
+int cb200_like_add_bao(cb200_handle* h, int kind, int num_bao, const int* type, const double* z, const double* obs,
+                       const double* invcov, double rs_rescale, double fixed_rs, const double* alpha_prob, int n_alpha,
+                       int* like_id) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (num_bao < 1 || num_bao > BAO_MAXN) return fail(h, "bao: num_bao out of range");
+  if (kind == 1 && (!alpha_prob || n_alpha < 399)) return fail(h, "bao: MGS needs its chi^2(alpha) table");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  std::unique_ptr<LikeEntry> L(new LikeEntry());
+  L->type = 3;
+  L->bao.kind = kind; L->bao.num_bao = num_bao; L->bao.rs_rescale = rs_rescale; L->bao.fixed_rs = fixed_rs;
+  L->bao.n_alpha = n_alpha;
+  for (int i = 0; i < num_bao; i++) {
+    L->bao.type[i] = type ? type[i] : 2;
+    L->bao.z[i] = z[i];
+    L->bao.obs[i] = obs ? obs[i] : 0.0;
+    if (kind == 0 && (L->bao.type[i] == 6 || L->bao.type[i] == 9 || L->bao.type[i] < 1 || L->bao.type[i] > 10))
+      return fail(h, "bao: measurement type not supported (f_sigma8 / dilation need power spectra)");
+  }
+  if (invcov) L->bao_invcov.upload(invcov, (size_t)num_bao * num_bao, h->stream);
+  if (alpha_prob) L->bao_prob.upload(alpha_prob, n_alpha, h->stream);
+  L->z_off = add_bg_z(h, z, num_bao);
+  L->nz = num_bao;
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  if (like_id) *like_id = (int)h->likes.size();
+  h->likes.push_back(std::move(L));
+  h->n_bg_likes++;
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_like_add_hst(cb200_handle* h, double H0, double H0_err, double zeff, double angconversion, int* like_id) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  std::unique_ptr<LikeEntry> L(new LikeEntry());
+  L->type = 4; L->hst_H0 = H0; L->hst_err = H0_err; L->hst_zeff = zeff; L->hst_ang = angconversion;
+  if (zeff > 0) { L->z_off = add_bg_z(h, &zeff, 1); L->nz = 1; }
+  if (like_id) *like_id = (int)h->likes.size();
+  h->likes.push_back(std::move(L));
+  h->n_bg_likes++;
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_like_add_sn(cb200_handle* h, int nsn, const double* cols, const double* A1, const double* A2, int twoscriptm,
+                      const double* const* cov, int alpha_index, int beta_index, int* like_id) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (nsn < 4) return fail(h, "sn: too few supernovae");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->stream;
+  std::unique_ptr<LikeEntry> L(new LikeEntry());
+  L->type = 5; L->sn_ia = alpha_index; L->sn_ib = beta_index;
+  L->sn_cols.upload(cols, (size_t)11 * nsn, s);
+  std::vector<double> ones(nsn, 1.0), zeros(nsn, 0.0);
+  L->sn_A1.upload(twoscriptm ? A1 : ones.data(), nsn, s);
+  L->sn_A2.upload(twoscriptm ? A2 : zeros.data(), nsn, s);
+  SnData& S = L->sn;
+  S.nsn = nsn; S.twoscriptm = twoscriptm ? 1 : 0;
+  const double* c = L->sn_cols.p;
+  S.zcmb = c; S.zhel = c + nsn; S.mag = c + 2 * nsn; S.stretch = c + 3 * nsn; S.colour = c + 4 * nsn;
+  S.pre_vars = c + 5 * nsn; S.stretch_var = c + 6 * nsn; S.colour_var = c + 7 * nsn; S.cov_ms = c + 8 * nsn;
+  S.cov_mc = c + 9 * nsn; S.cov_sc = c + 10 * nsn;
+  S.A1 = L->sn_A1.p; S.A2 = L->sn_A2.p;
+  int ncov = 0;
+  for (int m = 0; m < 6; m++) {
+    S.cov[m] = nullptr;
+    if (cov && cov[m]) { L->sn_cov[m].upload(cov[m], (size_t)nsn * nsn, s); S.cov[m] = L->sn_cov[m].p; ncov++; }
+  }
+  if (ncov == 0) return fail(h, "sn: diagonal-only errors are not supported (the shipped datasets all have covariances)");
+  S.alphabeta = (ncov > 1 || !S.cov[0]) ? 1 : 0;  // alphabeta_covmat, supernovae_JLA.f90:735-741
+  L->sn_nr = twoscriptm ? 3 : 2;
+  L->sn_ld = (nsn + 3) / 4 * 4;
+  if (!S.alphabeta) {
+    if (twoscriptm) return fail(h, "sn: two-scriptM fit with a nuisance-independent covariance is not supported");
+    // factor V once with the identity riding along: rows n.. of W become (L^-1)^T, then V^-1 = U U^T
+    const int n = nsn, ld = L->sn_ld;
+    DevBuf<double> W;
+    W.alloc((size_t)2 * n * ld);
+    W.zero(s);
+    std::vector<double> eye((size_t)n * ld, 0.0);
+    for (int i = 0; i < n; i++) eye[(size_t)i * ld + i] = 1.0;
+    CB_CUDA(cudaMemcpyAsync(W.p + (size_t)n * ld, eye.data(), sizeof(double) * eye.size(), cudaMemcpyHostToDevice, s));
+    DevBuf<int> bad;
+    bad.alloc(1);
+    CholParams cp;
+    cp.n = n; cp.nr = n; cp.ld = ld; cp.np = 1; cp.assemble = 1; cp.S = S; cp.nuis = nullptr; cp.n_nuis = 0;
+    cp.ia = -1; cp.ib = -1; cp.W = W.p; cp.pt_stride = (size_t)2 * n * ld; cp.status = bad.p;
+    sn_chol_kernel<<<1, 256, CH_SMEM, s>>>(cp);
+    CB_LAUNCH_CHECK();
+    L->sn_vinv.alloc((size_t)n * n);
+    dgemm(s, true, false, n, n, n, 1.0, W.p + (size_t)n * ld, ld, W.p + (size_t)n * ld, ld, L->sn_vinv.p, n, &h->n_launches);
+    int hb = 0;
+    std::vector<double> vi((size_t)n * n);
+    CB_CUDA(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaMemcpyAsync(vi.data(), L->sn_vinv.p, sizeof(double) * vi.size(), cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    if (hb) return fail(h, "sn: covariance matrix is not positive definite");
+    // amarg_E = sum of the inverse, upper triangle doubled (supernovae_JLA.f90:1123-1126)
+    double E = 0;
+    for (int i = 0; i < n; i++) {
+      double su = 0;
+      for (int j = 0; j < i; j++) su += vi[(size_t)j * n + i];
+      E = E + vi[(size_t)i * n + i] + 2.0 * su;
+    }
+    L->sn_sum_vinv = E;
+    h->n_launches += 1;
+  }
+  L->z_off = add_bg_z(h, cols, nsn);  // zcmb
+  L->nz = nsn;
+  CB_CUDA(cudaStreamSynchronize(s));
+  if (like_id) *like_id = (int)h->likes.size();
+  h->likes.push_back(std::move(L));
+  h->n_bg_likes++;
+  return 0;
+  CB_API_END(h)
+}
+
+static int loglike_device(cb200_handle* h, int bg_first, int npts, const double* d_cls, const int* d_status,
+                          const double* nuisance, int n_nuis, double* loglikes, double* total, int* status) {
   cudaStream_t s = h->stream;
   const int nlike = (int)h->likes.size();
   if (nlike == 0) return fail(h, "loglike: no likelihood registered");
+  if (h->n_cmb_likes > 0 && !d_cls) return fail(h, "loglike: CMB likelihoods registered but no Cls resident");
+  if (h->n_bg_likes > 0 && (bg_first < 0 || !h->r_bg.p)) return fail(h, "loglike: background likelihoods need cb200_set_background");
   const int LO = h->cfg.lmax_out + 1;
   h->w_ll.alloc((size_t)npts * nlike);
   h->w_total.alloc(npts);
   h->w_quad.alloc(npts);
   h->w_nuis.alloc((size_t)npts * std::max(1, n_nuis));
   if (n_nuis > 0) CB_CUDA(cudaMemcpyAsync(h->w_nuis.p, nuisance, sizeof(double) * npts * n_nuis, cudaMemcpyHostToDevice, s));
+  const int nzt = (int)h->bg_z.size();
+  const double* d_bg = h->n_bg_likes > 0 ? h->r_bg.p + (size_t)bg_first * NBG : nullptr;
+  if (h->n_bg_likes > 0 && nzt > 0) {  // K5: D_A(z), H(z) at every redshift the registered likelihoods need
+    cb200_handle::Scope sc(h, PH_BG);
+    if (h->bg_z_dirty) { h->d_bgz.upload(h->bg_z, s); h->bg_z_dirty = false; }
+    h->w_da.alloc((size_t)npts * nzt); h->w_hz.alloc((size_t)npts * nzt);
+    const long long nthr = (long long)npts * nzt;
+    bg_distance_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, s>>>(npts, nzt, d_bg, h->d_bgz.p, h->bg_tables(),
+                                                                     h->w_da.p, h->w_hz.p);
+    CB_LAUNCH_CHECK();
+    h->n_launches += 1;
+  }
   {
     cb200_handle::Scope sc(h, PH_LIKE);
     for (int li = 0; li < nlike; li++) {
@@ -918,6 +1140,57 @@ static int loglike_device(cb200_handle* h, int npts, const double* d_cls, const 
                                                                  L.log_cal_prior, h->w_ll.p + li, nlike);
         CB_LAUNCH_CHECK();
         h->n_launches += 3;
+      } else if (L.type == 3) {
+        BaoParams bp = L.bao;
+        bp.np = npts; bp.nz_total = nzt; bp.z_off = L.z_off; bp.bg = d_bg; bp.DA = h->w_da.p; bp.H = h->w_hz.p;
+        bp.invcov = L.bao_invcov.p; bp.alpha_prob = L.bao_prob.p; bp.out = h->w_ll.p + li; bp.out_stride = nlike;
+        bao_kernel<<<(npts + 127) / 128, 128, 0, s>>>(bp);
+        CB_LAUNCH_CHECK();
+        h->n_launches += 1;
+      } else if (L.type == 4) {
+        hst_kernel<<<(npts + 127) / 128, 128, 0, s>>>(npts, d_bg, h->w_da.p, nzt, L.z_off, L.hst_zeff, L.hst_ang,
+                                                     L.hst_H0, L.hst_err, h->w_ll.p + li, nlike);
+        CB_LAUNCH_CHECK();
+        h->n_launches += 1;
+      } else if (L.type == 5) {
+        if (L.sn_ia >= n_nuis || L.sn_ib >= n_nuis) return fail(h, "loglike: alpha/beta index outside the nuisance vector");
+        const int n = L.sn.nsn;
+        if (L.sn.alphabeta) {
+          // K6: per-point covariance, blocked DMMA Cholesky with ride-along right-hand sides
+          const int nr = L.sn_nr, ld = L.sn_ld;
+          const size_t pst = (size_t)(n + nr) * ld;
+          const int sub = std::min(npts, h->chunk);
+          h->w_snW.alloc((size_t)sub * pst);
+          h->w_snbad.alloc(sub);
+          for (int a = 0; a < npts; a += sub) {
+            const int m = std::min(sub, npts - a);
+            sn_prep_kernel<<<m, 256, 0, s>>>(L.sn, m, h->w_da.p + (size_t)a * nzt, nzt, L.z_off,
+                                             h->w_nuis.p + (size_t)a * n_nuis, n_nuis, L.sn_ia, L.sn_ib,
+                                             h->w_snW.p + (size_t)n * ld, pst, ld, 1);
+            CB_LAUNCH_CHECK();
+            CholParams cp;
+            cp.n = n; cp.nr = nr; cp.ld = ld; cp.np = m; cp.assemble = 1; cp.S = L.sn;
+            cp.nuis = h->w_nuis.p + (size_t)a * n_nuis; cp.n_nuis = n_nuis; cp.ia = L.sn_ia; cp.ib = L.sn_ib;
+            cp.W = h->w_snW.p; cp.pt_stride = pst; cp.status = h->w_snbad.p;
+            sn_chol_kernel<<<m, 256, CH_SMEM, s>>>(cp);
+            CB_LAUNCH_CHECK();
+            sn_final_kernel<<<m, 256, 0, s>>>(m, n, L.sn.twoscriptm, h->w_snW.p + (size_t)n * ld, pst, ld, h->w_snbad.p,
+                                              h->w_ll.p + (size_t)a * nlike + li, nlike);
+            CB_LAUNCH_CHECK();
+            h->n_launches += 3;
+          }
+        } else {
+          // covariance independent of the nuisance parameters: cached inverse, one DMMA GEMM per batch
+          h->w_resid.alloc((size_t)npts * n);
+          h->w_T.alloc((size_t)npts * n);
+          sn_prep_kernel<<<npts, 256, 0, s>>>(L.sn, npts, h->w_da.p, nzt, L.z_off, h->w_nuis.p, n_nuis, -1, -1,
+                                              h->w_resid.p, (size_t)n, n, 0);
+          CB_LAUNCH_CHECK();
+          dgemm(s, false, false, npts, n, n, 1.0, h->w_resid.p, n, L.sn_vinv.p, n, h->w_T.p, n, &h->n_launches);
+          sn_final_cached_kernel<<<npts, 256, 0, s>>>(npts, n, h->w_T.p, h->w_resid.p, L.sn_sum_vinv, h->w_ll.p + li, nlike);
+          CB_LAUNCH_CHECK();
+          h->n_launches += 2;
+        }
       }
     }
     total_kernel<<<(npts + 127) / 128, 128, 0, s>>>(npts, nlike, h->w_ll.p, d_status, h->w_total.p);
@@ -936,10 +1209,12 @@ int cb200_loglike_batch(cb200_handle* h, int first, int npts, const double* nuis
                         double* total, int* status) {
   if (!h) return -1;
   CB_API_BEGIN
-  if (!h->r_cls_out.p || first < 0 || first + npts > h->cfg.max_points) return fail(h, "loglike_batch: no resident Cls");
+  if (first < 0 || npts <= 0 || first + npts > h->cfg.max_points) return fail(h, "loglike_batch: point range exceeds max_points");
+  if (h->n_cmb_likes > 0 && !h->r_cls_out.p) return fail(h, "loglike_batch: no resident Cls");
   CB_CUDA(cudaSetDevice(h->cfg.device));
-  return loglike_device(h, npts, h->r_cls_out.p + (size_t)first * 5 * (h->cfg.lmax_out + 1), h->r_status.p + first,
-                        nuisance, n_nuis, loglikes, total, status);
+  const bool have_cls = h->r_cls_out.p != nullptr;
+  return loglike_device(h, first, npts, have_cls ? h->r_cls_out.p + (size_t)first * 5 * (h->cfg.lmax_out + 1) : nullptr,
+                        have_cls ? h->r_status.p + first : nullptr, nuisance, n_nuis, loglikes, total, status);
   CB_API_END(h)
 }
 
@@ -951,7 +1226,7 @@ int cb200_loglike_cls(cb200_handle* h, int npts, const double* cls, const double
   const size_t n = (size_t)npts * 5 * (h->cfg.lmax_out + 1);
   h->w_cls_in.alloc(n);
   CB_CUDA(cudaMemcpyAsync(h->w_cls_in.p, cls, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
-  return loglike_device(h, npts, h->w_cls_in.p, nullptr, nuisance, n_nuis, loglikes, total, status);
+  return loglike_device(h, h->r_bg.p ? 0 : -1, npts, h->w_cls_in.p, nullptr, nuisance, n_nuis, loglikes, total, status);
   CB_API_END(h)
 }
 
@@ -970,7 +1245,7 @@ int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset) {
     }
   }
   t->ms_spline = ms[PH_SPLINE]; t->ms_project = ms[PH_PROJECT]; t->ms_contract = ms[PH_CONTRACT];
-  t->ms_interp = ms[PH_INTERP]; t->ms_lens = ms[PH_LENS]; t->ms_like = ms[PH_LIKE];
+  t->ms_interp = ms[PH_INTERP]; t->ms_lens = ms[PH_LENS]; t->ms_like = ms[PH_LIKE]; t->ms_background = ms[PH_BG];
   t->ms_total = 0;
   for (int p = 0; p < PH_COUNT; p++) t->ms_total += ms[p];
   t->n_launches = h->n_launches;

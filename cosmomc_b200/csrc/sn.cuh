@@ -1,0 +1,290 @@
+// K6 — JLA / Pantheon supernova likelihood, batched over parameter points.
+//
+// Reference behaviour reproduced (source/supernovae_JLA.f90):
+//   :874-991    jla_prep            pre_vars, A1/A2 masks of the two-scriptM fit
+//   :773-866    invert_covariance_matrix   V(alpha,beta) = V0 + a^2 Va + b^2 Vb + 2a V0a - 2b V0b - 2ab Vab + diag
+//   :1028-1168  JLA_alpha_beta_like        scriptM pre-estimate, A..F marginalisation terms, chi^2
+//   :1170-1228  jla_LnLike                 lumdists = 5 log10((1+zhel)(1+zcmb) D_A(zcmb))
+// The reference factors V (DPOTRF), forms the full inverse (DPOTRI) and multiplies (DSYMV).  Here V = L L^T is
+// factored by a blocked left-looking Cholesky on the FP64 tensor pipe (DMMA m8n8k4), V is assembled on the fly
+// from the constant L2-resident blocks when a panel is first touched, and the right-hand sides [d, A1, A2] ride
+// along as extra rows of the panel, so that after the factorisation those rows hold y = L^-1 rhs and
+//   A = y_d.y_d, B = y_d.y_1, C = y_d.y_2, D = y_1.y_2, E = y_1.y_1, F = y_2.y_2
+// (algebraically identical to the V^-1 expressions, without ever forming V^-1).
+#pragma once
+#include "common.cuh"
+#include "dgemm.cuh"
+
+namespace cb200 {
+
+struct SnData {  // device pointers, all [nsn]
+  int nsn;
+  const double *zcmb, *zhel, *mag, *stretch, *colour, *pre_vars, *stretch_var, *colour_var, *cov_ms, *cov_mc, *cov_sc;
+  const double *A1, *A2;  // A1 = ones when !twoscriptm
+  const double* cov[6];   // mag, stretch, colour, mag_stretch, mag_colour, stretch_colour (null if absent), [nsn][nsn]
+  int twoscriptm, alphabeta;
+};
+
+__device__ __forceinline__ double sn_diag(const SnData& S, int i, double alpha, double beta) {
+  return S.pre_vars[i] + alpha * alpha * S.stretch_var[i] + beta * beta * S.colour_var[i] + 2.0 * alpha * S.cov_ms[i] -
+         2.0 * beta * S.cov_mc[i] - 2.0 * alpha * beta * S.cov_sc[i];
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sh[w];
+  return s;
+}
+
+// per point: luminosity distances, scriptM pre-estimate, diffmag -> rhs rows of the work matrix (or a dense [np][nsn])
+//   DA [np][nz_total] (+z_off) ; ab [np][n_nuis] with alpha at ia, beta at ib (<0: 0)
+__global__ void __launch_bounds__(256) sn_prep_kernel(SnData S, int np, const double* __restrict__ DA, int nz_total,
+                                                      int z_off, const double* __restrict__ nuis, int n_nuis, int ia,
+                                                      int ib, double* __restrict__ rhs, size_t rhs_pt_stride,
+                                                      int rhs_row_stride, int write_masks) {
+  __shared__ double sh[8];
+  const int pt = blockIdx.x;
+  const double alpha = ia >= 0 ? nuis[(size_t)pt * n_nuis + ia] : 0.0;
+  const double beta = ib >= 0 ? nuis[(size_t)pt * n_nuis + ib] : 0.0;
+  const double* da = DA + (size_t)pt * nz_total + z_off;
+  double w = 0, ws = 0;
+  for (int i = threadIdx.x; i < S.nsn; i += blockDim.x) {
+    const double lum = 5.0 * log10((1.0 + S.zhel[i]) * (1.0 + S.zcmb[i]) * da[i]);
+    const double iv = 1.0 / sn_diag(S, i, alpha, beta);
+    w += iv;
+    ws += (S.mag[i] - lum) * iv;
+  }
+  const double wtval = block_sum_256(w, sh);
+  const double est = block_sum_256(ws, sh) / wtval;
+  double* r = rhs + (size_t)pt * rhs_pt_stride;
+  for (int i = threadIdx.x; i < S.nsn; i += blockDim.x) {
+    const double lum = 5.0 * log10((1.0 + S.zhel[i]) * (1.0 + S.zcmb[i]) * da[i]);
+    r[i] = S.mag[i] - lum + alpha * S.stretch[i] - beta * S.colour[i] - est;
+    if (write_masks) {
+      r[(size_t)rhs_row_stride + i] = S.A1[i];
+      if (S.twoscriptm) r[(size_t)2 * rhs_row_stride + i] = S.A2[i];
+    }
+  }
+}
+
+// ---- blocked Cholesky with ride-along right-hand sides ----------------------------------------------------
+// W[pt]: (n + nr) rows x ld, row-major.  Rows 0..n-1: lower triangle of V (assembled on the fly when S != null,
+// else read from W), rows n..n+nr-1: right-hand sides.  On exit rows 0..n-1 hold L (lower), rows n.. hold (L^-1 rhs)^T.
+constexpr int CH_NB = 32, CH_ROWS = 128, CH_KC = 32, CH_AS = CH_KC + 4, CH_CS = CH_NB + 1;
+constexpr size_t CH_SMEM = sizeof(double) * (CH_ROWS * CH_AS + CH_NB * CH_AS + CH_ROWS * CH_CS + CH_NB * CH_CS);
+
+struct CholParams {
+  int n, nr, ld, np, assemble;
+  SnData S;
+  const double* nuis;
+  int n_nuis, ia, ib;
+  double* W;
+  size_t pt_stride;
+  int* status;  // [np] != 0: not positive definite
+};
+
+__global__ void __launch_bounds__(256, 2) sn_chol_kernel(CholParams p) {
+  extern __shared__ __align__(16) unsigned char ch_smem[];
+  double* As = reinterpret_cast<double*>(ch_smem);  // [128][36]
+  double* Bs = As + CH_ROWS * CH_AS;                 // [32][36]
+  double* Cs = Bs + CH_NB * CH_AS;                   // [128][33]
+  double* Ls = Cs + CH_ROWS * CH_CS;                 // [32][33]
+  __shared__ int s_bad;
+  const int pt = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.n, nrows = p.n + p.nr, ld = p.ld;
+  double* W = p.W + (size_t)pt * p.pt_stride;
+  double alpha = 0, beta = 0;
+  if (p.assemble) {
+    alpha = p.ia >= 0 ? p.nuis[(size_t)pt * p.n_nuis + p.ia] : 0.0;
+    beta = p.ib >= 0 ? p.nuis[(size_t)pt * p.n_nuis + p.ib] : 0.0;
+  }
+  const double cf[6] = {1.0, alpha * alpha, beta * beta, 2.0 * alpha, -2.0 * beta, -2.0 * alpha * beta};
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+
+  for (int c0 = 0; c0 < n; c0 += CH_NB) {
+    const int wcols = min(CH_NB, n - c0);
+    for (int r0 = c0; r0 < nrows; r0 += CH_ROWS) {
+      // ---- acc = sum_k L[r0+.., k] * L[c0+.., k], k < c0 (DMMA), warp = 16 rows x 32 cols
+      double acc[2][4][2];
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int k0 = 0; k0 < c0; k0 += CH_KC) {
+        __syncthreads();
+        // stage L[r0 .. r0+128)[k0 .. k0+32) and L[c0 .. c0+32)[k0 .. k0+32)
+        for (int e = tid; e < CH_ROWS * (CH_KC / 2); e += 256) {
+          const int rr = e / (CH_KC / 2), kk = (e % (CH_KC / 2)) * 2;
+          const int row = r0 + rr;
+          double2 v = make_double2(0.0, 0.0);
+          if (row < nrows) v = *reinterpret_cast<const double2*>(W + (size_t)row * ld + k0 + kk);
+          As[rr * CH_AS + kk] = v.x;
+          As[rr * CH_AS + kk + 1] = v.y;
+        }
+        for (int e = tid; e < CH_NB * (CH_KC / 2); e += 256) {
+          const int rr = e / (CH_KC / 2), kk = (e % (CH_KC / 2)) * 2;
+          const int row = c0 + rr;
+          double2 v = make_double2(0.0, 0.0);
+          if (row < n) v = *reinterpret_cast<const double2*>(W + (size_t)row * ld + k0 + kk);
+          Bs[rr * CH_AS + kk] = v.x;
+          Bs[rr * CH_AS + kk + 1] = v.y;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < CH_KC / 4; kk++) {
+          double a[2], b[4];
+#pragma unroll
+          for (int mi = 0; mi < 2; mi++) a[mi] = As[(warp * 16 + mi * 8 + (lane >> 2)) * CH_AS + kk * 4 + (lane & 3)];
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) b[ni] = Bs[(ni * 8 + (lane >> 2)) * CH_AS + kk * 4 + (lane & 3)];
+#pragma unroll
+          for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+      }
+      // ---- Cs = A - acc  (A assembled from the constant blocks, or read from W)
+#pragma unroll
+      for (int mi = 0; mi < 2; mi++) {
+        const int rr = warp * 16 + mi * 8 + (lane >> 2);
+        const int row = r0 + rr;
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int cc = ni * 8 + (lane & 3) * 2 + e;
+            const int col = c0 + cc;
+            double av = 0.0;
+            if (row < nrows && cc < wcols) {
+              if (row < n && p.assemble) {
+                const size_t o = (size_t)row * n + col;
+#pragma unroll
+                for (int m = 0; m < 6; m++)
+                  if (p.S.cov[m]) av += cf[m] * p.S.cov[m][o];
+                if (row == col) av += sn_diag(p.S, row, alpha, beta);
+              } else {
+                av = W[(size_t)row * ld + col];
+              }
+            }
+            Cs[rr * CH_CS + cc] = av - acc[mi][ni][e];
+          }
+      }
+      __syncthreads();
+      if (r0 == c0) {
+        // ---- factor the diagonal block (warp 0, lane = row)
+        if (warp == 0) {
+          double rowv[CH_NB];
+#pragma unroll
+          for (int j = 0; j < CH_NB; j++) rowv[j] = (lane < wcols && j < wcols) ? Cs[lane * CH_CS + j] : (lane == j ? 1.0 : 0.0);
+          bool bad = false;
+#pragma unroll
+          for (int k = 0; k < CH_NB; k++) {
+            double dkk = __shfl_sync(0xffffffffu, rowv[k], k);
+            if (!(dkk > 0.0)) { bad = true; dkk = 1.0; }
+            const double d = sqrt(dkk);
+            const double lik = (lane >= k) ? ((lane == k) ? d : rowv[k] / d) : 0.0;
+            rowv[k] = lik;
+#pragma unroll
+            for (int j = k + 1; j < CH_NB; j++) {
+              const double ljk = __shfl_sync(0xffffffffu, lik, j);
+              if (lane >= j) rowv[j] -= lik * ljk;
+            }
+          }
+          if (bad && lane == 0) s_bad = 1;
+#pragma unroll
+          for (int j = 0; j < CH_NB; j++) Ls[lane * CH_CS + j] = (j <= lane) ? rowv[j] : 0.0;
+        }
+        __syncthreads();
+      }
+      // ---- rows of the diagonal block take L_jj; the others solve X L_jj^T = Cs row by row
+      if (tid < CH_ROWS) {
+        const int row = r0 + tid;
+        if (row < nrows) {
+          double* out = W + (size_t)row * ld + c0;
+          if (row < c0 + wcols && r0 == c0) {
+            for (int c = 0; c < wcols; c++) out[c] = Ls[tid * CH_CS + c];
+          } else {
+            double x[CH_NB];
+#pragma unroll
+            for (int c = 0; c < CH_NB; c++) {
+              double s = Cs[tid * CH_CS + c];
+#pragma unroll
+              for (int k = 0; k < c; k++) s -= x[k] * Ls[c * CH_CS + k];
+              x[c] = s / Ls[c * CH_CS + c];
+            }
+#pragma unroll
+            for (int c = 0; c < CH_NB; c++)
+              if (c < wcols) out[c] = x[c];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    __threadfence_block();
+  }
+  if (tid == 0 && p.status) p.status[pt] = s_bad;
+}
+
+// chi^2 from the solved right-hand-side rows y_d, y_1, y_2 (each [n], row stride ld)
+__global__ void __launch_bounds__(256) sn_final_kernel(int np, int n, int twoscriptm, const double* __restrict__ Y,
+                                                       size_t pt_stride, int ld, const int* __restrict__ bad,
+                                                       double* __restrict__ out, int out_stride) {
+  __shared__ double sh[8];
+  const int pt = blockIdx.x;
+  const double* yd = Y + (size_t)pt * pt_stride;
+  const double* y1 = yd + ld;
+  const double* y2 = yd + 2 * (size_t)ld;
+  double A = 0, B = 0, C = 0, D = 0, E = 0, F = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = yd[i], a1 = y1[i];
+    A += d * d; B += d * a1; E += a1 * a1;
+    if (twoscriptm) {
+      const double a2 = y2[i];
+      C += d * a2; D += a1 * a2; F += a2 * a2;
+    }
+  }
+  A = block_sum_256(A, sh); B = block_sum_256(B, sh); E = block_sum_256(E, sh);
+  if (twoscriptm) { C = block_sum_256(C, sh); D = block_sum_256(D, sh); F = block_sum_256(F, sh); }
+  if (threadIdx.x == 0) {
+    const double inv_twopi = 1.0 / (2 * 3.14159265358979323846264338328);
+    double chisq;
+    if (twoscriptm) {
+      const double G = F - D * D / E;
+      chisq = (G > 0) ? A + log(E * inv_twopi) + log(G * inv_twopi) - C * C / G - B * B * F / (E * G) + 2.0 * B * C * D / (E * G)
+                      : 2e30;
+    } else {
+      chisq = A + log(E * inv_twopi) - B * B / E;
+    }
+    double r = chisq / 2;
+    if (bad && bad[pt]) r = 1e30;
+    out[(size_t)pt * out_stride] = r;
+  }
+}
+
+// covariance independent of (alpha, beta): V^-1 cached at set-up; T = D V^-1 (DMMA GEMM) then per point
+//   A = T.d, B = sum(T), E = sum(V^-1) (constant)
+__global__ void __launch_bounds__(256) sn_final_cached_kernel(int np, int n, const double* __restrict__ T,
+                                                              const double* __restrict__ Dm, double E,
+                                                              double* __restrict__ out, int out_stride) {
+  __shared__ double sh[8];
+  const int pt = blockIdx.x;
+  double A = 0, B = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double t = T[(size_t)pt * n + i];
+    A += t * Dm[(size_t)pt * n + i];
+    B += t;
+  }
+  A = block_sum_256(A, sh);
+  B = block_sum_256(B, sh);
+  if (threadIdx.x == 0) {
+    const double inv_twopi = 1.0 / (2 * 3.14159265358979323846264338328);
+    out[(size_t)pt * out_stride] = (A + log(E * inv_twopi) - B * B / E) / 2;
+  }
+}
+
+}  // namespace cb200

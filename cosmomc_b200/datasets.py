@@ -345,3 +345,173 @@ class CMBLikesPlan:
         c = np.array(cls[:, :self.lmax_w + 1], dtype=float)
         c[:4] = c[:4] / cal ** 2
         return np.einsum("bcxl,xl->bc", self.W, c) - self.offset
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# background-only likelihoods: BAO / MGS (source/bao.f90:113-234), HST (source/HST.f90:20-45),
+# JLA / Pantheon supernovae (source/supernovae_JLA.f90:602-765 read_jla_dataset, :874-991 jla_prep)
+BAO_TYPES = ['Az', 'DV_over_rs', 'rs_over_DV', 'DA_over_rs', 'F_AP', 'f_sigma8', 'bao_Hz_rs', 'bao_Hz_rs_103',
+             'dilation', 'DM_over_rs']   # 1-based codes, bao.f90:29-35
+
+
+class BAOPlan:
+    """BAO_ReadIni + BAO_InitProbDist for TBAOLikelihood and MGSLikelihood (tag 'MGS')."""
+
+    def __init__(self, dataset_path, tag=None, overrides=None):
+        ini = IniFile(dataset_path)
+        if overrides:
+            ini.params.update(overrides)
+        self.name = ini.string("name", os.path.basename(dataset_path))
+        self.tag = tag or self.name
+        self.num_bao = ini.int("num_bao", 1)
+        self.rs_rescale = ini.float("rs_rescale", 1.0)
+        has_type = ini.has("measurement_type")
+        self.types = np.zeros(self.num_bao, dtype=np.int32)
+        if has_type:
+            names = ini.split("measurement_type")
+            if len(names) == 1:
+                names = names * self.num_bao
+            self.types[:] = [BAO_TYPES.index(n) + 1 for n in names]
+        self.z = np.zeros(self.num_bao)
+        self.obs = np.zeros(self.num_bao)
+        self.err = np.zeros(self.num_bao)
+        if ini.has("zeff"):
+            zs = [float(x) for x in ini.split("zeff")]
+            self.z[:] = zs if len(zs) == self.num_bao else zs[0]
+            vals = [float(x) for x in ini.split("bao_measurement")]
+            if self.num_bao > 1:
+                self.obs[:] = vals[:self.num_bao]
+            else:
+                self.obs[0], self.err[0] = vals[0], vals[1]
+        else:
+            has_err = ini.bool("bao_measurements_file_has_error", True)
+            rows = []
+            with open(ini.relative_file("bao_measurements_file")) as f:
+                for raw in f:
+                    line = raw.split("#")[0].strip()
+                    if line:
+                        rows.append(line.split())
+            for i in range(self.num_bao):
+                r = rows[i]
+                self.z[i], self.obs[i] = float(r[0]), float(r[1])
+                k = 2
+                if has_err:
+                    self.err[i] = float(r[2])
+                    k = 3
+                if not has_type:
+                    self.types[i] = BAO_TYPES.index(r[k]) + 1
+        if np.any(self.z < 0.0001):
+            raise ValueError("Error reading BAO measurements")
+        self.invcov = np.zeros((self.num_bao, self.num_bao))
+        self.alpha_prob = None
+        if self.tag == "MGS":
+            self.alpha_prob = np.loadtxt(ini.relative_file("prob_dist")).reshape(-1)
+        elif ini.has("bao_invcov_file"):
+            self.invcov = np.loadtxt(ini.relative_file("bao_invcov_file"))
+        elif ini.has("bao_cov_file"):
+            self.invcov = np.linalg.inv(np.loadtxt(ini.relative_file("bao_cov_file")))   # Matrix_Inverse at load
+        else:
+            self.invcov[np.diag_indices(self.num_bao)] = 1 / self.err ** 2
+
+    def register(self, handle, fixed_rs=-1.0):
+        if self.alpha_prob is not None:
+            return handle.add_mgs(self.z[0], self.alpha_prob, fixed_rs)
+        return handle.add_bao(self.types, self.z, self.obs, self.invcov, self.rs_rescale, fixed_rs)
+
+
+class HSTPlan:
+    def __init__(self, ini_path):
+        ini = IniFile(ini_path)
+        self.name = ini.string("Hubble_name")
+        self.H0 = ini.float("Hubble_H0")
+        self.H0_err = ini.float("Hubble_H0_err")
+        self.zeff = ini.float("Hubble_zeff", 0.0)
+        self.angconversion = ini.float("Hubble_angconversion", 0.0) if self.zeff > 0 else 0.0
+
+    def register(self, handle):
+        return handle.add_hst(self.H0, self.H0_err, self.zeff, self.angconversion)
+
+
+SN_COV_NAMES = ["mag", "stretch", "colour", "mag_stretch", "mag_colour", "stretch_colour"]
+
+
+class SNPlan:
+    """read_jla_dataset + jla_prep.  `covs` (dict name -> [nsn][nsn]) overrides the *_covmat_file entries: the six JLA
+    blocks and the Pantheon systematics matrix are missing from the reference checkout, so tests and the bench pass
+    documented synthetic SPD stand-ins (cosmomc_b200/synthetic.py)."""
+
+    def __init__(self, dataset_path, covs=None, data_file=None):
+        ini = IniFile(dataset_path)
+        self.name = ini.string("name")
+        if data_file is None:
+            df = ini.string("data_file")
+            cand = [df, os.path.join(ini.dir, df), os.path.join(ini.dir, os.path.basename(df)),
+                    os.path.join(ini.dir, "..", df)]
+            data_file = next((c for c in cand if os.path.exists(c)), None)
+            if data_file is None:
+                raise FileNotFoundError(df)
+        if ini.bool("absdist_file", False):
+            raise ValueError("absdist_file not supported")
+        self.pecz = ini.float("pecz", 0.001)
+        self.twoscriptmfit = ini.bool("twoscriptmfit", False)
+        self.scriptmcut = ini.float("scriptmcut", 10.0) if self.twoscriptmfit else 10.0
+        idisp0 = ini.float("intrinsicdisp", 0.13)
+        idisp = [ini.float("intrinsicdisp%d" % i, idisp0) for i in range(10)]
+        cols, rows = None, []
+        with open(data_file) as f:
+            for raw in f:
+                if raw.startswith("#"):
+                    cols = raw[1:].split()
+                elif raw.strip():
+                    rows.append(raw.split())
+        if cols is None:
+            raise ValueError("SN data file must have a comment header")
+        tab = {c: np.array([float(r[i]) if i > 0 else 0.0 for r in rows]) for i, c in enumerate(cols) if i < len(rows[0])}
+        self.names = [r[0] for r in rows]
+        self.nsn = len(rows)
+        g = lambda k: tab.get(k, np.zeros(self.nsn))
+        self.lc = {k: g(k) for k in ["zcmb", "zhel", "dz", "mb", "dmb", "x1", "dx1", "color", "dcolor", "3rdvar",
+                                     "d3rdvar", "cov_m_s", "cov_m_c", "cov_s_c", "set"]}
+        L = self.lc
+        zfacsq = 25.0 / np.float64(np.float32(np.log(np.float32(10.0)))) ** 2   # single-precision literals, :882
+        ds = L["set"].astype(int)
+        intrinsicsq = np.array(idisp) ** 2
+        self.pre_vars = L["dmb"] ** 2 + intrinsicsq[np.clip(ds, 0, 9)] + zfacsq * self.pecz ** 2 * (
+            (1.0 + L["zcmb"]) / (L["zcmb"] * (1 + 0.5 * L["zcmb"]))) ** 2
+        self.A1 = np.ones(self.nsn)
+        self.A2 = np.zeros(self.nsn)
+        if self.twoscriptmfit:
+            self.A1 = (L["3rdvar"] <= self.scriptmcut).astype(np.float64)
+            self.A2 = 1.0 - self.A1
+            if not self.A1.any():
+                self.A1, self.A2 = self.A2, np.zeros(self.nsn)
+                self.twoscriptmfit = False
+            if not self.A2.any():
+                self.twoscriptmfit = False
+        self.covs = {}
+        for nm in SN_COV_NAMES:
+            if ini.bool("has_%s_covmat" % nm, False):
+                if covs is not None and nm in covs:
+                    self.covs[nm] = np.ascontiguousarray(covs[nm], dtype=np.float64)
+                else:
+                    fn = ini.string("%s_covmat_file" % nm)
+                    cand = [fn, os.path.join(ini.dir, fn), os.path.join(ini.dir, os.path.basename(fn))]
+                    path = next((c for c in cand if os.path.exists(c)), None)
+                    if path is None:
+                        raise FileNotFoundError("%s (missing from the reference checkout; pass covs=...)" % fn)
+                    c = np.loadtxt(path).reshape(-1)
+                    if len(c) == self.nsn ** 2 + 1:
+                        c = c[1:]
+                    self.covs[nm] = c.reshape(self.nsn, self.nsn)
+        self.alphabeta_covmat = len(self.covs) > 1 or "mag" not in self.covs
+
+    def columns(self):
+        L = self.lc
+        return np.stack([L["zcmb"], L["zhel"], L["mb"], L["x1"], L["color"], self.pre_vars, L["dx1"] ** 2,
+                         L["dcolor"] ** 2, L["cov_m_s"], L["cov_m_c"], L["cov_s_c"]])
+
+    def register(self, handle, alpha_index=-1, beta_index=-1):
+        covs = [self.covs.get(nm) for nm in SN_COV_NAMES]
+        if not self.alphabeta_covmat:
+            alpha_index = beta_index = -1
+        return handle.add_sn(self.columns(), covs, self.A1, self.A2, self.twoscriptmfit, alpha_index, beta_index)

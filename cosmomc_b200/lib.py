@@ -25,6 +25,7 @@ EXPORTS = [
     "cb200_debug_fetch", "cb200_keep_transfers", "cb200_like_add_pliklite", "cb200_like_add_cmblikes",
     "cb200_loglike_batch", "cb200_loglike_cls", "cb200_get_timing", "cb200_sync", "cb200_set_option",
     "cb200_timer_start", "cb200_timer_stop", "cb200_measure_fp64_peaks",
+    "cb200_background", "cb200_set_background", "cb200_like_add_bao", "cb200_like_add_hst", "cb200_like_add_sn",
 ]
 
 
@@ -49,7 +50,7 @@ class Timing(C.Structure):
                 ("ms_interp", C.c_float), ("ms_lens", C.c_float), ("ms_like", C.c_float), ("ms_total", C.c_float),
                 ("n_launches", C.c_longlong), ("proj_triples", C.c_longlong), ("ring_slabs", C.c_longlong),
                 ("ring_direct", C.c_longlong), ("ring_rows", C.c_longlong), ("ring_pairs", C.c_longlong),
-                ("phase_cycles", C.c_longlong * 6)]
+                ("phase_cycles", C.c_longlong * 6), ("ms_background", C.c_float)]
 
 
 _lib = None
@@ -96,6 +97,13 @@ def load():
     L.cb200_timer_start.argtypes = [C.c_void_p]
     L.cb200_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.cb200_measure_fp64_peaks.argtypes = [C.c_void_p, c_dp, c_dp]
+    L.cb200_background.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp, c_dp]
+    L.cb200_set_background.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp]
+    L.cb200_like_add_bao.argtypes = [C.c_void_p, C.c_int, C.c_int, c_ip, c_dp, c_dp, c_dp, C.c_double, C.c_double,
+                                     c_dp, C.c_int, c_ip]
+    L.cb200_like_add_hst.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, c_ip]
+    L.cb200_like_add_sn.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, C.c_int, C.POINTER(c_dp), C.c_int, C.c_int,
+                                    c_ip]
     _lib = L
     return L
 
@@ -292,6 +300,60 @@ class Handle:
             _pd(_d(noise)) if noise is not None else None, _pd(_d(chat)),
             _pd(_d(sqrt_fid)) if sqrt_fid is not None else None, _pd(_d(invcov)), log_cal_prior, cal_index,
             C.byref(lid)), "like_add_cmblikes")
+        self.n_like += 1
+        return lid.value
+
+    # ---- background functions and likelihoods
+    def background(self, bg, z, want_scalars=False):
+        """D_A(z) [Mpc], H(z) [Mpc^-1] for every bg row; optionally (tau0, age/Gyr, CosmomcTheta)."""
+        bg = _d(bg).reshape(-1, 16)
+        z = _d(np.atleast_1d(z))
+        npts = len(bg)
+        DA = np.zeros((npts, len(z)))
+        H = np.zeros((npts, len(z)))
+        sc = np.zeros((npts, 3)) if want_scalars else None
+        self._check(self.L.cb200_background(self.h, npts, _pd(bg), len(z), _pd(z), _pd(DA), _pd(H), _pd(sc)),
+                    "background")
+        return (DA, H, sc) if want_scalars else (DA, H)
+
+    def set_background(self, bg, first=0):
+        bg = _d(bg).reshape(-1, 16)
+        self._check(self.L.cb200_set_background(self.h, first, len(bg), _pd(bg)), "set_background")
+
+    def add_bao(self, types, z, obs, invcov, rs_rescale=1.0, fixed_rs=-1.0):
+        t, z, obs, ic = _i(types), _d(z), _d(obs), _d(invcov)
+        lid = C.c_int(-1)
+        self._check(self.L.cb200_like_add_bao(self.h, 0, len(z), _pi(t), _pd(z), _pd(obs), _pd(ic), rs_rescale,
+                                              fixed_rs, None, 0, C.byref(lid)), "like_add_bao")
+        self.n_like += 1
+        return lid.value
+
+    def add_mgs(self, z, alpha_prob, fixed_rs=-1.0):
+        z, ap = _d([z]), _d(alpha_prob)
+        t = _i([2])
+        lid = C.c_int(-1)
+        self._check(self.L.cb200_like_add_bao(self.h, 1, 1, _pi(t), _pd(z), None, None, 1.0, fixed_rs, _pd(ap), len(ap),
+                                              C.byref(lid)), "like_add_bao(MGS)")
+        self.n_like += 1
+        return lid.value
+
+    def add_hst(self, H0, H0_err, zeff=0.0, angconversion=0.0):
+        lid = C.c_int(-1)
+        self._check(self.L.cb200_like_add_hst(self.h, H0, H0_err, zeff, angconversion, C.byref(lid)), "like_add_hst")
+        self.n_like += 1
+        return lid.value
+
+    def add_sn(self, cols, covs, A1=None, A2=None, twoscriptm=False, alpha_index=-1, beta_index=-1):
+        """cols [11][nsn] (include/cosmob200.h), covs: list of 6 arrays or None."""
+        cols = _d(cols)
+        nsn = cols.shape[1]
+        keep = [None if c is None else _d(c) for c in covs]
+        arr = (c_dp * 6)(*[None if c is None else c.ctypes.data_as(c_dp) for c in keep])
+        a1 = _d(A1) if A1 is not None else None
+        a2 = _d(A2) if A2 is not None else None
+        lid = C.c_int(-1)
+        self._check(self.L.cb200_like_add_sn(self.h, nsn, _pd(cols), _pd(a1), _pd(a2), int(twoscriptm), arr, alpha_index,
+                                             beta_index, C.byref(lid)), "like_add_sn")
         self.n_like += 1
         return lid.value
 

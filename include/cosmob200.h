@@ -138,7 +138,41 @@ int cb200_like_add_cmblikes(cb200_handle* h, int nmaps, int nbins, int ncl_used,
                             int cal_index /* position of the calibration parameter in the nuisance vector, -1 none */,
                             int* like_id);
 
-/* -lnL of every registered CMB likelihood for points [first, first+npts) using the Cls resident on the device
+/* ---- background functions and background-only likelihoods ---------------------------------------------
+ * bg [npts][16] per point = H0, omegab, omegac, omegan, omegav, w, tcmb, nu_massless_degeneracy, n_eigenstates,
+ *   nu_mass_degeneracies[3], nu_mass_fractions[3], rdrag  — i.e. what CAMBCalc_CMBToCAMB + CAMBParams_Set hold in
+ *   CP / grho* after SetParamsForBackground (source/Calculator_CAMB.f90:84-129,151-177; camb/modules.f90:300-375),
+ *   plus r_drag from the thermal history (Theory%derived_parameters(derived_rdrag), source/bao.f90:237-248).
+ *   cosmomc_b200/params.py builds it from CosmoMC's parameters.
+ *
+ * cb200_background replaces TCosmologyCalculator%AngularDiameterDistance / Hofz / ComovingRadialDistance /
+ *   CMBToTheta and CAMB's DeltaPhysicalTimeGyr (source/Calculator_Cosmology.f90:17-39; camb/modules.f90:519-751):
+ *   DA, H [npts][nz] (Mpc, Mpc^-1; NULL to skip), scalars [npts][3] = tau0, age/Gyr, CosmomcTheta (NULL to skip). */
+int cb200_background(cb200_handle* h, int npts, const double* bg, int nz, const double* z, double* DA, double* H,
+                     double* scalars);
+/* make bg resident for points [first, first+npts): input of the background likelihoods in cb200_loglike_batch
+ * (replaces Calculator%SetParamsForBackground / GetNewBackgroundData, source/Calculator_CAMB.f90:151-177) */
+int cb200_set_background(cb200_handle* h, int first, int npts, const double* bg);
+
+/* BAO (source/bao.f90:113-308): kind 0 = TBAOLikelihood (quadratic form with invcov [num_bao][num_bao]),
+ * kind 1 = MGSLikelihood (tabulated chi^2(alpha), :390-410).  type[i]: 1-based measurement type codes of
+ * bao.f90:29-35 (1 Az, 2 DV_over_rs, 3 rs_over_DV, 4 DA_over_rs, 5 F_AP, 7 bao_Hz_rs, 8 bao_Hz_rs_103,
+ * 10 DM_over_rs).  fixed_rs > 0: BAO_fixed_rs. */
+int cb200_like_add_bao(cb200_handle* h, int kind, int num_bao, const int* type, const double* z, const double* obs,
+                       const double* invcov, double rs_rescale, double fixed_rs, const double* alpha_prob, int n_alpha,
+                       int* like_id);
+/* HST (source/HST.f90:47-59): (H0 - H0_obs)^2 / 2 sigma^2, or via D_A(zeff) when zeff > 0 */
+int cb200_like_add_hst(cb200_handle* h, double H0, double H0_err, double zeff, double angconversion, int* like_id);
+/* JLA / Pantheon (source/supernovae_JLA.f90:773-866,1028-1228).
+ *   cols [11][nsn] = zcmb, zhel, mag, stretch, colour, pre_vars (jla_prep :911-920), stretch_var, colour_var,
+ *                    cov_mag_stretch, cov_mag_colour, cov_stretch_colour
+ *   A1, A2 [nsn] masks of the two-scriptM fit (ignored when !twoscriptm)
+ *   cov[6] = mag, stretch, colour, mag_stretch, mag_colour, stretch_colour covariance blocks [nsn][nsn] (NULL: absent)
+ *   alpha_index / beta_index: positions of alpha, beta in the nuisance vector (-1: fixed to 0) */
+int cb200_like_add_sn(cb200_handle* h, int nsn, const double* cols, const double* A1, const double* A2, int twoscriptm,
+                      const double* const* cov, int alpha_index, int beta_index, int* like_id);
+
+/* -lnL of every registered likelihood for points [first, first+npts) using the Cls resident on the device
  * from the last cb200_powers (replaces TheoryLike_LogLikeWithTheorySet, source/calclike.f90:357-389).
  *   nuisance [npts][n_nuis_total] in registration order; loglikes [npts][n_like]; total [npts] */
 int cb200_loglike_batch(cb200_handle* h, int first, int npts, const double* nuisance, int n_nuis,
@@ -155,6 +189,7 @@ typedef struct cb200_timing {
   long long proj_triples; /* (q,l,tau) triples integrated by the last projection (if counting enabled) */
   long long ring_slabs, ring_direct, ring_rows, ring_pairs; /* windowed projection statistics (option "ring_stats") */
   long long phase_cycles[6]; /* per-warp clock64 sums: prologue, prefetch, barrier wait, ring fill, accumulate, metadata */
+  float ms_background;       /* K5 distance kernels */
 } cb200_timing;
 int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset);
 int cb200_sync(cb200_handle* h);

@@ -4,6 +4,7 @@
 #include "orc_core.hpp"
 #include "orc_cmb.hpp"
 #include "orc_like.hpp"
+#include "orc_bg.hpp"
 #include <memory>
 
 using namespace orc;
@@ -233,3 +234,26 @@ int orc_lens_cls(int nl, const int* ls, int Max_l, const double* cl_scalar, cons
 }  // extern "C"
 
 #include "orc_like_api.inc"
+
+extern "C" {
+// ---- background (orc_bg.hpp): bg[16] layout documented there.  DA, H [nz]; extras[3] = tau0, age/Gyr, CosmomcTheta
+static orc::NuTable g_nu_table;
+int orc_background(const double* bg, int nz, const double* z, double* DA, double* H, double* extras) {
+  ORC_TRY
+  g_nu_table.init();
+  Background B;
+  B.set(bg, &g_nu_table);
+  for (int i = 0; i < nz; i++) { DA[i] = B.AngularDiameterDistance(z[i]); H[i] = B.Hofz(z[i]); }
+  if (extras) { extras[0] = B.tau0(); extras[1] = B.age_gyr(); extras[2] = B.CosmomcTheta(); }
+  return 0;
+  ORC_CATCH
+}
+int orc_nu_table(double* r1, double* dr1, double* dlnam) {
+  ORC_TRY
+  g_nu_table.init();
+  for (int i = 0; i < NuTable::nrhopn; i++) { r1[i] = g_nu_table.r1[i + 1]; dr1[i] = g_nu_table.dr1[i + 1]; }
+  *dlnam = g_nu_table.dlnam;
+  return 0;
+  ORC_CATCH
+}
+}  // extern "C"

@@ -279,3 +279,158 @@ def cmblikes_chisq(nmaps, nbins, cl_use_index, like_approx, NoiseM, ChatM, sqrt_
                                     _p(_d(NoiseM)) if NoiseM is not None else None, _p(_d(ChatM)),
                                     _p(_d(sqrt_fid)) if sqrt_fid is not None else None, _p(_d(inv_cov)),
                                     _p(_d(binnedC)))
+
+
+# ---------------------------------------------------------------- background (orc_bg.hpp) and background likelihoods
+def background(bg, z):
+    """bg [16] (layout: cosmomc_b200/params.py) -> D_A(z), H(z) [Mpc^-1], (tau0, age/Gyr, CosmomcTheta)."""
+    lib().orc_background.restype = C.c_int
+    bg = _d(bg)
+    z = _d(np.atleast_1d(z))
+    DA = np.zeros_like(z)
+    H = np.zeros_like(z)
+    ex = np.zeros(3)
+    if lib().orc_background(_p(bg), len(z), _p(z), _p(DA), _p(H), _p(ex)) != 0:
+        raise RuntimeError("orc_background failed")
+    return DA, H, ex
+
+
+def nu_table():
+    r1 = np.zeros(2000)
+    dr1 = np.zeros(2000)
+    dl = C.c_double(0)
+    lib().orc_nu_table(_p(r1), _p(dr1), C.byref(dl))
+    return r1, dr1, dl.value
+
+
+CONST_C = 2.99792458e8  # source/settings.f90 const_c
+
+# measurement types of source/bao.f90:29-35 (1-based codes as in the reference)
+BAO_TYPES = ['Az', 'DV_over_rs', 'rs_over_DV', 'DA_over_rs', 'F_AP', 'f_sigma8', 'bao_Hz_rs', 'bao_Hz_rs_103',
+             'dilation', 'DM_over_rs']
+
+
+def bao_loglike(bg, rs_drag, rs_rescale, types, zs, obs, invcov):
+    """BAO_LnLike (source/bao.f90:265-308).  types: 1-based codes into BAO_TYPES."""
+    rs = rs_drag * rs_rescale
+    DA, H, _ = background(bg, zs)
+    th = np.zeros(len(zs))
+    for j, (t, z) in enumerate(zip(types, zs)):
+        Dv = ((DA[j] * (1 + z)) ** 2 * z / H[j]) ** (1. / 3.)
+        if t == 2:
+            th[j] = Dv / rs
+        elif t == 7:
+            th[j] = CONST_C * H[j] / 1e3 * rs
+        elif t == 8:
+            th[j] = CONST_C * H[j] / 1e3 * rs * 1.0e-3
+        elif t == 3:
+            th[j] = rs / Dv
+        elif t == 1:
+            omegam = 1.0 - bg[4] - (1 - (bg[1] + bg[2] + bg[3] + bg[4]))
+            omh2 = omegam * (bg[0] / 100) ** 2
+            th[j] = 100 * Dv * np.sqrt(omh2) / (CONST_C / 1e3 * z)
+        elif t == 4:
+            th[j] = DA[j] / rs
+        elif t == 10:
+            th[j] = (1 + z) * DA[j] / rs
+        elif t == 5:
+            th[j] = (1 + z) * DA[j] * H[j]
+        else:
+            raise ValueError("unsupported BAO type")
+    d = th - np.asarray(obs)
+    return quadform(np.asarray(invcov), d) / 2
+
+
+def mgs_loglike(bg, rs_drag, z, alpha_prob):
+    """BAO_MGS_loglike (source/bao.f90:390-410)."""
+    DA, H, _ = background(bg, [z])
+    Dv = ((DA[0] * (1 + z)) ** 2 * z / H[0]) ** (1. / 3.)
+    alphamgs = Dv / rs_drag / (638.9518 / 148.69)
+    if alphamgs > 1.1985 or alphamgs < 0.8005:
+        return 1e30
+    ii = 1 + int(np.floor((alphamgs - 0.8005) / np.float64(np.float32(0.001))))
+    return (alpha_prob[ii - 1] + alpha_prob[ii]) / 2.0 / 2.0
+
+
+def hst_loglike(bg, H0_obs, H0_err, zeff=0.0, angconversion=0.0):
+    """HST_LnLike (source/HST.f90:47-59)."""
+    if zeff > 0:
+        DA, _, _ = background(bg, [zeff])
+        th = angconversion / DA[0]
+    else:
+        th = bg[0]
+    return (th - H0_obs) ** 2 / (2 * H0_err ** 2)
+
+
+class SN:
+    """JLA / Pantheon likelihood (source/supernovae_JLA.f90:874-991 jla_prep, :773-866 invert_covariance_matrix,
+    :1028-1168 JLA_alpha_beta_like, :1170-1228 jla_LnLike), LAPACK through numpy/scipy."""
+
+    def __init__(self, lc, covs, pecz=0.0, twoscriptmfit=False, scriptmcut=10.0, intrinsicdisp=0.0):
+        # lc: dict of columns zcmb zhel dz mb dmb x1 dx1 color dcolor 3rdvar cov_m_s cov_m_c cov_s_c ; covs: dict
+        self.lc = {k: np.asarray(v, dtype=np.float64) for k, v in lc.items()}
+        self.covs = covs
+        L = self.lc
+        self.nsn = len(L["zcmb"])
+        zfacsq = 25.0 / np.float64(np.float32(np.log(np.float32(10.0)))) ** 2
+        self.pre_vars = L["dmb"] ** 2 + intrinsicdisp ** 2 + zfacsq * pecz ** 2 * (
+            (1.0 + L["zcmb"]) / (L["zcmb"] * (1 + 0.5 * L["zcmb"]))) ** 2
+        self.twoscriptmfit = twoscriptmfit
+        if twoscriptmfit:
+            self.A1 = (L["3rdvar"] <= scriptmcut).astype(np.float64)
+            self.A2 = 1.0 - self.A1
+            if not self.A1.any():
+                self.A1, self.A2 = self.A2, np.zeros(self.nsn)
+                self.twoscriptmfit = False
+            if not self.A2.any():
+                self.twoscriptmfit = False
+
+    def diag(self, alpha, beta):
+        L = self.lc
+        return (self.pre_vars + alpha * alpha * L["dx1"] ** 2 + beta * beta * L["dcolor"] ** 2
+                + 2.0 * alpha * L["cov_m_s"] - 2.0 * beta * L["cov_m_c"] - 2.0 * alpha * beta * L["cov_s_c"])
+
+    def covariance(self, alpha, beta):
+        c = self.covs
+        V = np.zeros((self.nsn, self.nsn))
+        if "mag" in c: V = V + c["mag"]
+        if "stretch" in c: V = V + alpha * alpha * c["stretch"]
+        if "colour" in c: V = V + beta * beta * c["colour"]
+        if "mag_stretch" in c: V = V + 2.0 * alpha * c["mag_stretch"]
+        if "mag_colour" in c: V = V - 2.0 * beta * c["mag_colour"]
+        if "stretch_colour" in c: V = V - 2.0 * alpha * beta * c["stretch_colour"]
+        V[np.diag_indices(self.nsn)] += self.diag(alpha, beta)
+        return V
+
+    def alpha_beta_like(self, lumdists, alpha, beta):
+        import scipy.linalg as sl
+        L = self.lc
+        invvars = 1.0 / self.diag(alpha, beta)
+        wtval = invvars.sum()
+        est = ((L["mb"] - lumdists) * invvars).sum() / wtval
+        diffmag = L["mb"] - lumdists + alpha * L["x1"] - beta * L["color"] - est
+        cf = sl.cho_factor(self.covariance(alpha, beta), lower=False)   # DPOTRF('U')
+        inv = sl.cho_solve(cf, np.eye(self.nsn))                       # DPOTRI
+        iv = inv @ diffmag                                             # DSYMV
+        A = diffmag @ iv
+        if self.twoscriptmfit:
+            B = iv @ self.A1
+            Cc = iv @ self.A2
+            iv = inv @ self.A1
+            D = iv @ self.A2
+            E = iv @ self.A1
+            iv = inv @ self.A2
+            F = iv @ self.A2
+            G = F - D * D / E
+            chisq = (A + np.log(E / (2 * np.pi)) + np.log(G / (2 * np.pi)) - Cc * Cc / G - B * B * F / (E * G)
+                     + 2.0 * B * Cc * D / (E * G))
+        else:
+            B = iv.sum()
+            E = np.trace(inv) + 2.0 * np.triu(inv, 1).sum()
+            chisq = A + np.log(E / (2 * np.pi)) - B ** 2 / E
+        return chisq / 2
+
+    def loglike(self, DA, alpha=0.0, beta=0.0):
+        L = self.lc
+        lumdists = 5.0 * np.log10((1.0 + L["zhel"]) * (1.0 + L["zcmb"]) * DA)
+        return self.alpha_beta_like(lumdists, alpha, beta)
