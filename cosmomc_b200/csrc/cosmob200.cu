@@ -101,9 +101,9 @@ struct cb200_handle {
   DevBuf<double> d_A1, d_M, d_tab, d_apod;
   std::vector<int> lj;
   // chunk work buffers
-  int chunk = 0, LS = 0, LL = 0;
+  int chunk = 0, LS = 0, LL = 0, LST = 0;
   DevBuf<double> w_coef, w_ddsrc, w_part, w_icl, w_cl, w_cin, w_sc, w_corr, w_lcon, w_initpower, w_alens, w_aphi;
-  DevBuf<double> w_delta;
+  DevBuf<double> w_delta, w_clt, w_delta_sh[2], w_d2[2], w_pw, r_icl_t, r_clt;
   bool keep_transfers = false;
   int last_chunk_p0 = 0, last_chunk_np = 0;
   DevBuf<unsigned long long> d_triples;
@@ -290,7 +290,9 @@ void parallel_for(int n, const std::function<void(int, int)>& fn) {
 void ensure_store(cb200_handle* h, int k) {
   PointStore& S = h->store[k];
   if (S.cap) return;
-  S.cap = h->cfg.max_points; S.NT = h->cfg.n_tau_max; S.NK = h->cfg.n_k_max; S.NQ = h->cfg.n_q_max;
+  S.cap = h->cfg.max_points;
+  if (k == 0) { S.NT = h->cfg.n_tau_max; S.NK = h->cfg.n_k_max; S.NQ = h->cfg.n_q_max; }
+  else { S.NT = h->cfg.n_tau_max_tensor; S.NK = h->cfg.n_k_max_tensor; S.NQ = h->cfg.n_q_max_tensor; }
   const size_t P = S.cap;
   S.thermo.alloc(P * 5); S.tau.alloc(P * S.NT); S.dtau.alloc(P * S.NT); S.ksrc.alloc(P * S.NK);
   S.q.alloc(P * S.NQ); S.dq.alloc(P * S.NQ); S.n_tau.alloc(P); S.n_k.alloc(P); S.n_q.alloc(P); S.tseg.alloc(P);
@@ -300,11 +302,20 @@ void ensure_store(cb200_handle* h, int k) {
 
 void ensure_work(cb200_handle* h) {
   if (h->w_icl.p) return;
-  const int C = h->chunk, NT = h->cfg.n_tau_max, NK = h->cfg.n_k_max, NQ = h->cfg.n_q_max;
+  const bool tens = h->cfg.compute_tensors != 0;
+  const int C = h->chunk, NQ = std::max(h->cfg.n_q_max, tens ? h->cfg.n_q_max_tensor : 0);
+  const int NK = std::max(h->cfg.n_k_max, tens ? h->cfg.n_k_max_tensor : 0);
+  const size_t NTK = std::max((size_t)h->cfg.n_tau_max * h->cfg.n_k_max,
+                              tens ? (size_t)h->cfg.n_tau_max_tensor * h->cfg.n_k_max_tensor : (size_t)0);
   const int NQB = (NQ + PROJ_Q - 1) / PROJ_Q;  // v1 needs the larger partial buffer
   h->w_coef.alloc((size_t)C * 4 * NK);
-  h->w_ddsrc.alloc((size_t)C * NT * 3 * NK);
+  h->w_ddsrc.alloc((size_t)C * NTK * 3);
   h->w_part.alloc((size_t)C * NQB * 6 * PROJ_LP);
+  if (tens) {
+    h->w_clt.alloc((size_t)C * 4 * h->LST);
+    h->r_icl_t.alloc((size_t)h->cfg.max_points * 6 * PROJ_LP);
+    h->r_clt.alloc((size_t)h->cfg.max_points * 4 * h->LST);
+  }
   h->w_icl.alloc((size_t)C * 6 * PROJ_LP);
   h->w_cl.alloc((size_t)C * 6 * h->LS);
   h->w_cin.alloc((size_t)C * 4 * h->LL);
@@ -347,6 +358,7 @@ void cb200_default_config(cb200_config* c) {
   c->max_points = 1024;
   c->chunk_points = 0;
   c->n_tau_max = 768; c->n_k_max = 256; c->n_q_max = 3072;
+  c->n_tau_max_tensor = 2304; c->n_k_max_tensor = 128; c->n_q_max_tensor = 1024;
 }
 
 int cb200_create(const cb200_config* cfg, cb200_handle** out) {
@@ -366,6 +378,9 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
     if (c.n_tau_max <= 0) c.n_tau_max = 768;
     if (c.n_k_max <= 0) c.n_k_max = 256;
     if (c.n_q_max <= 0) c.n_q_max = 3072;
+    if (c.n_tau_max_tensor <= 0) c.n_tau_max_tensor = 2304;
+    if (c.n_k_max_tensor <= 0) c.n_k_max_tensor = 128;
+    if (c.n_q_max_tensor <= 0) c.n_q_max_tensor = 1024;
     if (c.max_points <= 0) c.max_points = 1024;
     if (c.lmax_out <= 0) c.lmax_out = c.lmax_computed_cl;
     {  // massive-neutrino density table of the background functions (camb/modules.f90:1532-1610)
@@ -399,10 +414,11 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
       throw std::runtime_error("lmax_computed_cl exceeds lmax_lensed");
     h->LS = ((max_l + 1 + 3) / 4) * 4;
     h->LL = ((h->lg.lmax + 1 + 3) / 4) * 4;
+    h->LST = ((c.lmax_tensor + 1 + 3) / 4) * 4;
     cb200_info& I = h->info;
     I.max_l = max_l; I.max_eta_k = (int)max_eta_k; I.max_l_tensor = c.lmax_tensor; I.max_eta_k_tensor = (int)max_eta_k_tensor;
     I.n_lsamp = (int)h->kind[0].ls.size(); I.n_lsamp_tensor = (int)h->kind[1].ls.size();
-    I.num_xx = h->kind[0].num_xx; I.lmax_lensed = h->lg.lmax_lensed; I.lens_lmax = h->lg.lmax;
+    I.num_xx = h->kind[0].num_xx; I.num_xx_tensor = h->kind[1].num_xx; I.lmax_lensed = h->lg.lmax_lensed; I.lens_lmax = h->lg.lmax;
     I.lens_npoints = h->lg.npoints; I.lens_jmax = h->lg.jmax;
     I.n_tau_max = c.n_tau_max; I.n_k_max = c.n_k_max; I.n_q_max = c.n_q_max; I.max_points = c.max_points;
     I.chunk_points = h->chunk;
@@ -600,154 +616,156 @@ int cb200_keep_transfers(cb200_handle* h, int on) {
   return 0;
 }
 
-int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, const double* alens,
-                 const double* aphiphi, double* cls_out, double* derived_out, int* status) {
-  if (!h) return -1;
-  CB_API_BEGIN
-  if (!h->have_templates) return fail(h, "powers: call cb200_set_templates first");
-  PointStore& S = h->store[0];
-  if (!S.cap || first < 0 || npts <= 0 || first + npts > S.cap) return fail(h, "powers: point range not resident");
-  CB_CUDA(cudaSetDevice(h->cfg.device));
-  ensure_work(h);
+}  // extern "C"
+
+namespace {
+
+struct ProjLaunch { int q_per_block, nqb_total; };
+
+// K0 + K1 + K2 for one chunk of points of one perturbation type: resident sources -> sampled C_l in w_icl
+// (source spline, line-of-sight projection fused with the partial k-contraction, fixed-order reduction + l-norms)
+void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, double* d_delta) {
+  cudaStream_t s = h->stream;
+  PointStore& S = h->store[kind];
+  const KindSet& K = h->kind[kind];
+  const int nl = (int)K.ls.size();
+  PointView v = S.view();
+  int nq_max = 0;
+  for (int i = 0; i < np; i++) nq_max = std::max(nq_max, S.h_nq[p0 + i]);
+  {  // K0
+    cb200_handle::Scope sc(h, PH_SPLINE);
+    spline_setup_kernel<<<(np + 63) / 64, 64, 0, s>>>(v, p0, np, h->w_coef.p);
+    CB_LAUNCH_CHECK();
+    const long long rows = (long long)np * S.NT * 3;
+    source_spline_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(v, p0, np, h->w_coef.p, h->w_ddsrc.p);
+    CB_LAUNCH_CHECK();
+    h->n_launches += 2;
+  }
+  ProjLaunch pl{PROJ_Q, (S.NQ + PROJ_Q - 1) / PROJ_Q};
+  {  // K1
+    cb200_handle::Scope sc(h, PH_PROJECT);
+    if (h->proj_kernel == 1) {
+      ProjParams pp;
+      pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB = pl.nqb_total; pp.tensors = kind;
+      pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes = K.d_bes.p;
+      pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
+      pp.delta = d_delta;
+      pp.triples = h->count_triples ? h->d_triples.p : nullptr;
+      pp.bseg = K.bseg;
+      for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
+      constexpr size_t META = sizeof(ProjMeta) * PROJ_NS * PROJ_SLAB * PROJ_Q;
+      constexpr size_t RED = sizeof(double) * (PROJ_NS - 1) * PROJ_Q * 3 * PROJ_LP;
+      const size_t smem = std::max(META, RED) + sizeof(ProjQ) * PROJ_Q;
+      dim3 grid((nq_max + PROJ_Q - 1) / PROJ_Q, np);
+      project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB><<<grid, 32 * PROJ_LW * PROJ_NS, smem, s>>>(pp);
+    } else if (h->proj_kernel == 3) {
+      pl.q_per_block = W3_QC;
+      pl.nqb_total = (S.NQ + W3_QC - 1) / W3_QC;
+      Proj3Params pp;
+      pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB = pl.nqb_total; pp.tensors = kind;
+      pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes3 = K.d_bes3.p;
+      pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
+      pp.delta = d_delta;
+      pp.triples = h->count_triples ? h->d_triples.p : nullptr;
+      pp.ring_stats = h->ring_stats ? h->d_ring_stats.p : nullptr;
+      pp.bseg = K.bseg;
+      for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
+      dim3 grid((nq_max + W3_QC - 1) / W3_QC, (nl + 31) / 32, np);
+      if (h->count_triples || h->ring_stats) project3_kernel<true><<<grid, 32 * W3_NW, W3_SMEM, s>>>(pp);
+      else project3_kernel<false><<<grid, 32 * W3_NW, W3_SMEM, s>>>(pp);
+    } else {
+      pl.q_per_block = W2_QC;
+      pl.nqb_total = (S.NQ + W2_QC - 1) / W2_QC;
+      Proj2Params pp;
+      pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB2 = pl.nqb_total; pp.tensors = kind;
+      pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes3 = K.d_bes3.p;
+      pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
+      pp.delta = d_delta;
+      pp.triples = h->count_triples ? h->d_triples.p : nullptr;
+      pp.ring_stats = h->ring_stats ? h->d_ring_stats.p : nullptr;
+      pp.bseg = K.bseg;
+      for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
+      dim3 grid((nq_max + W2_QC - 1) / W2_QC, (nl + 31) / 32, np);
+      if (h->count_triples || h->ring_stats) project2_kernel<true><<<grid, 32 * W2_NW, W2_SMEM, s>>>(pp);
+      else project2_kernel<false><<<grid, 32 * W2_NW, W2_SMEM, s>>>(pp);
+    }
+    CB_LAUNCH_CHECK();
+    h->n_launches += 1;
+  }
+  {  // K2
+    cb200_handle::Scope sc(h, PH_CONTRACT);
+    dim3 grid((6 * PROJ_LP + 127) / 128, np);
+    contract_reduce_kernel<<<grid, 128, 0, s>>>(np, p0, S.n_q.p, pl.q_per_block, pl.nqb_total, nl, K.d_ls.p, kind,
+                                               (have_alens && kind == 0) ? h->w_alens.p : nullptr, h->w_part.p,
+                                               h->w_icl.p, 0);
+    CB_LAUNCH_CHECK();
+    h->n_launches += 1;
+  }
+}
+
+// K3: sampled C_l (w_icl) -> all-l spectra
+void interp_chunk(cb200_handle* h, int kind, int np, double* d_cl, int LSk) {
+  cb200_handle::Scope sc(h, PH_INTERP);
+  const KindSet& K = h->kind[kind];
+  InterpParams ip;
+  ip.np = np; ip.nl = (int)K.ls.size(); ip.max_l = K.max_l; ip.LS = LSk; ip.nspec = kind ? 4 : 6;
+  ip.templated = kind ? 0 : 1;
+  ip.icl = h->w_icl.p; ip.ls = K.d_ls.p; ip.llo_of_l = K.d_llo.p; ip.tmpl = h->d_tmpl.p; ip.cl = d_cl;
+  interp_cls_kernel<<<np, 192, 0, h->stream>>>(ip, PROJ_LP);
+  CB_LAUNCH_CHECK();
+  h->n_launches += 1;
+}
+
+// K4 + units: unlensed w_cl (+ optional tensor spectra) -> lensed C_l, CosmoMC-unit Cls, derived, status at slot p0
+void lens_chunk(cb200_handle* h, int p0, int np, const double* d_cl_tensor, int tensor_shared, bool have_aphi) {
   cudaStream_t s = h->stream;
   const KindSet& K = h->kind[0];
   const LensGeom& g = h->lg;
-  const int nl = (int)K.ls.size();
-  const int NQB = (S.NQ + PROJ_Q - 1) / PROJ_Q;
   const int lmax_out = h->cfg.lmax_out;
-  if (h->keep_transfers) h->w_delta.alloc((size_t)h->chunk * S.NQ * PROJ_LP * 3);
+  cb200_handle::Scope sc(h, PH_LENS);
+  dim3 gp((g.lmax + 1 + 127) / 128, np);
+  lens_prep_kernel<<<gp, 128, 0, s>>>(np, g, h->LS, h->LL, h->w_cl.p, h->d_tmpl.p, h->w_cin.p);
+  CB_LAUNCH_CHECK();
+  // (1) sigma^2 | Cg2 = Cphil3[2..lmax] x A1
+  dgemm(s, false, false, np, 2 * g.NTHP, g.lmax - 1, 1.0, h->w_cin.p + 2, 4 * h->LL, h->d_A1.p, 2 * g.NTHP,
+        h->w_sc.p, 2 * g.NTHP, &h->n_launches);
+  LensCorrParams cp;
+  cp.np = np; cp.LL = h->LL; cp.g = g; cp.sc = h->w_sc.p; cp.cin = h->w_cin.p; cp.tab = h->d_tab.p;
+  cp.lj = h->d_lj.p; cp.apod = h->d_apod.p; cp.corr = h->w_corr.p;
+  const size_t csm = sizeof(double) * LENS_PB * 3 * g.jmax;
+  lens_corr_kernel<<<(np + LENS_PB - 1) / LENS_PB, g.NTHP, csm, s>>>(cp);
+  CB_LAUNCH_CHECK();
+  // (3) four correlation -> multipole transforms
+  const size_t ms = (size_t)g.NTHP * g.NLL;
+  for (int k4 = 0; k4 < 4; k4++)
+    dgemm(s, false, false, np, g.lmax_lensed - 1, g.NTHP, 1.0, h->w_corr.p + (size_t)k4 * g.NTHP, 4 * g.NTHP,
+          h->d_M.p + k4 * ms, g.NLL, h->w_lcon.p + (size_t)k4 * g.NLL, 4 * g.NLL, &h->n_launches);
+  FinishParams fp;
+  fp.np = np; fp.LS = h->LS; fp.NLL = g.NLL; fp.lmax_out = lmax_out; fp.lmax_computed_cl = h->cfg.lmax_computed_cl;
+  fp.lmax_lensed = g.lmax_lensed; fp.n_highl = h->n_highl;
+  fp.lmax_tensor = h->cfg.lmax_tensor; fp.have_tensor = d_cl_tensor ? 1 : 0; fp.LST = h->LST;
+  fp.dtheta = g.dtheta; fp.cl = h->w_cl.p; fp.lcon = h->w_lcon.p; fp.cl_tensor = d_cl_tensor; fp.tensor_shared = tensor_shared;
+  fp.highl = h->d_highl.p; fp.aphiphi = have_aphi ? h->w_aphi.p : nullptr;
+  fp.cl_lensed = h->r_cl_lensed.p + (size_t)p0 * 4 * h->LS;
+  fp.cls_out = h->r_cls_out.p + (size_t)p0 * 5 * (lmax_out + 1);
+  fp.saved_highl_norm = h->cfg.highl_norm_first_call ? h->saved_highl_norm : 0.0;
+  const int lspan = std::max(h->LS, lmax_out + 1);
+  dim3 gf((lspan + 127) / 128, np);
+  lens_finish_kernel<<<gf, 128, 0, s>>>(fp);
+  CB_LAUNCH_CHECK();
+  derived_status_kernel<<<np, 32, 0, s>>>(np, h->LS, lmax_out, K.max_l, h->w_cl.p, fp.cls_out,
+                                          h->r_derived.p + (size_t)p0 * 4, h->r_status.p + p0,
+                                          h->cfg.compute_tensors ? h->w_initpower.p : nullptr);
+  CB_LAUNCH_CHECK();
+  h->n_launches += 4;
+  // keep intermediates resident for parity read-backs
+  CB_CUDA(cudaMemcpyAsync(h->r_cl.p + (size_t)p0 * 6 * h->LS, h->w_cl.p, sizeof(double) * np * 6 * h->LS,
+                          cudaMemcpyDeviceToDevice, s));
+}
 
-  for (int c0 = 0; c0 < npts; c0 += h->chunk) {
-    const int np = std::min(h->chunk, npts - c0);
-    const int p0 = first + c0;
-    h->last_chunk_p0 = p0; h->last_chunk_np = np;
-    CB_CUDA(cudaMemcpyAsync(h->w_initpower.p, initpower + (size_t)c0 * 10, sizeof(double) * 10 * np,
-                            cudaMemcpyHostToDevice, s));
-    if (alens) CB_CUDA(cudaMemcpyAsync(h->w_alens.p, alens + c0, sizeof(double) * np, cudaMemcpyHostToDevice, s));
-    if (aphiphi) CB_CUDA(cudaMemcpyAsync(h->w_aphi.p, aphiphi + c0, sizeof(double) * np, cudaMemcpyHostToDevice, s));
-    PointView v = S.view();
-    int nq_max = 0;
-    for (int i = 0; i < np; i++) nq_max = std::max(nq_max, S.h_nq[p0 + i]);
-    const int nqb_used = (nq_max + PROJ_Q - 1) / PROJ_Q;
-    {  // K0
-      cb200_handle::Scope sc(h, PH_SPLINE);
-      spline_setup_kernel<<<(np + 63) / 64, 64, 0, s>>>(v, p0, np, h->w_coef.p);
-      CB_LAUNCH_CHECK();
-      const long long rows = (long long)np * S.NT * 3;
-      source_spline_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(v, p0, np, h->w_coef.p, h->w_ddsrc.p);
-      CB_LAUNCH_CHECK();
-      h->n_launches += 2;
-    }
-    int q_per_block = PROJ_Q, nqb_total = NQB;
-    {  // K1
-      cb200_handle::Scope sc(h, PH_PROJECT);
-      if (h->proj_kernel == 1) {
-        ProjParams pp;
-        pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB = NQB; pp.tensors = 0;
-        pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes = K.d_bes.p;
-        pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
-        pp.delta = h->keep_transfers ? h->w_delta.p : nullptr;
-        pp.triples = h->count_triples ? h->d_triples.p : nullptr;
-        pp.bseg = K.bseg;
-        for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
-        constexpr size_t META = sizeof(ProjMeta) * PROJ_NS * PROJ_SLAB * PROJ_Q;
-        constexpr size_t RED = sizeof(double) * (PROJ_NS - 1) * PROJ_Q * 3 * PROJ_LP;
-        const size_t smem = std::max(META, RED) + sizeof(ProjQ) * PROJ_Q;
-        dim3 grid(nqb_used, np);
-        project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB><<<grid, 32 * PROJ_LW * PROJ_NS, smem, s>>>(pp);
-      } else if (h->proj_kernel == 3) {
-        q_per_block = W3_QC;
-        nqb_total = (S.NQ + W3_QC - 1) / W3_QC;
-        Proj3Params pp;
-        pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB = nqb_total; pp.tensors = 0;
-        pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes3 = K.d_bes3.p;
-        pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
-        pp.delta = h->keep_transfers ? h->w_delta.p : nullptr;
-        pp.triples = h->count_triples ? h->d_triples.p : nullptr;
-        pp.ring_stats = h->ring_stats ? h->d_ring_stats.p : nullptr;
-        pp.bseg = K.bseg;
-        for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
-        dim3 grid((nq_max + W3_QC - 1) / W3_QC, (nl + 31) / 32, np);
-        if (h->count_triples || h->ring_stats) project3_kernel<true><<<grid, 32 * W3_NW, W3_SMEM, s>>>(pp);
-        else project3_kernel<false><<<grid, 32 * W3_NW, W3_SMEM, s>>>(pp);
-      } else {
-        q_per_block = W2_QC;
-        nqb_total = (S.NQ + W2_QC - 1) / W2_QC;
-        Proj2Params pp;
-        pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB2 = nqb_total; pp.tensors = 0;
-        pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes3 = K.d_bes3.p;
-        pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
-        pp.delta = h->keep_transfers ? h->w_delta.p : nullptr;
-        pp.triples = h->count_triples ? h->d_triples.p : nullptr;
-        pp.ring_stats = h->ring_stats ? h->d_ring_stats.p : nullptr;
-        pp.bseg = K.bseg;
-        for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
-        dim3 grid((nq_max + W2_QC - 1) / W2_QC, (nl + 31) / 32, np);
-        if (h->count_triples || h->ring_stats) project2_kernel<true><<<grid, 32 * W2_NW, W2_SMEM, s>>>(pp);
-        else project2_kernel<false><<<grid, 32 * W2_NW, W2_SMEM, s>>>(pp);
-      }
-      CB_LAUNCH_CHECK();
-      h->n_launches += 1;
-    }
-    {  // K2
-      cb200_handle::Scope sc(h, PH_CONTRACT);
-      dim3 grid((6 * PROJ_LP + 127) / 128, np);
-      contract_reduce_kernel<<<grid, 128, 0, s>>>(np, p0, S.n_q.p, q_per_block, nqb_total, nl, K.d_ls.p, 0,
-                                                 alens ? h->w_alens.p : nullptr, h->w_part.p, h->w_icl.p);
-      CB_LAUNCH_CHECK();
-      h->n_launches += 1;
-    }
-    {  // K3
-      cb200_handle::Scope sc(h, PH_INTERP);
-      InterpParams ip;
-      ip.np = np; ip.nl = nl; ip.max_l = K.max_l; ip.LS = h->LS; ip.nspec = 6; ip.templated = 1;
-      ip.icl = h->w_icl.p; ip.ls = K.d_ls.p; ip.llo_of_l = K.d_llo.p; ip.tmpl = h->d_tmpl.p; ip.cl = h->w_cl.p;
-      interp_cls_kernel<<<np, 192, 0, s>>>(ip, PROJ_LP);
-      CB_LAUNCH_CHECK();
-      h->n_launches += 1;
-    }
-    {  // K4
-      cb200_handle::Scope sc(h, PH_LENS);
-      dim3 gp((g.lmax + 1 + 127) / 128, np);
-      lens_prep_kernel<<<gp, 128, 0, s>>>(np, g, h->LS, h->LL, h->w_cl.p, h->d_tmpl.p, h->w_cin.p);
-      CB_LAUNCH_CHECK();
-      // (1) sigma^2 | Cg2 = Cphil3[2..lmax] x A1
-      dgemm(s, false, false, np, 2 * g.NTHP, g.lmax - 1, 1.0, h->w_cin.p + 2, 4 * h->LL, h->d_A1.p, 2 * g.NTHP,
-            h->w_sc.p, 2 * g.NTHP, &h->n_launches);
-      LensCorrParams cp;
-      cp.np = np; cp.LL = h->LL; cp.g = g; cp.sc = h->w_sc.p; cp.cin = h->w_cin.p; cp.tab = h->d_tab.p;
-      cp.lj = h->d_lj.p; cp.apod = h->d_apod.p; cp.corr = h->w_corr.p;
-      const size_t csm = sizeof(double) * LENS_PB * 3 * g.jmax;
-      lens_corr_kernel<<<(np + LENS_PB - 1) / LENS_PB, g.NTHP, csm, s>>>(cp);
-      CB_LAUNCH_CHECK();
-      // (3) four correlation -> multipole transforms
-      const size_t ms = (size_t)g.NTHP * g.NLL;
-      for (int k4 = 0; k4 < 4; k4++)
-        dgemm(s, false, false, np, g.lmax_lensed - 1, g.NTHP, 1.0, h->w_corr.p + (size_t)k4 * g.NTHP, 4 * g.NTHP,
-              h->d_M.p + k4 * ms, g.NLL, h->w_lcon.p + (size_t)k4 * g.NLL, 4 * g.NLL, &h->n_launches);
-      FinishParams fp;
-      fp.np = np; fp.LS = h->LS; fp.NLL = g.NLL; fp.lmax_out = lmax_out; fp.lmax_computed_cl = h->cfg.lmax_computed_cl;
-      fp.lmax_lensed = g.lmax_lensed; fp.n_highl = h->n_highl; fp.lmax_tensor = 0; fp.have_tensor = 0; fp.LST = 0;
-      fp.dtheta = g.dtheta; fp.cl = h->w_cl.p; fp.lcon = h->w_lcon.p; fp.cl_tensor = nullptr; fp.tensor_shared = 0;
-      fp.highl = h->d_highl.p; fp.aphiphi = aphiphi ? h->w_aphi.p : nullptr;
-      fp.cl_lensed = h->r_cl_lensed.p + (size_t)p0 * 4 * h->LS;
-      fp.cls_out = h->r_cls_out.p + (size_t)p0 * 5 * (lmax_out + 1);
-      fp.saved_highl_norm = h->cfg.highl_norm_first_call ? h->saved_highl_norm : 0.0;
-      const int lspan = std::max(h->LS, lmax_out + 1);
-      dim3 gf((lspan + 127) / 128, np);
-      lens_finish_kernel<<<gf, 128, 0, s>>>(fp);
-      CB_LAUNCH_CHECK();
-      derived_status_kernel<<<np, 32, 0, s>>>(np, h->LS, lmax_out, K.max_l, h->w_cl.p, fp.cls_out,
-                                              h->r_derived.p + (size_t)p0 * 4, h->r_status.p + p0);
-      CB_LAUNCH_CHECK();
-      h->n_launches += 4;
-    }
-    // keep intermediates resident for parity read-backs
-    CB_CUDA(cudaMemcpyAsync(h->r_icl.p + (size_t)p0 * 6 * PROJ_LP, h->w_icl.p, sizeof(double) * np * 6 * PROJ_LP,
-                            cudaMemcpyDeviceToDevice, s));
-    CB_CUDA(cudaMemcpyAsync(h->r_cl.p + (size_t)p0 * 6 * h->LS, h->w_cl.p, sizeof(double) * np * 6 * h->LS,
-                            cudaMemcpyDeviceToDevice, s));
-  }
+int powers_finish(cb200_handle* h, int first, int npts, double* cls_out, double* derived_out, int* status) {
+  cudaStream_t s = h->stream;
+  const int lmax_out = h->cfg.lmax_out;
   if (cls_out)
     CB_CUDA(cudaMemcpyAsync(cls_out, h->r_cls_out.p + (size_t)first * 5 * (lmax_out + 1),
                             sizeof(double) * npts * 5 * (lmax_out + 1), cudaMemcpyDeviceToHost, s));
@@ -767,6 +785,134 @@ int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, 
     h->saved_highl_norm = tt / hl[0];
   }
   return 0;
+}
+
+void upload_chunk_params(cb200_handle* h, int c0, int np, const double* initpower, const double* alens,
+                         const double* aphiphi) {
+  cudaStream_t s = h->stream;
+  CB_CUDA(cudaMemcpyAsync(h->w_initpower.p, initpower + (size_t)c0 * 10, sizeof(double) * 10 * np, cudaMemcpyHostToDevice, s));
+  if (alens) CB_CUDA(cudaMemcpyAsync(h->w_alens.p, alens + c0, sizeof(double) * np, cudaMemcpyHostToDevice, s));
+  if (aphiphi) CB_CUDA(cudaMemcpyAsync(h->w_aphi.p, aphiphi + c0, sizeof(double) * np, cudaMemcpyHostToDevice, s));
+}
+
+}  // namespace
+
+extern "C" {
+
+int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, const double* alens,
+                 const double* aphiphi, double* cls_out, double* derived_out, int* status) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (!h->kind[0].active) return fail(h, "powers: background-only handle");
+  if (!h->have_templates) return fail(h, "powers: call cb200_set_templates first");
+  PointStore& S = h->store[0];
+  if (!S.cap || first < 0 || npts <= 0 || first + npts > S.cap) return fail(h, "powers: point range not resident");
+  const bool tens = h->cfg.compute_tensors != 0;
+  if (tens && !h->store[1].cap) return fail(h, "powers: compute_tensors but no tensor sources uploaded");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  ensure_work(h);
+  cudaStream_t s = h->stream;
+  if (h->keep_transfers) h->w_delta.alloc((size_t)h->chunk * S.NQ * PROJ_LP * 3);
+
+  for (int c0 = 0; c0 < npts; c0 += h->chunk) {
+    const int np = std::min(h->chunk, npts - c0);
+    const int p0 = first + c0;
+    h->last_chunk_p0 = p0; h->last_chunk_np = np;
+    upload_chunk_params(h, c0, np, initpower, alens, aphiphi);
+    project_chunk(h, 0, p0, np, alens != nullptr, h->keep_transfers ? h->w_delta.p : nullptr);
+    CB_CUDA(cudaMemcpyAsync(h->r_icl.p + (size_t)p0 * 6 * PROJ_LP, h->w_icl.p, sizeof(double) * np * 6 * PROJ_LP,
+                            cudaMemcpyDeviceToDevice, s));
+    interp_chunk(h, 0, np, h->w_cl.p, h->LS);
+    if (tens) {  // tensor pass of CAMB_GetResults (camb/camb.f90:106-237): same stages on the tensor sources
+      project_chunk(h, 1, p0, np, false, nullptr);
+      CB_CUDA(cudaMemcpyAsync(h->r_icl_t.p + (size_t)p0 * 6 * PROJ_LP, h->w_icl.p, sizeof(double) * np * 6 * PROJ_LP,
+                              cudaMemcpyDeviceToDevice, s));
+      interp_chunk(h, 1, np, h->w_clt.p, h->LST);
+      CB_CUDA(cudaMemcpyAsync(h->r_clt.p + (size_t)p0 * 4 * h->LST, h->w_clt.p, sizeof(double) * np * 4 * h->LST,
+                              cudaMemcpyDeviceToDevice, s));
+    }
+    lens_chunk(h, p0, np, tens ? h->w_clt.p : nullptr, 0, aphiphi != nullptr);
+  }
+  return powers_finish(h, first, npts, cls_out, derived_out, status);
+  CB_API_END(h)
+}
+
+// Semi-slow step with SHARED transfer functions: one resident source point, many initial-power points
+// (CosmoMC calls GetNewPowerData without GetNewTransferData when only the InitPower block moved,
+// source/CalcLike_Cosmology.f90:73-85; BK15 chains with fixed cosmology, batch3/BK15only.ini).  The transfer
+// functions Delta_l(q) are projected once; the k-contraction of the whole batch is then the dense product
+//   iCl[pt][X][l] = sum_q  P(q; pt) dq/q  x  Delta_a Delta_b (q, l)          (FP64 tensor-pipe GEMM)
+int cb200_powers_shared(cb200_handle* h, int src_point, int first, int npts, const double* initpower,
+                        const double* alens, const double* aphiphi, double* cls_out, double* derived_out, int* status) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (!h->kind[0].active) return fail(h, "powers_shared: background-only handle");
+  if (!h->have_templates) return fail(h, "powers_shared: call cb200_set_templates first");
+  PointStore& S = h->store[0];
+  if (!S.cap || src_point < 0 || src_point >= S.cap) return fail(h, "powers_shared: source point not resident");
+  if (first < 0 || npts <= 0 || first + npts > h->cfg.max_points) return fail(h, "powers_shared: output range exceeds max_points");
+  const bool tens = h->cfg.compute_tensors != 0;
+  if (tens && !h->store[1].cap) return fail(h, "powers_shared: compute_tensors but no tensor sources uploaded");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  ensure_work(h);
+  cudaStream_t s = h->stream;
+  // ---- transfer functions of the source point, once per perturbation type
+  std::vector<double> ip1(10, 0.0);
+  ip1[0] = 1; ip1[1] = 1; ip1[7] = 0.05; ip1[8] = 0.05;
+  CB_CUDA(cudaMemcpyAsync(h->w_initpower.p, ip1.data(), sizeof(double) * 10, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  const int nk = tens ? 2 : 1;
+  for (int kind = 0; kind < nk; kind++) {
+    PointStore& Sk = h->store[kind];
+    const int nq = Sk.h_nq[src_point];
+    h->w_delta_sh[kind].alloc((size_t)Sk.NQ * PROJ_LP * 3);
+    h->w_d2[kind].alloc((size_t)Sk.NQ * 6 * PROJ_LP);
+    project_chunk(h, kind, src_point, 1, false, h->w_delta_sh[kind].p);
+    cb200_handle::Scope sc(h, PH_CONTRACT);
+    delta_products_kernel<<<(nq * PROJ_LP + 127) / 128, 128, 0, s>>>(nq, kind, h->w_delta_sh[kind].p, h->w_d2[kind].p);
+    CB_LAUNCH_CHECK();
+    h->n_launches += 1;
+  }
+  for (int c0 = 0; c0 < npts; c0 += h->chunk) {
+    const int np = std::min(h->chunk, npts - c0);
+    const int p0 = first + c0;
+    h->last_chunk_p0 = p0; h->last_chunk_np = np;
+    upload_chunk_params(h, c0, np, initpower, alens, aphiphi);
+    for (int kind = 0; kind < nk; kind++) {
+      PointStore& Sk = h->store[kind];
+      const KindSet& K = h->kind[kind];
+      const int nq = Sk.h_nq[src_point];
+      {
+        cb200_handle::Scope sc(h, PH_CONTRACT);
+        h->w_pw.alloc((size_t)h->chunk * Sk.NQ);
+        dim3 gw((nq + 127) / 128, np);
+        power_weights_kernel<<<gw, 128, 0, s>>>(np, nq, kind, Sk.q.p + (size_t)src_point * Sk.NQ,
+                                                 Sk.dq.p + (size_t)src_point * Sk.NQ, h->w_initpower.p, h->w_pw.p, Sk.NQ);
+        CB_LAUNCH_CHECK();
+        dgemm(s, false, false, np, 6 * PROJ_LP, nq, 1.0, h->w_pw.p, Sk.NQ, h->w_d2[kind].p, 6 * PROJ_LP, h->w_part.p,
+              6 * PROJ_LP, &h->n_launches);
+        dim3 grid((6 * PROJ_LP + 127) / 128, np);
+        contract_reduce_kernel<<<grid, 128, 0, s>>>(np, 0, Sk.n_q.p, 1 << 30, 1, (int)K.ls.size(), K.d_ls.p, kind,
+                                                   (alens && kind == 0) ? h->w_alens.p : nullptr, h->w_part.p,
+                                                   h->w_icl.p, nq);
+        CB_LAUNCH_CHECK();
+        h->n_launches += 2;
+      }
+      if (kind == 0) {
+        CB_CUDA(cudaMemcpyAsync(h->r_icl.p + (size_t)p0 * 6 * PROJ_LP, h->w_icl.p, sizeof(double) * np * 6 * PROJ_LP,
+                                cudaMemcpyDeviceToDevice, s));
+        interp_chunk(h, 0, np, h->w_cl.p, h->LS);
+      } else {
+        CB_CUDA(cudaMemcpyAsync(h->r_icl_t.p + (size_t)p0 * 6 * PROJ_LP, h->w_icl.p, sizeof(double) * np * 6 * PROJ_LP,
+                                cudaMemcpyDeviceToDevice, s));
+        interp_chunk(h, 1, np, h->w_clt.p, h->LST);
+        CB_CUDA(cudaMemcpyAsync(h->r_clt.p + (size_t)p0 * 4 * h->LST, h->w_clt.p, sizeof(double) * np * 4 * h->LST,
+                                cudaMemcpyDeviceToDevice, s));
+      }
+    }
+    lens_chunk(h, p0, np, tens ? h->w_clt.p : nullptr, 0, aphiphi != nullptr);
+  }
+  return powers_finish(h, first, npts, cls_out, derived_out, status);
   CB_API_END(h)
 }
 
@@ -816,6 +962,26 @@ int cb200_debug_fetch(cb200_handle* h, int what, int point, int max_n, double* o
       const int local = point - h->last_chunk_p0;
       if (local < 0 || local >= h->last_chunk_np) return fail(h, "debug_fetch: point not in the last chunk");
       fetch(h->w_delta.p + (size_t)local * S.NQ * PROJ_LP * 3, (size_t)S.h_nq[point] * PROJ_LP * 3);
+      break;
+    }
+    case 8: {  // tensor iCl [4][n_lsamp_tensor]
+      if (!h->r_icl_t.p) return fail(h, "debug_fetch: no tensor spectra");
+      const int nlt = (int)h->kind[1].ls.size();
+      std::vector<double> t((size_t)6 * PROJ_LP);
+      CB_CUDA(cudaMemcpy(t.data(), h->r_icl_t.p + (size_t)point * 6 * PROJ_LP, sizeof(double) * t.size(), cudaMemcpyDeviceToHost));
+      if (4 * nlt > max_n) return fail(h, "debug_fetch: buffer too small");
+      for (int X = 0; X < 4; X++) for (int j = 0; j < nlt; j++) out[X * nlt + j] = t[(size_t)X * PROJ_LP + j];
+      *n = 4 * nlt;
+      break;
+    }
+    case 9: {  // Cl_tensor [4][lmax_tensor+1] (dimensionless) TT, EE, BB, TE
+      if (!h->r_clt.p) return fail(h, "debug_fetch: no tensor spectra");
+      std::vector<double> t((size_t)4 * h->LST);
+      CB_CUDA(cudaMemcpy(t.data(), h->r_clt.p + (size_t)point * 4 * h->LST, sizeof(double) * t.size(), cudaMemcpyDeviceToHost));
+      const int w = h->cfg.lmax_tensor + 1;
+      if (4 * w > max_n) return fail(h, "debug_fetch: buffer too small");
+      for (int X = 0; X < 4; X++) for (int l = 0; l < w; l++) out[X * w + l] = t[(size_t)X * h->LST + l];
+      *n = 4 * w;
       break;
     }
     case 4: fetch(S.q.p + (size_t)point * S.NQ, S.h_nq[point]); break;

@@ -357,7 +357,7 @@ __global__ void lens_finish_kernel(FinishParams p) {
 // rms deflection angle (Calculator_CAMB.f90:440-449) and the reject flags (:239-256); one warp per point
 __global__ void derived_status_kernel(int np, int LS, int lmax_out, int max_l, const double* __restrict__ cl,
                                       const double* __restrict__ cls_out, double* __restrict__ derived /*[np][4]*/,
-                                      int* __restrict__ status) {
+                                      int* __restrict__ status, const double* __restrict__ initpower /*tensors: [np][10]*/) {
   const int lp = blockIdx.x, lane = threadIdx.x;
   if (lp >= np) return;
   double rms = 0;
@@ -383,7 +383,14 @@ __global__ void derived_status_kernel(int np, int LS, int lmax_out, int max_l, c
   if (lane == 0) {
     if (derived) {
       derived[(size_t)lp * 4 + 0] = sqrt(rms) * 180 / kPi * 60;
-      derived[(size_t)lp * 4 + 1] = 0; derived[(size_t)lp * 4 + 2] = 0; derived[(size_t)lp * 4 + 3] = 0;
+      double r02 = 0, rbb = 0, at = 0;
+      if (initpower) {  // tensor-derived ratios, Calculator_CAMB.f90:451-455
+        const double* ip = initpower + (size_t)lp * 10;
+        r02 = tensor_power_dev(ip, 0.002) / scalar_power_dev(ip, 0.002);
+        at = tensor_power_dev(ip, ip[8]);
+        rbb = tensor_power_dev(ip, 0.01) / scalar_power_dev(ip, 0.01);
+      }
+      derived[(size_t)lp * 4 + 1] = r02; derived[(size_t)lp * 4 + 2] = rbb; derived[(size_t)lp * 4 + 3] = at;
     }
     if (status) status[lp] = bad ? 1 : 0;
   }

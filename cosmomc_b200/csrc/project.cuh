@@ -407,14 +407,15 @@ __global__ void __launch_bounds__(32 * PROJ_LW * NS, 1) project_kernel(const Pro
 // fixed-order sum of the per-CTA partials + the l-dependent normalisations (cmbmain.f90:2222-2257, :2388-2393)
 __global__ void contract_reduce_kernel(int np, int p0, const int* __restrict__ n_q, int Q, int NQB, int nl,
                                        const int* __restrict__ ls, int tensors, const double* __restrict__ alens,
-                                       const double* __restrict__ part, double* __restrict__ icl /*[np][6][PROJ_LP]*/) {
+                                       const double* __restrict__ part, double* __restrict__ icl /*[np][6][PROJ_LP]*/,
+                                       int nq_shared /* > 0: every point uses this wavenumber count */) {
   int lp = blockIdx.y;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (lp >= np || t >= 6 * PROJ_LP) return;
   const int X = t / PROJ_LP, j = t % PROJ_LP;
   double s = 0;
   if (j < nl) {
-    const int nb = (n_q[p0 + lp] + Q - 1) / Q;
+    const int nb = ((nq_shared > 0 ? nq_shared : n_q[p0 + lp]) + Q - 1) / Q;
     const double* pp = part + (((size_t)lp * NQB) * 6 + X) * PROJ_LP + j;
     for (int b = 0; b < nb; b++) s += pp[(size_t)b * 6 * PROJ_LP];
     const double ell = ls[j];
@@ -441,6 +442,35 @@ __global__ void contract_reduce_kernel(int np, int p0, const int* __restrict__ n
     }
   }
   icl[((size_t)lp * 6 + X) * PROJ_LP + j] = s;
+}
+
+// ---- shared-transfer contraction (one source point, many initial-power points): operands of the DMMA GEMM ----
+// D2[q][X][l] = Delta_a Delta_b of CalcScalCls / CalcTensCls (cmbmain.f90:2195-2215, :2377-2383)
+__global__ void delta_products_kernel(int nq, int tensors, const double* __restrict__ delta /*[nq][PROJ_LP][3]*/,
+                                      double* __restrict__ d2 /*[nq][6][PROJ_LP]*/) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq * PROJ_LP) return;
+  const int q = t / PROJ_LP, j = t % PROJ_LP;
+  const double* d = delta + (size_t)t * 3;
+  const double d0 = d[0], d1 = d[1], dd2 = d[2];
+  double* o = d2 + (size_t)q * 6 * PROJ_LP + j;
+  if (tensors) {
+    o[0] = d0 * d0; o[PROJ_LP] = d1 * d1; o[2 * PROJ_LP] = dd2 * dd2; o[3 * PROJ_LP] = d0 * d1;
+    o[4 * PROJ_LP] = 0; o[5 * PROJ_LP] = 0;
+  } else {
+    o[0] = d0 * d0; o[PROJ_LP] = d1 * d1; o[2 * PROJ_LP] = d0 * d1;
+    o[3 * PROJ_LP] = dd2 * dd2; o[4 * PROJ_LP] = dd2 * d0; o[5 * PROJ_LP] = dd2 * d1;
+  }
+}
+// W[pt][q] = P(q; initpower_pt) dq/q
+__global__ void power_weights_kernel(int np, int nq, int tensors, const double* __restrict__ q,
+                                     const double* __restrict__ dq, const double* __restrict__ initpower,
+                                     double* __restrict__ W, int ldw) {
+  const int lp = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lp >= np || i >= nq) return;
+  const double* ip = initpower + (size_t)lp * 10;
+  const double qv = q[i];
+  W[(size_t)lp * ldw + i] = (tensors ? tensor_power_dev(ip, qv) : scalar_power_dev(ip, qv)) * (dq[i] / qv);
 }
 
 }  // namespace cb200

@@ -25,7 +25,7 @@ EXPORTS = [
     "cb200_debug_fetch", "cb200_keep_transfers", "cb200_like_add_pliklite", "cb200_like_add_cmblikes",
     "cb200_loglike_batch", "cb200_loglike_cls", "cb200_get_timing", "cb200_sync", "cb200_set_option",
     "cb200_timer_start", "cb200_timer_stop", "cb200_measure_fp64_peaks",
-    "cb200_background", "cb200_set_background", "cb200_like_add_bao", "cb200_like_add_hst", "cb200_like_add_sn",
+    "cb200_powers_shared", "cb200_background", "cb200_set_background", "cb200_like_add_bao", "cb200_like_add_hst", "cb200_like_add_sn",
 ]
 
 
@@ -35,14 +35,15 @@ class Config(C.Structure):
                 ("lmax_tensor", C.c_int), ("accurate_bb", C.c_int), ("k_eta_max_scalar", C.c_double),
                 ("accuracy_level", C.c_double), ("lmax_out", C.c_int), ("highl_norm_first_call", C.c_int),
                 ("max_points", C.c_int), ("chunk_points", C.c_int), ("n_tau_max", C.c_int), ("n_k_max", C.c_int),
-                ("n_q_max", C.c_int)]
+                ("n_q_max", C.c_int), ("n_tau_max_tensor", C.c_int), ("n_k_max_tensor", C.c_int),
+                ("n_q_max_tensor", C.c_int)]
 
 
 class Info(C.Structure):
     _fields_ = [(n, C.c_int) for n in
                 ["max_l", "max_eta_k", "max_l_tensor", "max_eta_k_tensor", "n_lsamp", "n_lsamp_tensor", "num_xx",
                  "lmax_lensed", "lens_lmax", "lens_npoints", "lens_jmax", "n_tau_max", "n_k_max", "n_q_max",
-                 "max_points", "chunk_points"]]
+                 "max_points", "chunk_points", "num_xx_tensor"]]
 
 
 class Timing(C.Structure):
@@ -83,6 +84,7 @@ def load():
     L.cb200_get_bessel_table.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_dp]
     L.cb200_upload_sources.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_dp, C.c_void_p, C.c_int]
     L.cb200_powers.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip]
+    L.cb200_powers_shared.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip]
     L.cb200_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_ip]
     L.cb200_keep_transfers.argtypes = [C.c_void_p, C.c_int]
     L.cb200_like_add_pliklite.argtypes = [C.c_void_p, c_ip, C.c_int, c_ip, c_ip, c_dp, C.c_int, c_dp, c_dp, C.c_int,
@@ -215,8 +217,9 @@ class Handle:
 
     def bessel_table(self, kind=0):
         nl = self.info.n_lsamp if kind == 0 else self.info.n_lsamp_tensor
-        x = np.zeros(self.info.num_xx)
-        ajl = np.zeros((nl, self.info.num_xx))
+        nx = self.info.num_xx if kind == 0 else self.info.num_xx_tensor
+        x = np.zeros(nx)
+        ajl = np.zeros((nl, nx))
         ajlpr = np.zeros_like(ajl)
         self._check(self.L.cb200_get_bessel_table(self.h, kind, _pd(x), _pd(ajl), _pd(ajlpr)), "get_bessel_table")
         return x, ajl, ajlpr
@@ -227,7 +230,9 @@ class Handle:
         npts = len(thermo)
         n_k = _i(n_k)
         k = _d(k)
-        assert k.shape == (npts, self.info.n_k_max), (k.shape, self.info.n_k_max)
+        nkm = self.cfg.n_k_max_tensor if kind == 1 else self.info.n_k_max
+        ntm = self.cfg.n_tau_max_tensor if kind == 1 else self.info.n_tau_max
+        assert k.shape == (npts, nkm), (k.shape, nkm)
         if src_device_ptr is not None:
             ptr, isdev = C.c_void_p(src_device_ptr), 1
         elif src_host_ptr is not None:  # caller-owned (e.g. pinned) host buffer with the padded layout
@@ -236,7 +241,7 @@ class Handle:
             ptr, isdev = None, 0
         else:
             src = _d(src)
-            assert src.shape == (npts, self.info.n_tau_max, 3, self.info.n_k_max), src.shape
+            assert src.shape == (npts, ntm, 3, nkm), src.shape
             self._keep = src
             ptr, isdev = C.c_void_p(src.ctypes.data), 0
         self._check(self.L.cb200_upload_sources(self.h, kind, first, npts, _pd(thermo), _pi(n_k), _pd(k), ptr, isdev),
@@ -253,6 +258,19 @@ class Handle:
         st = np.zeros(npts, dtype=np.int32)
         self._check(self.L.cb200_powers(self.h, first, npts, _pd(ip), _pd(al), _pd(ap), _pd(cls), _pd(der), _pi(st)),
                     "powers")
+        return cls, der, st
+
+    def powers_shared(self, initpower, alens=None, aphiphi=None, src_point=0, first=0, want_cls=True):
+        """Semi-slow step with one shared source point and many initial-power points (BK15-style chains)."""
+        ip = _d(initpower).reshape(-1, 10)
+        npts = len(ip)
+        al = _d(alens) if alens is not None else None
+        ap = _d(aphiphi) if aphiphi is not None else None
+        cls = np.zeros((npts, 5, self.cfg.lmax_out + 1)) if want_cls else None
+        der = np.zeros((npts, 4)) if want_cls else None
+        st = np.zeros(npts, dtype=np.int32) if want_cls else None
+        self._check(self.L.cb200_powers_shared(self.h, src_point, first, npts, _pd(ip), _pd(al), _pd(ap), _pd(cls),
+                                               _pd(der), _pi(st)), "powers_shared")
         return cls, der, st
 
     def powers_resident(self, initpower, alens=None, aphiphi=None, first=0):

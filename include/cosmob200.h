@@ -39,6 +39,7 @@ typedef struct cb200_config {
   int max_points;            /* capacity of resident source storage (points) */
   int chunk_points;          /* points processed per internal pass (work-buffer size); 0 = auto */
   int n_tau_max, n_k_max, n_q_max; /* capacities per point; 0 = defaults 768 / 256 / 3072 */
+  int n_tau_max_tensor, n_k_max_tensor, n_q_max_tensor; /* same for the tensor pass; 0 = 2304 / 128 / 1024 */
 } cb200_config;
 
 typedef struct cb200_info {
@@ -51,6 +52,7 @@ typedef struct cb200_info {
   int lens_npoints;            /* theta samples actually integrated (camb/lensing.f90:163-177) */
   int lens_jmax;               /* sampled l in the correlation sums (camb/lensing.f90:183-189) */
   int n_tau_max, n_k_max, n_q_max, max_points, chunk_points;
+  int num_xx_tensor;           /* Bessel abscissae of the tensor pass (kmax = Max_eta_k_tensor) */
 } cb200_info;
 
 void cb200_default_config(cb200_config* cfg);
@@ -105,9 +107,18 @@ int cb200_upload_sources(cb200_handle* h, int kind, int first, int npts, const d
 int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, const double* alens,
                  const double* aphiphi, double* cls_out, double* derived_out, int* status);
 
+/* Same step when the transfer functions are SHARED by the whole batch: CosmoMC calls GetNewPowerData without
+ * GetNewTransferData when only the initial-power block moved (source/CalcLike_Cosmology.f90:73-85; e.g. BK15 chains
+ * at fixed cosmology).  Sources of resident point `src_point` (scalar, and tensor when compute_tensors) are projected
+ * once, the k-contraction of the npts initial-power points is one FP64 tensor-pipe GEMM; outputs go to the resident
+ * slots [first, first+npts). */
+int cb200_powers_shared(cb200_handle* h, int src_point, int first, int npts, const double* initpower,
+                        const double* alens, const double* aphiphi, double* cls_out, double* derived_out, int* status);
+
 /* Intermediate read-backs for parity tests (device -> host copies of the last cb200_powers call):
  *   what: 0 iCl [6][n_lsamp], 1 Cl_scalar [6][max_l+1], 2 Cl_lensed [4][max_l+1] (dimensionless),
- *         3 transfers Delta [n_q][n_lsamp_pad][3] (only if cb200_keep_transfers(h,1)), 4 q, 5 dq, 6 tau, 7 dtau */
+ *         3 transfers Delta [n_q][n_lsamp_pad][3] (only if cb200_keep_transfers(h,1)), 4 q, 5 dq, 6 tau, 7 dtau,
+ *         8 tensor iCl [4][n_lsamp_tensor], 9 Cl_tensor [4][lmax_tensor+1] TT,EE,BB,TE (dimensionless) */
 int cb200_debug_fetch(cb200_handle* h, int what, int point, int max_n, double* out, int* n);
 int cb200_keep_transfers(cb200_handle* h, int on);
 

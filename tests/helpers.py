@@ -73,3 +73,73 @@ def oracle_point(batch, i, bessel, ls, tmpl_unl, highl_lensed, keep=False):
     if keep:
         res["Delta"] = Delta
     return res
+
+
+# ---- tensor pass (CAMB's second pass: Max_l_tensor = 600, Max_eta_k_tensor = 1500) -------------------------------
+MAX_L_T = 600
+MAX_ETA_K_T = 1500
+
+
+def small_batch_tensor(thermo, seed=7, NT=2304, NK=128):
+    """Synthetic tensor sources (T, E, B shaped stand-ins) on the ORACLE's tensor grids for the given thermo rows."""
+    import pyoracle as o
+    from cosmomc_b200 import synthetic as syn
+    npts = len(thermo)
+    rng = np.random.default_rng(seed + 100)
+    pert = rng.normal(0.0, 1.0, (npts, 6))
+    tau = np.zeros((npts, NT))
+    k = np.zeros((npts, NK))
+    n_tau = np.zeros(npts, dtype=np.int32)
+    n_k = np.zeros(npts, dtype=np.int32)
+    for i in range(npts):
+        th = thermo[i]
+        t, dt = o.time_steps(th[1], th[2], th[0], MAX_ETA_K_T, True, th[3], th[4])
+        kk = o.source_k(th[0], th[1], MAX_ETA_K_T, True, MAX_L_T)
+        n_tau[i], n_k[i] = len(t), len(kk)
+        tau[i, :len(t)] = t
+        tau[i, len(t):] = t[-1]
+        k[i, :len(kk)] = kk
+        k[i, len(kk):] = kk[-1]
+    src = 1e-3 * syn.make_sources(thermo, tau, k, pert).numpy()
+    return dict(thermo=thermo, tau=tau, k=k, n_tau=n_tau, n_k=n_k, src=src)
+
+
+def oracle_tensor_point(tb, i, bessel_t, ls_t, ip):
+    """tensor pass of point i: Delta, iCl_tensor [4][47], Cl_tensor [4][601] (TT, EE, BB, TE; dimensionless)"""
+    import pyoracle as o
+    th = tb["thermo"][i]
+    nt, nk = tb["n_tau"][i], tb["n_k"][i]
+    src = np.ascontiguousarray(tb["src"][i, :nt, :, :nk])
+    q, dq, Delta, triples = o.project(bessel_t, th[0], th[1], th[2], th[3], th[4], MAX_ETA_K_T, MAX_L_T, True,
+                                      tb["k"][i, :nk], src)
+    iCl = o.calc_cls(q, dq, ls_t, Delta, ip, 1.0, tensors=True)
+    cl = np.zeros((4, MAX_L_T + 1))
+    for X in range(4):
+        cl[X, :] = o.interp_cl(ls_t, iCl[X])[:MAX_L_T + 1]
+    return dict(q=q, iCl=iCl, cl=cl, triples=triples)
+
+
+def oracle_point_with_tensors(batch, i, bessel, ls, tmpl_unl, highl_lensed, cl_tensor, ip=None, alens=None):
+    """scalar chain of point i with initial power `ip`, tensors added in SetPowersFromCAMB"""
+    import pyoracle as o
+    th = batch["thermo"][i]
+    nt, nk = batch["n_tau"][i], batch["n_k"][i]
+    src = np.ascontiguousarray(batch["src"][i, :nt, :, :nk])
+    q, dq, Delta, triples = o.project(bessel, th[0], th[1], th[2], th[3], th[4], MAX_ETA_K, MAX_L, False,
+                                      batch["k"][i, :nk], src)
+    return oracle_from_delta(q, dq, Delta, ls, tmpl_unl, highl_lensed, batch["initpower"][i] if ip is None else ip,
+                             batch["alens"][i] if alens is None else alens, cl_tensor)
+
+
+def oracle_from_delta(q, dq, Delta, ls, tmpl_unl, highl_lensed, ip, alens, cl_tensor=None):
+    import pyoracle as o
+    iCl = o.calc_cls(q, dq, ls, Delta, ip, alens)
+    cl = np.zeros((6, MAX_L + 1))
+    for X in range(6):
+        cl[X, :] = o.interp_cl(ls, iCl[X], template_index=X + 1 if X < 3 else 0, tmpl=tmpl_unl)[:MAX_L + 1]
+    lensed = o.lens_cls(ls, MAX_L, np.stack([cl[0], cl[1], cl[2], cl[3]]), tmpl_unl)
+    lens_pad = np.zeros((4, MAX_L + 1))
+    lens_pad[:, :lensed.shape[1]] = lensed
+    out, hn, rms = o.set_powers(lens_pad, cl[3], LMAX_COMPUTED, [LMAX_OUT] * 5, highl_lensed, lmax_out=LMAX_OUT,
+                                cl_tensor=cl_tensor, lmax_tensor=MAX_L_T if cl_tensor is not None else 0)
+    return dict(iCl=iCl, cl=cl, cls_out=out, rms=rms)
