@@ -13,6 +13,7 @@
 #include "like.cuh"
 #include "background.cuh"
 #include "sn.cuh"
+#include "bk.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -79,6 +80,10 @@ struct LikeEntry {
   DevBuf<double> Wt_cmb, Wt_pp, offset, noise, chat, sqrt_fid;
   DevBuf<int> cl_use;
   bool has_noise = false, has_sqrt_fid = false;
+  // BK foreground model attached to a cmblikes entry (TBK_planck extends TCMBLikes)
+  bool has_fg = false;
+  BkParams bk{};
+  DevBuf<double> bk_nu, bk_R, bk_dnu, bk_fgW;
 };
 
 enum Phase { PH_SPLINE = 0, PH_PROJECT, PH_CONTRACT, PH_INTERP, PH_LENS, PH_LIKE, PH_BG, PH_COUNT };
@@ -1064,6 +1069,38 @@ int cb200_like_add_cmblikes(cb200_handle* h, int nmaps, int nbins, int ncl_used,
   CB_API_END(h)
 }
 
+int cb200_like_set_bk_foregrounds(cb200_handle* h, int like_id, int nmaps, const int* map_field, const int* bc_class,
+                                  const int* bp_offset, const double* bp_nu, const double* bp_R, const double* bp_dnu,
+                                  const double* th_dust, const double* th_sync, const double* nu_bar, double fpivot_dust,
+                                  double fpivot_sync, const double* fpivot_dust_decorr, const double* fpivot_sync_decorr,
+                                  int lform_dust, int lform_sync, int lmin, int lmax, const double* fgW, int nuis_offset) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (like_id < 0 || like_id >= (int)h->likes.size() || h->likes[like_id]->type != 2)
+    return fail(h, "bk_foregrounds: like_id is not a cmblikes likelihood");
+  LikeEntry& L = *h->likes[like_id];
+  if (nmaps != L.nmaps || nmaps > BK_MAXMAPS) return fail(h, "bk_foregrounds: map count mismatch");
+  if (lmax + 1 > BK_MAXL || lmax != L.lmax_w || lmin < 1) return fail(h, "bk_foregrounds: multipole range not supported");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  BkParams& b = L.bk;
+  b.nmaps = nmaps; b.nbins = L.nbins; b.ncl = L.ncl; b.lmin = lmin; b.lmax = lmax; b.nuis_off = nuis_offset;
+  b.lform_dust = lform_dust; b.lform_sync = lform_sync;
+  b.fpivot_dust = fpivot_dust; b.fpivot_sync = fpivot_sync;
+  for (int k = 0; k < 2; k++) { b.fp_dust_decorr[k] = fpivot_dust_decorr[k]; b.fp_sync_decorr[k] = fpivot_sync_decorr[k]; }
+  for (int i = 0; i < nmaps; i++) {
+    b.field[i] = map_field[i]; b.bc_class[i] = bc_class[i]; b.bp_off[i] = bp_offset[i];
+    b.th_dust[i] = th_dust[i]; b.th_sync[i] = th_sync[i]; b.nu_bar[i] = nu_bar[i];
+  }
+  b.bp_off[nmaps] = bp_offset[nmaps];
+  const size_t nb = bp_offset[nmaps];
+  L.bk_nu.upload(bp_nu, nb, h->stream); L.bk_R.upload(bp_R, nb, h->stream); L.bk_dnu.upload(bp_dnu, nb, h->stream);
+  L.bk_fgW.upload(fgW, (size_t)L.nbins * L.ncl * (lmax + 1), h->stream);
+  CB_CUDA(cudaStreamSynchronize(h->stream));
+  L.has_fg = true;
+  return 0;
+  CB_API_END(h)
+}
+
 // ---------------------------------------------------------------------------------- background + its likelihoods
 int cb200_set_background(cb200_handle* h, int first, int npts, const double* bg) {
   if (!h) return -1;
@@ -1290,6 +1327,15 @@ static int loglike_device(cb200_handle* h, int bg_first, int npts, const double*
         dgemm(s, false, false, npts, nb, 4 * LO, 1.0, d_cls, 5 * LO, L.Wt_cmb.p, nb, h->w_bc.p, nb, &h->n_launches);
         dgemm(s, false, false, npts, nb, LO, 1.0, d_cls + (size_t)4 * LO, 5 * LO, L.Wt_pp.p, nb, h->w_bp.p, nb,
               &h->n_launches);
+        if (L.has_fg) {
+          if (L.bk.nuis_off + 16 > n_nuis) return fail(h, "loglike: BK foreground parameters outside the nuisance vector");
+          BkParams bk = L.bk;
+          bk.np = npts; bk.n_nuis = n_nuis; bk.nuis = h->w_nuis.p; bk.binned = h->w_bc.p;
+          bk.bp_nu = L.bk_nu.p; bk.bp_R = L.bk_R.p; bk.bp_dnu = L.bk_dnu.p; bk.fgW = L.bk_fgW.p;
+          bk_foreground_kernel<<<npts, 256, 0, s>>>(bk);
+          CB_LAUNCH_CHECK();
+          h->n_launches += 1;
+        }
         CmbLikesBinParams cp;
         cp.np = npts; cp.nmaps = L.nmaps; cp.ncl = L.ncl; cp.nbins = L.nbins; cp.ncl_used = L.ncl_used;
         cp.like_approx = L.like_approx; cp.n_nuis = n_nuis; cp.cal_index = L.cal_index;

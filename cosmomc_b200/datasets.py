@@ -119,12 +119,19 @@ def _top_comment(path):
 class CMBLikesPlan:
     """Dense form of a binned CMBlikes data set (gaussian or HL), ready for cb200_like_add_cmblikes."""
 
-    def __init__(self, dataset_path, overrides=None):
+    def __init__(self, dataset_path, overrides=None, cov_provider=None):
+        """cov_provider: object with .block(rows, cols) standing in for the covmat_fiducial file when that blob is
+        missing from the reference checkout (BK15_covmat_dust.dat; cosmomc_b200/synthetic.py documents the stand-in)."""
         ini = IniFile(dataset_path)
         if overrides:
             ini.params.update(overrides)
         self.name = os.path.basename(dataset_path)
+        self.cov_provider = cov_provider
         self._read(ini)
+        self._read_extra(ini)
+
+    def _read_extra(self, ini):
+        pass
 
     # -- naming helpers (CMBlikes.f90:196-330)
     def _pair_to_maps(self, s):
@@ -286,15 +293,19 @@ class CMBLikesPlan:
         self.ncl_used = len(used)
         self.cl_use_index = np.array([ix for _, ix in used], dtype=np.int32)
         cov_cl_used = np.array([k for k, _ in used], dtype=int)
-        full_cov = np.loadtxt(ini.relative_file("covmat_fiducial"))
         scale = ini.float("covmat_scale", 1.0)
         num_in = len(cl_in_index)
         n = nb * self.ncl_used
         cov = np.zeros((n, n))
-        for bx in range(nb):
-            for by in range(nb):
-                cov[bx * self.ncl_used:(bx + 1) * self.ncl_used, by * self.ncl_used:(by + 1) * self.ncl_used] = \
-                    scale * full_cov[np.ix_((bx + self.bin_min) * num_in + cov_cl_used, (by + self.bin_min) * num_in + cov_cl_used)]
+        if self.cov_provider is not None:
+            rows = np.concatenate([(bx + self.bin_min) * num_in + cov_cl_used for bx in range(nb)])
+            cov = scale * self.cov_provider.block(rows, rows)
+        else:
+            full_cov = np.loadtxt(ini.relative_file("covmat_fiducial"))
+            for bx in range(nb):
+                for by in range(nb):
+                    cov[bx * self.ncl_used:(bx + 1) * self.ncl_used, by * self.ncl_used:(by + 1) * self.ncl_used] = \
+                        scale * full_cov[np.ix_((bx + self.bin_min) * num_in + cov_cl_used, (by + self.bin_min) * num_in + cov_cl_used)]
         self.cov = cov
         inv = np.linalg.inv(cov)
         self.invcov = 0.5 * (inv + inv.T)
@@ -515,3 +526,109 @@ class SNPlan:
         if not self.alphabeta_covmat:
             alpha_index = beta_index = -1
         return handle.add_sn(self.columns(), covs, self.A1, self.A2, self.twoscriptmfit, alpha_index, beta_index)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BICEP/Keck (source/CMB_BK_Planck.f90): TBK_planck_ReadIni (:36-70), TBK_planck_Read_Bandpass (:72-105)
+BK_T_CMB = 2.72548
+BK_GHZ_KELVIN = 6.62606957e-34 / 1.3806488e-23 * 1e9
+LFORM = {"flat": 0, "lin": 1, "quad": 2}
+
+
+def read_bandpass(fname, fpivot_dust, fpivot_sync):
+    R = np.loadtxt(fname)
+    nu = R[:, 0]
+    n = len(nu)
+    dnu = np.zeros(n)
+    dnu[0] = nu[1] - nu[0]
+    dnu[1:n - 1] = (nu[2:] - nu[:n - 2]) / 2
+    dnu[n - 1] = nu[n - 1] - nu[n - 2]
+    ex = np.exp(BK_GHZ_KELVIN * nu / BK_T_CMB)
+    th_int = np.sum(dnu * R[:, 1] * nu ** 4 * ex / (ex - 1) ** 2)
+
+    def th0(nu0):
+        e = np.exp(BK_GHZ_KELVIN * nu0 / BK_T_CMB)
+        return nu0 ** 4 * e / (e - 1) ** 2
+    nu_bar = np.sum(dnu * nu * R[:, 1]) / np.sum(dnu * R[:, 1])
+    return dict(nu=nu, R=R[:, 1].copy(), dnu=dnu, th_dust=th_int / th0(fpivot_dust), th_sync=th_int / th0(fpivot_sync),
+                nu_bar=nu_bar)
+
+
+class BK15Plan(CMBLikesPlan):
+    """BK15-style data set: generic binned HL CMBlikes + the foreground model of TBK_planck."""
+
+    def _read_extra(self, ini):
+        self.fpivot_dust = ini.float("fpivot_dust", 353.0)
+        self.fpivot_sync = ini.float("fpivot_sync", 23.0)
+        self.fpivot_dust_decorr = [ini.float("fpivot_dust_decorr(1)", 217.0), ini.float("fpivot_dust_decorr(2)", 353.0)]
+        self.fpivot_sync_decorr = [ini.float("fpivot_sync_decorr(1)", 23.0), ini.float("fpivot_sync_decorr(2)", 33.0)]
+        self.lform_dust = LFORM.get(ini.string("lform_dust_decorr", "flat"), 0)
+        self.lform_sync = LFORM.get(ini.string("lform_sync_decorr", "flat"), 0)
+        if self.nmaps != self.nmaps_required:
+            raise NotImplementedError("BK foregrounds with maps_required beyond maps_use")
+        self.bandpasses = [read_bandpass(ini.relative_file("bandpass[%s]" % m), self.fpivot_dust, self.fpivot_sync)
+                           for m in self.used_map_order]
+        self.bc_class = [1 if "95" in m else 2 if "150" in m else 3 if "220" in m else 0 for m in self.used_map_order]
+        self.used_fields = [self.map_fields[self.map_names.index(m)] for m in self.used_map_order]
+        # band-power window of every used map pair on its own EE / BB spectrum (what the foreground model is binned with)
+        fgW = np.zeros((self.nbins_used, self.ncl, self.lmax_w + 1))
+        ix = 0
+        for i in range(self.nmaps):
+            for j in range(i + 1):
+                fi, fj = self.used_fields[i], self.used_fields[j]
+                if fi == fj and fi in (1, 2):
+                    fgW[:, ix, :] = self.W[:, ix, SPEC_SLOT[(fi, fi)], :]
+                ix += 1
+        self.fgW = fgW
+
+    def register(self, handle, nuis_offset=0, cal_index=-1):
+        lid = CMBLikesPlan.register(self, handle, cal_index)
+        handle.set_bk_foregrounds(lid, self.used_fields, self.bc_class,
+                                  [(b["nu"], b["R"], b["dnu"]) for b in self.bandpasses],
+                                  [b["th_dust"] for b in self.bandpasses], [b["th_sync"] for b in self.bandpasses],
+                                  [b["nu_bar"] for b in self.bandpasses], self.fpivot_dust, self.fpivot_sync,
+                                  self.fpivot_dust_decorr, self.fpivot_sync_decorr, self.lform_dust, self.lform_sync,
+                                  self.pcl_lmin, self.pcl_lmax, self.fgW, nuis_offset)
+        return lid
+
+    # ---- compact fixture (tests / bench on the GPU box have no reference tree)
+    PACK_KEYS = ["nmaps", "nbins_used", "ncl", "ncl_used", "like_approx", "lmax_w", "pcl_lmin", "pcl_lmax", "cl_use_index",
+                 "offset", "chat", "noise", "sqrt_fid", "fgW", "used_fields", "bc_class", "fpivot_dust", "fpivot_sync",
+                 "fpivot_dust_decorr", "fpivot_sync_decorr", "lform_dust", "lform_sync", "cov"]
+
+    def save_pack(self, path):
+        d = {k: np.asarray(getattr(self, k)) for k in self.PACK_KEYS}
+        d["used_map_order"] = np.array(self.used_map_order)
+        for i, b in enumerate(self.bandpasses):
+            for k, v in b.items():
+                d["bp%d_%s" % (i, k)] = np.asarray(v)
+        np.savez_compressed(path, **d)
+
+    @classmethod
+    def from_pack(cls, path):
+        z = np.load(path)
+        self = cls.__new__(cls)
+        for k in cls.PACK_KEYS:
+            v = z[k]
+            setattr(self, k, v.item() if v.ndim == 0 else v)
+        for k in ("nmaps", "nbins_used", "ncl", "ncl_used", "like_approx", "lmax_w", "pcl_lmin", "pcl_lmax", "lform_dust", "lform_sync"):
+            setattr(self, k, int(getattr(self, k)))
+        self.used_map_order = [str(x) for x in z["used_map_order"]]
+        self.used_fields = [int(x) for x in self.used_fields]
+        self.bc_class = [int(x) for x in self.bc_class]
+        self.bandpasses = [{k: (z["bp%d_%s" % (i, k)] if z["bp%d_%s" % (i, k)].ndim else float(z["bp%d_%s" % (i, k)]))
+                            for k in ("nu", "R", "dnu", "th_dust", "th_sync", "nu_bar")} for i in range(self.nmaps)]
+        self.nmaps_required = self.nmaps
+        inv = np.linalg.inv(self.cov)
+        self.invcov = 0.5 * (inv + inv.T)
+        self.log_cal_prior = -1.0
+        W = np.zeros((self.nbins_used, self.ncl, 5, self.lmax_w + 1))
+        ix = 0
+        for i in range(self.nmaps):
+            for j in range(i + 1):
+                fi, fj = self.used_fields[i], self.used_fields[j]
+                if fi == fj and fi in (1, 2):
+                    W[:, ix, SPEC_SLOT[(fi, fi)], :] = self.fgW[:, ix, :]
+                ix += 1
+        self.W = W
+        return self

@@ -25,7 +25,7 @@ EXPORTS = [
     "cb200_debug_fetch", "cb200_keep_transfers", "cb200_like_add_pliklite", "cb200_like_add_cmblikes",
     "cb200_loglike_batch", "cb200_loglike_cls", "cb200_get_timing", "cb200_sync", "cb200_set_option",
     "cb200_timer_start", "cb200_timer_stop", "cb200_measure_fp64_peaks",
-    "cb200_powers_shared", "cb200_background", "cb200_set_background", "cb200_like_add_bao", "cb200_like_add_hst", "cb200_like_add_sn",
+    "cb200_powers_shared", "cb200_like_set_bk_foregrounds", "cb200_background", "cb200_set_background", "cb200_like_add_bao", "cb200_like_add_hst", "cb200_like_add_sn",
 ]
 
 
@@ -99,6 +99,9 @@ def load():
     L.cb200_timer_start.argtypes = [C.c_void_p]
     L.cb200_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.cb200_measure_fp64_peaks.argtypes = [C.c_void_p, c_dp, c_dp]
+    L.cb200_like_set_bk_foregrounds.argtypes = [C.c_void_p, C.c_int, C.c_int, c_ip, c_ip, c_ip, c_dp, c_dp, c_dp, c_dp,
+                                                c_dp, c_dp, C.c_double, C.c_double, c_dp, c_dp, C.c_int, C.c_int,
+                                                C.c_int, C.c_int, c_dp, C.c_int]
     L.cb200_background.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp, c_dp]
     L.cb200_set_background.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp]
     L.cb200_like_add_bao.argtypes = [C.c_void_p, C.c_int, C.c_int, c_ip, c_dp, c_dp, c_dp, C.c_double, C.c_double,
@@ -320,6 +323,22 @@ class Handle:
             C.byref(lid)), "like_add_cmblikes")
         self.n_like += 1
         return lid.value
+
+    def set_bk_foregrounds(self, like_id, map_field, bc_class, bandpasses, th_dust, th_sync, nu_bar, fpivot_dust,
+                           fpivot_sync, fpivot_dust_decorr, fpivot_sync_decorr, lform_dust, lform_sync, lmin, lmax, fgW,
+                           nuis_offset):
+        """bandpasses: list of (nu, R, dnu) arrays per used map."""
+        off = np.zeros(len(bandpasses) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(b[0]) for b in bandpasses])
+        nu = _d(np.concatenate([b[0] for b in bandpasses]))
+        R = _d(np.concatenate([b[1] for b in bandpasses]))
+        dnu = _d(np.concatenate([b[2] for b in bandpasses]))
+        fgW = _d(fgW)
+        self._check(self.L.cb200_like_set_bk_foregrounds(
+            self.h, like_id, len(bandpasses), _pi(_i(map_field)), _pi(_i(bc_class)), _pi(off), _pd(nu), _pd(R), _pd(dnu),
+            _pd(_d(th_dust)), _pd(_d(th_sync)), _pd(_d(nu_bar)), fpivot_dust, fpivot_sync, _pd(_d(fpivot_dust_decorr)),
+            _pd(_d(fpivot_sync_decorr)), lform_dust, lform_sync, lmin, lmax, _pd(fgW), nuis_offset),
+            "like_set_bk_foregrounds")
 
     # ---- background functions and likelihoods
     def background(self, bg, z, want_scalars=False):

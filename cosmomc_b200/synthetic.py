@@ -189,3 +189,30 @@ def synthetic_sn_covs(lc, names=("mag", "stretch", "colour", "mag_stretch", "mag
         else:
             out[nm] = basis[nm] @ basis[nm].T
     return out
+
+
+class LowRankCov:
+    """cov = diag(d) + U U^T, addressed by index blocks (stand-in for a covariance file that is too big / missing)."""
+
+    def __init__(self, d, U):
+        self.d, self.U = np.asarray(d), np.asarray(U)
+
+    def block(self, rows, cols):
+        out = self.U[rows] @ self.U[cols].T
+        same = np.asarray(rows)[:, None] == np.asarray(cols)[None, :]
+        out[same] += self.d[np.asarray(rows)][np.where(same)[0]]
+        return out
+
+    def full(self):
+        return np.diag(self.d) + self.U @ self.U.T
+
+
+def synthetic_bk15_cov(scale_per_entry, seed=15, rank=40, frac=0.12):
+    """Documented stand-in for data/BK15/BK15_covmat_dust.dat (MISSING from the reference checkout): band-power
+    covariance over all (bin, spectrum) entries of the data set, sigma = frac * scale (|fiducial| + |noise| of that
+    entry) on the diagonal plus a rank-`rank` correlated part of comparable size."""
+    rng = np.random.default_rng(seed)
+    sc = np.asarray(scale_per_entry, dtype=np.float64).reshape(-1)
+    sig = frac * sc + 1e-6 * sc.max()
+    U = rng.normal(0.0, 1.0, (len(sc), rank)) * (0.5 * sig[:, None] / np.sqrt(rank))
+    return LowRankCov(sig ** 2, U)

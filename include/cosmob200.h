@@ -149,6 +149,20 @@ int cb200_like_add_cmblikes(cb200_handle* h, int nmaps, int nbins, int ncl_used,
                             int cal_index /* position of the calibration parameter in the nuisance vector, -1 none */,
                             int* like_id);
 
+/* BICEP/Keck foreground model attached to a registered cmblikes likelihood (TBK_planck extends TCMBLikes and
+ * overrides AddForegrounds, source/CMB_BK_Planck.f90:21-31,229-340): dust + synchrotron + correlated component with
+ * bandpass-integrated frequency scalings (:109-183), band-centre errors and optional decorrelation (:187-227).
+ *   map_field [nmaps] 0-based theory field of each used map (1 = E, 2 = B); bc_class [nmaps] 0 none / 1 '95' / 2 '150' /
+ *   3 '220' (which gamma_* parameter applies, :266-274); bandpasses concatenated: bp_offset [nmaps+1], bp_nu / bp_R /
+ *   bp_dnu; th_dust, th_sync, nu_bar [nmaps] from TBK_planck_Read_Bandpass (:72-105);
+ *   lform_*: 0 flat, 1 lin, 2 quad; fgW [nbins][ncl][lmax+1] the band-power window of every map pair (zero for pairs
+ *   that are not EE or BB); nuis_offset: position of BBdust (first of the 16 BK15.paramnames) in the nuisance vector. */
+int cb200_like_set_bk_foregrounds(cb200_handle* h, int like_id, int nmaps, const int* map_field, const int* bc_class,
+                                  const int* bp_offset, const double* bp_nu, const double* bp_R, const double* bp_dnu,
+                                  const double* th_dust, const double* th_sync, const double* nu_bar, double fpivot_dust,
+                                  double fpivot_sync, const double* fpivot_dust_decorr, const double* fpivot_sync_decorr,
+                                  int lform_dust, int lform_sync, int lmin, int lmax, const double* fgW, int nuis_offset);
+
 /* ---- background functions and background-only likelihoods ---------------------------------------------
  * bg [npts][16] per point = H0, omegab, omegac, omegan, omegav, w, tcmb, nu_massless_degeneracy, n_eigenstates,
  *   nu_mass_degeneracies[3], nu_mass_fractions[3], rdrag  — i.e. what CAMBCalc_CMBToCAMB + CAMBParams_Set hold in

@@ -434,3 +434,87 @@ class SN:
         L = self.lc
         lumdists = 5.0 * np.log10((1.0 + L["zhel"]) * (1.0 + L["zcmb"]) * DA)
         return self.alpha_beta_like(lumdists, alpha, beta)
+
+
+# ---------------------------------------------------------------- BICEP/Keck foregrounds (source/CMB_BK_Planck.f90)
+_BK_T_CMB = 2.72548
+_BK_GK = 6.62606957e-34 / 1.3806488e-23 * 1e9
+
+
+def bk_dust_scaling(beta, Tdust, bp, nu0, bcerr):
+    """DustScaling (:109-147). bp: dict nu, R, dnu, th_dust, nu_bar."""
+    nu = bp["nu"]
+    gb_int = np.sum(bp["dnu"] * bp["R"] * nu ** (3 + beta) / (np.exp(_BK_GK * nu / Tdust) - 1))
+    gb0 = nu0 ** (3 + beta) / (np.exp(_BK_GK * nu0 / Tdust) - 1)
+    th_err = gb_err = 1.0
+    if bcerr != 1.:
+        nb = bp["nu_bar"]
+        th_err = bcerr ** 4 * np.exp(_BK_GK * nb * (bcerr - 1) / _BK_T_CMB) * (np.exp(_BK_GK * nb / _BK_T_CMB) - 1) ** 2 / \
+            (np.exp(_BK_GK * nb * bcerr / _BK_T_CMB) - 1) ** 2
+        gb_err = bcerr ** (3 + beta) * (np.exp(_BK_GK * nb / Tdust) - 1) / (np.exp(_BK_GK * nb * bcerr / Tdust) - 1)
+    return (gb_int / gb0) / bp["th_dust"] * (gb_err / th_err)
+
+
+def bk_sync_scaling(beta, bp, nu0, bcerr):
+    """SyncScaling (:151-183)"""
+    nu = bp["nu"]
+    pl_int = np.sum(bp["dnu"] * bp["R"] * nu ** (2 + beta))
+    pl0 = nu0 ** (2 + beta)
+    th_err = pl_err = 1.0
+    if bcerr != 1.:
+        nb = bp["nu_bar"]
+        th_err = bcerr ** 4 * np.exp(_BK_GK * nb * (bcerr - 1) / _BK_T_CMB) * (np.exp(_BK_GK * nb / _BK_T_CMB) - 1) ** 2 / \
+            (np.exp(_BK_GK * nb * bcerr / _BK_T_CMB) - 1) ** 2
+        pl_err = bcerr ** (2 + beta)
+    return (pl_int / pl0) / bp["th_sync"] * (pl_err / th_err)
+
+
+def bk_decorrelation(Delta, nu0, nu1, nupivot, l, lform):
+    """Decorrelation (:187-227); lform 0 flat / 1 lin / 2 quad; l array"""
+    scl_nu = np.log(nu0 / nu1) ** 2 / np.log(nupivot[0] / nupivot[1]) ** 2
+    scl_ell = np.ones_like(l, dtype=float) if lform == 0 else (l / 80.0) if lform == 1 else (l / 80.0) ** 2
+    if Delta > 1:
+        return 2.0 - np.exp(np.log(2.0 - Delta) * scl_nu * scl_ell)
+    return np.exp(np.log(Delta) * scl_nu * scl_ell)
+
+
+def bk_foregrounds(plan, P):
+    """TBK_planck_AddForegrounds (:229-340): foreground D_l added to every used map pair -> [ncl][lmax+1].
+    plan: cosmomc_b200.datasets.BK15Plan (set-up data only); P: the 16 BK15.paramnames values."""
+    Adust, Async, alphadust, betadust, Tdust, alphasync, betasync, corr, EEd, EEs, Dd, Ds = P[:12]
+    n = plan.nmaps
+    bcerr = [1.0 if c == 0 else P[12] + P[12 + c] + 1. for c in plan.bc_class]
+    fd = [bk_dust_scaling(betadust, Tdust, plan.bandpasses[i], plan.fpivot_dust, bcerr[i]) for i in range(n)]
+    fs = [bk_sync_scaling(betasync, plan.bandpasses[i], plan.fpivot_sync, bcerr[i]) for i in range(n)]
+    l = np.arange(plan.pcl_lmin, plan.pcl_lmax + 1).astype(float)
+    dustpow = Adust * (l / 80.0) ** alphadust
+    syncpow = Async * (l / 80.0) ** alphasync
+    dspow = corr * np.sqrt(Adust * Async) * (l / 80.0) ** ((alphadust + alphasync) / 2)
+    need_d, need_s = abs(Dd - 1) > 1e-5, abs(Ds - 1) > 1e-5
+    out = np.zeros((plan.ncl, plan.pcl_lmax + 1))
+    ix = 0
+    for i in range(n):
+        for j in range(i + 1):
+            fi, fj = plan.used_fields[i], plan.used_fields[j]
+            if fi == fj and fi in (1, 2):
+                dust, sync, ds = fd[i] * fd[j], fs[i] * fs[j], fd[i] * fs[j] + fs[i] * fd[j]
+                if fi == 1:
+                    dust, sync, ds = dust * EEd, sync * EEs, ds * np.sqrt(EEd * EEs)
+                dd = dsy = 1.0
+                if need_d and i != j:
+                    dd = bk_decorrelation(Dd, plan.bandpasses[i]["nu_bar"] * bcerr[i], plan.bandpasses[j]["nu_bar"] * bcerr[j],
+                                          plan.fpivot_dust_decorr, l, plan.lform_dust)
+                if need_s and i != j:
+                    dsy = bk_decorrelation(Ds, plan.bandpasses[i]["nu_bar"] * bcerr[i], plan.bandpasses[j]["nu_bar"] * bcerr[j],
+                                           plan.fpivot_sync_decorr, l, plan.lform_sync)
+                out[ix, plan.pcl_lmin:] = dust * dustpow * dd + sync * syncpow * dsy + ds * dspow
+            ix += 1
+    return out
+
+
+def bk_loglike(plan, cls, P):
+    """-lnL of a BK15-style data set: theory Cls [5][>=lmax+1] (CosmoMC units) + foregrounds -> binned -> HL chi^2/2"""
+    binned = plan.binned_theory(cls) + np.einsum("bcl,cl->bc", plan.fgW, bk_foregrounds(plan, P))
+    chi2 = cmblikes_chisq(plan.nmaps, plan.nbins_used, plan.cl_use_index, plan.like_approx, plan.noise, plan.chat,
+                          plan.sqrt_fid, plan.invcov, binned)
+    return chi2 / 2
