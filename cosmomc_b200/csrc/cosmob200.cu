@@ -9,6 +9,7 @@
 #include "project.cuh"
 #include "project2.cuh"
 #include "project3.cuh"
+#include "project4.cuh"
 #include "lens.cuh"
 #include "like.cuh"
 #include "background.cuh"
@@ -115,6 +116,7 @@ struct cb200_handle {
   bool count_triples = false, ring_stats = false;
   int proj_kernel = 3;
   DevBuf<unsigned long long> d_ring_stats;
+  DevBuf<unsigned char> w_fallback;  // [chunk][NQB] blocks left to the chunked kernel by project4_kernel
   // resident outputs
   DevBuf<double> r_cl_lensed, r_cls_out, r_derived, r_icl, r_cl;
   DevBuf<int> r_status;
@@ -316,6 +318,8 @@ void ensure_work(cb200_handle* h) {
   h->w_coef.alloc((size_t)C * 4 * NK);
   h->w_ddsrc.alloc((size_t)C * NTK * 3);
   h->w_part.alloc((size_t)C * NQB * 6 * PROJ_LP);
+  h->w_fallback.alloc((size_t)C * NQB);
+  h->w_fallback.zero(h->stream);
   if (tens) {
     h->w_clt.alloc((size_t)C * 4 * h->LST);
     h->r_icl_t.alloc((size_t)h->cfg.max_points * 6 * PROJ_LP);
@@ -435,8 +439,14 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
     CB_CUDA(cudaFuncSetAttribute(project2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
     CB_CUDA(cudaFuncSetAttribute(project3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
     CB_CUDA(cudaFuncSetAttribute(project3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
+    CB_CUDA(cudaFuncSetAttribute(project4_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
+    CB_CUDA(cudaFuncSetAttribute(project4_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
+    CB_CUDA(cudaFuncSetAttribute(project4_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
+    CB_CUDA(cudaFuncSetAttribute(project4_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
+    CB_CUDA(cudaFuncSetAttribute(project4_kernel<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
+    CB_CUDA(cudaFuncSetAttribute(project4_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
     const char* pk = std::getenv("CB200_PROJ_KERNEL");
-    if (pk && pk[0] >= '1' && pk[0] <= '3') h->proj_kernel = pk[0] - '0';
+    if (pk && pk[0] >= '1' && pk[0] <= '4') h->proj_kernel = pk[0] - '0';
   } catch (const std::exception& e) {
     std::fprintf(stderr, "cb200_create: %s\n", e.what());
     return -1;
@@ -663,6 +673,55 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       const size_t smem = std::max(META, RED) + sizeof(ProjQ) * PROJ_Q;
       dim3 grid((nq_max + PROJ_Q - 1) / PROJ_Q, np);
       project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB><<<grid, 32 * PROJ_LW * PROJ_NS, smem, s>>>(pp);
+    } else if (h->proj_kernel == 4) {
+      pl.q_per_block = W4_QC;
+      pl.nqb_total = (S.NQ + W4_QC - 1) / W4_QC;
+      Proj4Params pp;
+      pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB = pl.nqb_total; pp.tensors = kind;
+      static_assert(W3_QC >= W4_QC, "the fallback pass uses the same wavenumber blocks");
+      const int noct = (nl + 7) / 8;
+      const int LK = noct <= 6 ? 6 : noct <= 11 ? 11 : 12;
+      pp.zero = 0;
+      pp.rb = LK * 128;
+      pp.R = std::min(w4_ring_rows(LK, S.NT), 4096);
+      pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes = K.d_bes.p;
+      pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
+      pp.delta = d_delta;
+      pp.triples = h->count_triples ? h->d_triples.p : nullptr;
+      pp.ring_stats = h->ring_stats ? h->d_ring_stats.p : nullptr;
+      pp.fallback = h->w_fallback.p;
+      pp.bseg = K.bseg;
+      for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
+      dim3 grid((nq_max + W4_QC - 1) / W4_QC, np);
+      const bool cnt = h->count_triples || h->ring_stats;
+      const size_t smem = w4_smem_bytes(LK, S.NT, pp.R);
+      if (LK == 6) {
+        if (cnt) project4_kernel<6, true><<<grid, W4_NT, smem, s>>>(pp);
+        else project4_kernel<6, false><<<grid, W4_NT, smem, s>>>(pp);
+      } else if (LK == 11) {
+        if (cnt) project4_kernel<11, true><<<grid, W4_NT, smem, s>>>(pp);
+        else project4_kernel<11, false><<<grid, W4_NT, smem, s>>>(pp);
+      } else {
+        if (cnt) project4_kernel<12, true><<<grid, W4_NT, smem, s>>>(pp);
+        else project4_kernel<12, false><<<grid, W4_NT, smem, s>>>(pp);
+      }
+      CB_LAUNCH_CHECK();
+      // fallback pass: blocks whose table window does not fit the ring (the first, log-spaced wavenumber block)
+      Proj3Params p3;
+      p3.v = v; p3.p0 = p0; p3.nl = nl; p3.num_xx = K.num_xx; p3.NQB = pl.nqb_total; p3.tensors = kind;
+      p3.max_eta_k = K.max_eta_k; p3.ddsrc = h->w_ddsrc.p; p3.bx = K.d_bx.p; p3.bes3 = K.d_bes3.p;
+      p3.initpower = h->w_initpower.p; p3.part = h->w_part.p;
+      p3.delta = d_delta;
+      p3.triples = h->count_triples ? h->d_triples.p : nullptr;
+      p3.ring_stats = nullptr;
+      p3.need = h->w_fallback.p;
+      p3.qc_rt = W4_QC;
+      p3.bseg = K.bseg;
+      for (int i = 0; i < PROJ_LP; i++) p3.ls[i] = i < nl ? K.ls[i] : 0;
+      dim3 grid3((nq_max + W4_QC - 1) / W4_QC, (nl + 31) / 32, np);
+      if (h->count_triples) project3_kernel<true><<<grid3, 32 * W3_NW, W3_SMEM, s>>>(p3);
+      else project3_kernel<false><<<grid3, 32 * W3_NW, W3_SMEM, s>>>(p3);
+      h->n_launches += 1;
     } else if (h->proj_kernel == 3) {
       pl.q_per_block = W3_QC;
       pl.nqb_total = (S.NQ + W3_QC - 1) / W3_QC;
@@ -673,6 +732,7 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       pp.delta = d_delta;
       pp.triples = h->count_triples ? h->d_triples.p : nullptr;
       pp.ring_stats = h->ring_stats ? h->d_ring_stats.p : nullptr;
+      pp.need = nullptr; pp.qc_rt = 0;
       pp.bseg = K.bseg;
       for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
       dim3 grid((nq_max + W3_QC - 1) / W3_QC, (nl + 31) / 32, np);
@@ -1469,6 +1529,8 @@ int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset) {
   for (int i = 0; i < 6; i++) t->phase_cycles[i] = (long long)rs[4 + i];
   t->ring_slabs = (long long)rs[0]; t->ring_direct = (long long)rs[1]; t->ring_rows = (long long)rs[2];
   t->ring_pairs = (long long)rs[3];
+  t->proj_mask_mismatch = (h->proj_kernel == 4) ? (long long)rs[1] : 0;
+  if (getenv("CB200_DEBUG_WAIT")) fprintf(stderr, "[cb200] consumer warp0 wait cycles: all %llu, before producer arrive %llu\n", rs[10], rs[11]);
   if (reset) {
     for (int p = 0; p < PH_COUNT; p++) {
       for (auto& e : h->ev[p]) { h->ev_pool.push_back(e.first); h->ev_pool.push_back(e.second); }
@@ -1545,7 +1607,7 @@ int cb200_set_option(cb200_handle* h, const char* name, double value) {
   if (n == "count_triples") h->count_triples = value != 0;
   else if (n == "keep_transfers") h->keep_transfers = value != 0;
   else if (n == "ring_stats") h->ring_stats = value != 0;
-  else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 3) ? (int)value : 3;
+  else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 4) ? (int)value : 3;
   else return fail(h, "set_option: unknown option " + n);
   return 0;
 }

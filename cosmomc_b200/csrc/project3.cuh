@@ -65,6 +65,8 @@ struct Proj3Params {
   double* delta;            // optional [chunk][NQ][PROJ_LP][3]
   unsigned long long* triples;
   unsigned long long* ring_stats;  // optional [16]
+  int qc_rt;                       // wavenumbers per block actually used (<= W3_QC; 0 = W3_QC): matches the caller's block size
+  const unsigned char* need;       // optional [chunk][NQB]: run only the flagged (point, wavenumber block) pairs
   LinSegs bseg;
   int ls[PROJ_LP];
 };
@@ -87,8 +89,10 @@ __global__ void __launch_bounds__(32 * W3_NW, CB200_W3_MINB) project3_kernel(con
   const PointView& v = p.v;
   const int lp = blockIdx.z, pt = p.p0 + lp, qb = blockIdx.x, chunk = blockIdx.y;
   const int nq = v.n_q[pt];
-  const int q0 = qb * QC;
+  const int qcr = p.qc_rt > 0 ? p.qc_rt : QC;
+  const int q0 = qb * qcr;
   if (q0 >= nq || chunk * 32 >= p.nl) return;
+  if (p.need && !p.need[(size_t)lp * p.NQB + qb]) return;  // fallback pass behind project4_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int qr = lane >> 3, li = lane & 7;  // quarter-warp = wavenumber slot ; octet position
 
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(32 * W3_NW, CB200_W3_MINB) project3_kernel(con
   if (tid < QC) {
     ProjQ3 c;
     const int qi = q0 + tid;
-    c.valid = qi < nq;
+    c.valid = (qi < nq) && (tid < qcr);
     c.pad = 0;
     if (c.valid) {
       const double qv = v.q[(size_t)pt * v.NQ + qi];

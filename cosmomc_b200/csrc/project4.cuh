@@ -1,0 +1,690 @@
+// K1 v4 — windowed line-of-sight projection: ALL multipoles per quarter-warp, warp-specialised producer/consumer.
+//
+// Same reference behaviour as project.cuh / project2.cuh / project3.cuh (camb/cmbmain.f90:478-498, 1295-1374,
+// 1387-1420, 1440-1562, partial k-contraction of :2132-2264).  What changes against v3 (ncu of v3: no unit is
+// saturated — 2.86e7 shared-memory wavefronts and 1.28e8 warp instructions per point, 25 % occupancy, two
+// barriers per slab, metadata and ring filled three times because a CTA only covers 32 of the 88 multipoles):
+//   * one CTA = (point, 32 wavenumbers) and ALL sampled multipoles: a quarter-warp still owns one (q, tau)
+//     pair per step, but each lane now carries LK = ceil(n_l / 8) multipoles (l-slots li + 8k), so the 48 B of
+//     per-pair metadata are read once per 88 multipoles instead of once per 32, the pair metadata is computed
+//     once (not once per multipole chunk) and the ring is filled once per wavenumber block;
+//   * warp specialisation: 8 CONSUMER warps do nothing but the accumulation (shared-memory loads + FP64 FMAs);
+//     4 PRODUCER warps compute the (q, tau)-pair metadata of the next slab (table row, spline weights,
+//     k-interpolated d-tau-weighted sources; global loads software-pipelined one more slab ahead) and cp.async
+//     the table rows that slab needs into the ring.  The two sides meet only on two pairs of mbarriers
+//     (full / empty per metadata buffer); there is no CTA-wide barrier inside the time loop;
+//   * the ring holds whole table rows [row][n_l] (16 B nodes {j_l, j_l''}); the rows of a slab are known
+//     analytically (x = q (tau0 - tau) is monotone in q and tau) and are tabulated once per CTA, so the producer
+//     fills slab s+1 while slab s is consumed whenever both windows fit (else it waits for slab s to drain);
+//   * multipole octets with no active lane anywhere in the warp are skipped (no loads, no FP64 issue).
+#pragma once
+#include "common.cuh"
+#include "project.cuh"
+#include "project3.cuh"
+
+namespace cb200 {
+
+#ifndef CB200_W4_GROUPS
+#define CB200_W4_GROUPS 0
+#endif
+#ifndef CB200_W4_S
+#define CB200_W4_S 4
+#endif
+#ifndef CB200_W4_NQG
+#define CB200_W4_NQG 6
+#endif
+constexpr int W4_NQG = CB200_W4_NQG;  // wavenumber groups (4 wavenumbers = one warp's quarter-warps)
+constexpr int W4_NCW = 2 * W4_NQG;    // consumer warps: wavenumber group x multipole half (even / odd octets)
+constexpr int W4_QC = 4 * W4_NQG;     // wavenumbers per CTA
+constexpr int W4_S = CB200_W4_S;      // time samples per slab
+constexpr int W4_NPAIR = W4_QC * W4_S;
+#ifndef CB200_W4_NPW
+#define CB200_W4_NPW 4
+#endif
+constexpr int W4_NPW = CB200_W4_NPW;  // producer warps
+constexpr int W4_NT = 32 * (W4_NCW + W4_NPW);  // threads per CTA
+constexpr int w4_pnn() {  // largest divisor of S that the producer threads cover in one sweep
+  int best = 1;
+  for (int d = 1; d <= W4_S; d++)
+    if (W4_S % d == 0 && d * W4_QC <= 32 * W4_NPW) best = d;
+  return best;
+}
+constexpr int W4_PNN = w4_pnn();               // time samples covered by one sweep of the producer threads
+constexpr int W4_PPT = W4_S / W4_PNN;          // (q, tau) pairs per producer thread: same q, samples W4_PNN apart
+static_assert(W4_PNN >= 1 && W4_S % W4_PNN == 0, "slab shape");
+#ifndef CB200_W4_CREG
+#define CB200_W4_CREG 144
+#endif
+#ifndef CB200_W4_PREG
+#define CB200_W4_PREG 80
+#endif
+#define CB200_STR2(x) #x
+#define CB200_STR(x) CB200_STR2(x)
+constexpr int W4_SMEM_TOTAL = 227 * 1024;
+
+struct __align__(16) Proj4Rec {  // third metadata word of a pair
+  double s2;  // lensing-potential source x dtau
+  int off;    // byte offset of node row i0 in the ring
+  int jr;     // active multipole slots [jlo, jhi]: jlo | (jhi + 1) << 8 ; none: 127
+};
+
+struct Proj4Params {
+  PointView v;
+  int p0, nl, num_xx, NQB, tensors;
+  int zero;                 // always 0: an operand the assembler cannot fold (see the batch chaining in the consumer)
+  int R, rb;                // ring capacity in rows (+1 mirror row), row stride in bytes (= 128 * octets)
+  double max_eta_k;
+  const double* ddsrc;
+  const double* bx;
+  const double2* bes;       // [num_xx][PROJ_LP]
+  const double* initpower;
+  double* part;             // [chunk][NQB][6][PROJ_LP]
+  double* delta;            // optional [chunk][NQ][PROJ_LP][3]
+  unsigned long long* triples;
+  unsigned long long* ring_stats;  // optional [16]
+  unsigned char* fallback;  // [chunk][NQB]: 1 = a slab of this block needs more table rows than the ring holds
+  LinSegs bseg;
+  int ls[PROJ_LP];
+};
+
+#ifndef CB200_W4_KB
+#define CB200_W4_KB 6
+#endif
+#ifndef CB200_W4_NST
+#define CB200_W4_NST 4
+#endif
+constexpr int W4_NST = CB200_W4_NST;  // metadata buffers = slabs the producer may run ahead of the consumers
+constexpr size_t W4_META_BYTES = (size_t)W4_NST * W4_NPAIR * 48;
+constexpr size_t W4_QC_BYTES = sizeof(ProjQ3) * W4_QC;
+constexpr size_t W4_MISC_BYTES = 512;
+inline size_t w4_slab_table_bytes(int NT) { return (size_t)8 * ((NT + W4_S - 1) / W4_S + 2); }
+// per-(wavenumber, multipole slot) integration windows {n1, n2} as 2 x u16, rows padded to an odd word count
+inline size_t w4_wtab_bytes(int LK) { return (size_t)4 * W4_QC * (8 * LK + 1); }
+// ring rows that fit for a row stride of rb bytes (one extra mirror row)
+inline int w4_ring_rows(int LK, int NT) {
+  return (int)((W4_SMEM_TOTAL - W4_META_BYTES - W4_QC_BYTES - W4_MISC_BYTES - w4_slab_table_bytes(NT) - w4_wtab_bytes(LK)) /
+               (size_t)(LK * 128)) - 1;
+}
+inline size_t w4_smem_bytes(int LK, int NT, int R) {
+  return (size_t)(R + 1) * LK * 128 + W4_META_BYTES + W4_QC_BYTES + W4_MISC_BYTES + w4_slab_table_bytes(NT) + w4_wtab_bytes(LK);
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n"
+      "W4_WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
+      " @p bra W4_DONE_%=;\n"
+      " bra W4_WAIT_%=;\n"
+      "W4_DONE_%=:\n}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+// predicated 16-byte shared load: the destination keeps its (undefined) previous contents when !pred
+__device__ __forceinline__ double2 lds128_if(unsigned saddr, bool pred) {
+  double2 r;
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %3, 0;\n @p ld.shared.v2.f64 {%0, %1}, [%2];\n}\n"
+               : "=d"(r.x), "=d"(r.y)
+               : "r"(saddr), "r"((unsigned)pred));
+  return r;
+}
+
+__device__ __forceinline__ double2 ldg128_if(unsigned long long gaddr, bool pred) {
+  double2 r;
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %3, 0;\n @p ld.global.nc.v2.f64 {%0, %1}, [%2];\n}\n"
+               : "=d"(r.x), "=d"(r.y)
+               : "l"(gaddr), "r"((unsigned)pred));
+  return r;
+}
+
+template <int LK, bool COUNT>
+__global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p) {
+  constexpr int NCW = W4_NCW, NQG = W4_NQG, QC = W4_QC, S = W4_S, NPAIR = W4_NPAIR;
+  constexpr int LKH = (LK + 1) / 2;  // octets per consumer lane: k = 2 kk + lh
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int R = p.R;
+  constexpr int rb = LK * 128;  // ring row stride in bytes
+  unsigned char* ring = smem_raw;                                            // [(R+1)][rb]
+  unsigned char* meta_base = smem_raw + (size_t)(R + 1) * rb;                // 2 x {af[NPAIR], s01[NPAIR], rec[NPAIR]}
+  ProjQ3* qc = reinterpret_cast<ProjQ3*>(meta_base + W4_META_BYTES);         // [QC]
+  int* s_q1 = reinterpret_cast<int*>(meta_base + W4_META_BYTES + W4_QC_BYTES);  // [QC]
+  int* s_q2 = s_q1 + QC;                                                     // [QC]
+  int* s_misc = s_q2 + QC;                                                   // n_lo, n_hi
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_misc + 4);  // (s_misc[2]: block needs the fallback)  // full[NST], empty[NST]
+  constexpr int NJ = 8 * LK, NJP = NJ + 1;
+  unsigned* s_wtab = reinterpret_cast<unsigned*>(meta_base + W4_META_BYTES + W4_QC_BYTES + W4_MISC_BYTES);  // [QC][NJP]
+  int2* s_win = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(s_wtab) + (size_t)4 * QC * NJP);  // [slab] rows lo, hi
+
+  const PointView& v = p.v;
+  const int lp = blockIdx.y, pt = p.p0 + lp, qb = blockIdx.x;
+  const int nq = v.n_q[pt];
+  const int q0 = qb * QC;
+  if (q0 >= nq) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool consumer = warp < NCW;
+  const int qr = lane >> 3, li = lane & 7;   // quarter-warp = wavenumber slot ; octet position
+  const int wg = warp % NQG, lh = (warp / NQG) & 1;  // consumer: wavenumber group, multipole half
+
+  const int nt = v.n_tau[pt], nk = v.n_k[pt];
+  const double tau0 = v.thermo[(size_t)pt * 5];
+  const double* tau = v.tau + (size_t)pt * v.NT;
+  const double* dtau = v.dtau + (size_t)pt * v.NT;
+  const double* ksrc = v.ksrc + (size_t)pt * v.NK;
+  const LinSegs& tseg = v.tseg[pt];
+  const size_t row_stride = (size_t)v.NK;
+  const size_t tau_stride = (size_t)v.NSRC * v.NK;
+  const double* src = v.src + (size_t)pt * v.NT * tau_stride;
+  const double* dds = p.ddsrc + (size_t)lp * v.NT * tau_stride;
+  const double* ip = p.initpower + (size_t)lp * 10;
+  const int noct = (p.nl + 7) >> 3;  // octets that hold multipoles
+
+  // ---- per-wavenumber constants (InterpolateSources set-up, cmbmain.f90:1307-1320) ----
+  if (tid < QC) {
+    ProjQ3 c;
+    const int qi = q0 + tid;
+    c.valid = qi < nq;
+    c.pad = 0;
+    if (c.valid) {
+      const double qv = v.q[(size_t)pt * v.NQ + qi];
+      const double dqv = v.dq[(size_t)pt * v.NQ + qi];
+      c.q = qv;
+      c.w = (p.tensors ? tensor_power_dev(ip, qv) : scalar_power_dev(ip, qv)) * (dqv / qv);
+      int klo = 1;
+      while ((qv > ksrc[klo]) && (klo < (nk - 1))) klo++;
+      c.klo = klo;
+      const double ho = ksrc[klo] - ksrc[klo - 1];
+      c.a0 = (ksrc[klo] - qv) / ho;
+      c.b0 = (qv - ksrc[klo - 1]) / ho;
+      c.ho2o6 = ho * ho / 6;
+      c.a03h = (c.a0 * c.a0 * c.a0 - c.a0);
+      c.b03h = (c.b0 * c.b0 * c.b0 - c.b0);
+      const double max_etak_tensor = p.max_eta_k / 10;
+      int step = 2;
+      for (int i = nt; i >= 2; i--) {
+        double xf = __dmul_rn(qv, __dsub_rn(tau0, tau[i - 1]));
+        bool ok = xf > 1.e-8;
+        if (p.tensors) ok = ok && (__dmul_rn(qv, tau[i - 1]) < max_etak_tensor);
+        if (ok) { step = i; break; }
+      }
+      c.steps = step;
+    } else {
+      c.q = 1; c.w = 0; c.klo = 1; c.a0 = c.b0 = c.a03h = c.b03h = c.ho2o6 = 0; c.steps = 0;
+    }
+    qc[tid] = c;
+    s_q1[tid] = 0x7fffffff; s_q2[tid] = 0;
+  }
+  if (tid == 0) {
+    s_misc[0] = 0x7fffffff; s_misc[1] = 0; s_misc[2] = 0;
+    for (int i = 0; i < W4_NST; i++) {
+      mbar_init(s_bar + i, 32 * W4_NPW);     // full: every producer thread arrives (+ the bytes of its bulk copies)
+      mbar_init(s_bar + W4_NST + i, NCW);    // empty: one lane per consumer warp
+    }
+  }
+  __syncthreads();
+
+  // ---- integration windows of this lane's wavenumber (quarter) and its LK multipoles (consumer warps) ----
+  const int myqi = wg * 4 + qr;
+  const ProjQ3& myq = qc[myqi];
+  // Integration windows [n1, n2] of every (wavenumber, multipole) go to shared memory; both bounds fall with l
+  // (tmin and tmax do, and the index lookup is monotone), so for a given (q, tau) pair the active multipoles are
+  // ONE run of l-slots [jlo, jhi], which the producer tracks incrementally and ships with the pair metadata.
+  // Never-active entries keep that structure: cut from above (l > llmax, window not reached, padding, invalid q)
+  // = {0, 0}; cut from below (q >= qmax_int: Limber only) = {0x7fff, 0x7fff}.
+  unsigned win[COUNT ? LKH : 1];  // COUNT builds re-derive the mask from the exact windows and compare
+  unsigned reached = 0, doint = 0;
+  if (consumer) {
+    int un1 = 0x7fffffff, un2 = 0;
+#pragma unroll
+    for (int k = 0; k < LKH; k++) {
+      int n1 = 0, n2 = 0;
+      const int j = li + 8 * (2 * k + lh);
+      const bool lvalid = j < p.nl;
+      const int l = lvalid ? p.ls[j] : 0;
+      if (myq.valid && lvalid) {
+        const double qv = myq.q;
+        int llmax = (int)llround(__dmul_rn(qv, tau0));
+        if (llmax < 15) llmax = 17;
+        else llmax = (int)llround(__dmul_rn(qv, __dadd_rn(tau0, __ddiv_rn(6 * kPi, qv))));
+        if (l <= llmax) {
+          double xlim = 0.05 * l;
+          xlim = fmax(xlim, 35.0);
+          xlim = l - xlim;
+          const double tau2 = tau[1];
+          double tmin = __dsub_rn(tau0, __ddiv_rn((double)(80 * l), qv));
+          tmin = fmax(tau2, tmin);
+          double tmax = __dsub_rn(tau0, __ddiv_rn(xlim, qv));
+          tmax = fmin(tau0, tmax);
+          if (!(tmax < tau2)) {
+            reached |= 1u << k;
+            bool di = true;
+            if (!p.tensors) {
+              double qmax_int = __ddiv_rn((double)(max(850, l) * 3), tau0);
+              qmax_int = __dmul_rn(qmax_int, (double)1.2f);
+              di = qv < qmax_int;
+            }
+            if (di) {
+              doint |= 1u << k;
+              n1 = lin_index_of(tseg, tmin);
+              n2 = min(myq.steps, lin_index_of(tseg, tmax));
+            } else {
+              n1 = n2 = 0x7fff;
+            }
+          }
+        }
+      }
+      if (j < NJ) s_wtab[myqi * NJP + j] = (unsigned)n1 | ((unsigned)n2 << 16);
+      const bool live = (n2 >= n1) && n1 > 0 && n1 < 0x7fff;
+      if (live) {
+        un1 = min(un1, n1);
+        un2 = max(un2, n2);
+      }
+      if (COUNT) win[k] = live ? ((unsigned)n1 | ((unsigned)(n2 - n1) << 16)) : 0x7fffu;
+    }
+    // union over the quarter's multipoles: which (q, tau) pairs have to be visited at all
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      un1 = min(un1, __shfl_xor_sync(0xffffffffu, un1, o));
+      un2 = max(un2, __shfl_xor_sync(0xffffffffu, un2, o));
+    }
+    if (li == 0 && un1 <= un2) {  // union over both multipole halves
+      atomicMin(&s_q1[myqi], un1); atomicMax(&s_q2[myqi], un2);
+      atomicMin(&s_misc[0], un1); atomicMax(&s_misc[1], un2);
+    }
+  }
+  __syncthreads();
+  const int n_lo = s_misc[0], n_hi = s_misc[1];
+  const int nslab = (n_lo <= n_hi) ? (n_hi - n_lo) / S + 1 : 0;
+
+  // ---- analytic table-row window of every slab (superset of the rows its visited pairs touch):
+  //      x = q (tau0 - tau) decreases with tau and grows with q, the block's wavenumbers are ascending ----
+  {
+    const int nvalid = min(QC, nq - q0);
+    const double q_first = qc[0].q, q_last = qc[nvalid - 1].q;
+    for (int t = tid; t < nslab; t += W4_NT) {
+      const int nb = n_lo + t * S;
+      const int na = max(nb, 1), nz = min(min(nb + S - 1, n_hi), nt);
+      const double xhi = fabs(__dmul_rn(q_last, __dsub_rn(tau0, tau[na - 1])));
+      const double xlo = fabs(__dmul_rn(q_first, __dsub_rn(tau0, tau[nz - 1])));
+      double x0, x1, ih;
+      int bhi = lin_locate(p.bseg, xhi, x0, x1, ih);
+      int blo = lin_locate(p.bseg, xlo, x0, x1, ih);
+      bhi = min(bhi, p.num_xx - 1);
+      blo = min(blo, p.num_xx - 1);
+      s_win[t] = make_int2(max(blo - 1, 0), bhi);  // rows i0 .. i0 + 1
+      if (bhi - max(blo - 1, 0) + 1 > R) s_misc[2] = 1;
+    }
+  }
+  __syncthreads();
+  // A slab that needs more table rows than the ring holds (in practice only the first, log-spaced wavenumber
+  // block): the whole block is left to the chunked kernel (project3.cuh), which the host launches on the flagged
+  // blocks right after this kernel.
+  if (p.fallback) {
+    if (tid == 0) p.fallback[(size_t)lp * p.NQB + qb] = (unsigned char)(s_misc[2] != 0);
+  }
+  if (s_misc[2] != 0) return;
+
+  unsigned long long my_triples = 0, st_slabs = 0, st_rows = 0, st_late = 0, st_mismatch = 0;
+  long long st_wait_all = 0, st_wait_prod = 0;
+  long long ck_a = 0, ck_b = 0, ck_c = 0, ck_t0 = clock64(), ck_t;
+#define CK4(var) do { if (COUNT) { ck_t = clock64(); var += ck_t - ck_t0; ck_t0 = ck_t; } } while (0)
+
+  // Register re-balancing: the four producer warps (one warp group, one warp per SM sub-partition) give registers
+  // back, the consumers take them.  The pool is what the CTA was launched with (64 K / threads, per thread), so
+  // NPW x (launch - PREG) must cover NCW x (CREG - launch).
+  static_assert(W4_NPW == 4 && W4_NCW % 4 == 0 && W4_NPW * (65536 / W4_NT / 8 * 8 - CB200_W4_PREG) >= W4_NCW * (CB200_W4_CREG - 65536 / W4_NT / 8 * 8), "setmaxnreg works on aligned groups of 4 warps");
+  if (!consumer) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 " CB200_STR(CB200_W4_PREG) ";\n");
+    // =========================================== PRODUCER ===========================================
+    const int m_pair = tid - 32 * NCW;               // pair of the slab owned by this thread
+    const bool m_live = m_pair < QC * W4_PNN;        // spare producer threads only take part in the barriers
+    const int m_qi = m_live ? m_pair % QC : 0, m_nn = m_pair / QC;
+    const ProjQ3 pc = qc[m_qi];
+    const int pw1 = (pc.valid && m_live) ? max(s_q1[m_qi], 1) : 0x7fffffff;
+    const int pw2 = pc.valid ? min(s_q2[m_qi], pc.steps) : 0;
+    const double* Sp0 = src + (pc.klo - 1);
+    const double* Dp0 = dds + (pc.klo - 1);
+    constexpr int PPT = W4_PPT, PNN = W4_PNN;
+    double f_tau[PPT], f_dtau[PPT], f_s[PPT][3][4];
+    bool f_valid[PPT];
+    auto prefetch = [&](int nb) {
+#pragma unroll
+      for (int u = 0; u < PPT; u++) {
+        const int n = nb + m_nn + u * PNN;
+        f_valid[u] = (n >= pw1) && (n <= pw2);
+        if (f_valid[u]) {
+          f_tau[u] = __ldg(tau + n - 1);
+          f_dtau[u] = __ldg(dtau + n - 1);
+          const double* Sp = Sp0 + (size_t)(n - 1) * tau_stride;
+          const double* Dp = Dp0 + (size_t)(n - 1) * tau_stride;
+#pragma unroll
+          for (int sI = 0; sI < 3; sI++) {
+            f_s[u][sI][0] = __ldg(Sp + sI * row_stride);
+            f_s[u][sI][1] = __ldg(Sp + sI * row_stride + 1);
+            f_s[u][sI][2] = __ldg(Dp + sI * row_stride);
+            f_s[u][sI][3] = __ldg(Dp + sI * row_stride + 1);
+          }
+        }
+      }
+    };
+    // rows [a, b] of the table -> ring by TMA bulk copies (one per row; slot 0 is mirrored behind slot R-1);
+    // their bytes are accounted on the slab's `full` barrier, so nobody waits for them but the consumers
+    auto fetch_rows = [&](int a, int b, unsigned long long* bar) {
+      for (int row = a + m_pair; row <= b; row += 32 * W4_NPW) {
+        const int slot = row % R;
+        const double2* g = p.bes + (size_t)row * PROJ_LP;
+        mbar_expect_tx(bar, slot == 0 ? 2 * rb : rb);
+        bulk_g2s(ring + (size_t)slot * rb, g, rb, bar);
+        if (slot == 0) bulk_g2s(ring + (size_t)R * rb, g, rb, bar);
+      }
+      if (COUNT && p.ring_stats && m_pair == 0 && b >= a) st_rows += b - a + 1;
+    };
+    int rlo = 0x7fffffff;      // lowest resident row (identical in every producer thread by construction)
+    int released = -1;         // slabs <= released have been released by every consumer warp
+    int jlo[PPT], jhi[PPT];    // active multipole slots of this thread's pairs (both only ever move down)
+#pragma unroll
+    for (int u = 0; u < PPT; u++) { jlo[u] = NJ; jhi[u] = NJ - 1; }
+    const unsigned* wrow = s_wtab + m_qi * NJP;
+    if (nslab > 0) prefetch(n_lo);
+    CK4(ck_a);
+    for (int t = 0; t < nslab; t++) {
+      const int par = t % W4_NST;
+      // metadata buffer `par` is free once the consumers have released slab t - NST (slabs are released in order)
+      if (t >= W4_NST) {
+        mbar_wait(s_bar + W4_NST + par, ((t - W4_NST) / W4_NST) & 1);
+        released = max(released, t - W4_NST);
+      }
+      CK4(ck_c);
+      const int2 w = s_win[t];
+      // The windows slide towards lower rows (x falls with tau).  Rows [w.x, ...] may overwrite ring slots only if
+      // the highest row still needed by the oldest slab not yet released stays within R rows of w.x.
+      while (released + 1 < t && s_win[released + 1].y - w.x + 1 > R) {
+        const int r = released + 1;
+        mbar_wait(s_bar + W4_NST + (r % W4_NST), (r / W4_NST) & 1);
+        released = r;
+        if (COUNT && p.ring_stats && m_pair == 0) st_late++;
+      }
+      CK4(ck_c);
+      {
+        const int f_hi = (rlo <= w.y) ? rlo - 1 : w.y;  // rows >= rlo are resident (fetched for earlier slabs)
+        if (w.x <= f_hi) fetch_rows(w.x, f_hi, s_bar + par);
+        rlo = min(rlo, w.x);
+      }
+      if (COUNT && p.ring_stats && m_pair == 0) st_slabs++;
+      CK4(ck_b);
+      // ---- metadata of this thread's pairs ----
+#pragma unroll
+      for (int u = 0; u < PPT; u++) {
+        const int n = n_lo + t * S + m_nn + u * PNN;
+        const int pidx = m_pair + u * QC * PNN;
+        unsigned char* mb = meta_base + (size_t)par * NPAIR * 48;
+        double2* m_af = reinterpret_cast<double2*>(mb);
+        double2* m_s01 = reinterpret_cast<double2*>(mb + NPAIR * 16);
+        Proj4Rec* m_rec = reinterpret_cast<Proj4Rec*>(mb + NPAIR * 32);
+        int moff = 0, jr = 127;
+        double ma = 0, mfac = 0, ms0 = 0, ms1 = 0, ms2 = 0;
+        // slots still inside their window at time sample n: n2 >= n from above, n1 <= n from below
+        while (jhi[u] >= 0 && (int)(wrow[jhi[u]] >> 16) < n) jhi[u]--;
+        while (jlo[u] > 0 && (int)(wrow[jlo[u] - 1] & 0xffffu) <= n) jlo[u]--;
+        if (f_valid[u]) {
+          const double x = fabs(__dmul_rn(pc.q, __dsub_rn(tau0, f_tau[u])));
+          double x0, x1, inv_h;
+          int bi = lin_locate(p.bseg, x, x0, x1, inv_h);
+          if (bi > p.num_xx - 1) { bi = p.num_xx - 1; x0 = p.bx[bi - 1]; x1 = p.bx[bi]; inv_h = 1.0 / (x1 - x0); }
+          // interpolation weights (values, not indices): reciprocal multiplies instead of the reference's divisions
+          const double fac = x1 - x0;
+          ma = (x1 - x) * inv_h;
+          mfac = fac * fac * ma * (1.0 / 6.0);
+          if (n >= 2) {  // Source_q(1,:) is forced to zero (IntegrationVars_Init, cmbmain.f90:1380)
+            ms0 = (pc.a0 * f_s[u][0][0] + pc.b0 * f_s[u][0][1] + (pc.a03h * f_s[u][0][2] + pc.b03h * f_s[u][0][3]) * pc.ho2o6) * f_dtau[u];
+            ms1 = (pc.a0 * f_s[u][1][0] + pc.b0 * f_s[u][1][1] + (pc.a03h * f_s[u][1][2] + pc.b03h * f_s[u][1][3]) * pc.ho2o6) * f_dtau[u];
+            ms2 = (pc.a0 * f_s[u][2][0] + pc.b0 * f_s[u][2][1] + (pc.a03h * f_s[u][2][2] + pc.b03h * f_s[u][2][3]) * pc.ho2o6) * f_dtau[u];
+          }
+          moff = ((bi - 1) % R) * rb;
+          if (jlo[u] <= jhi[u]) jr = jlo[u] | ((jhi[u] + 1) << 8);
+        }
+        if (m_live) {
+          m_af[pidx] = make_double2(ma, mfac);
+          m_s01[pidx] = make_double2(ms0, ms1);
+          Proj4Rec rec; rec.s2 = ms2; rec.off = moff; rec.jr = jr;
+          m_rec[pidx] = rec;
+        }
+      }
+      if (t + 1 < nslab) prefetch(n_lo + (t + 1) * S);
+      CK4(ck_a);
+      if (COUNT && m_pair == 0) s_bar[16 + par] = (unsigned long long)clock64();
+      mbar_arrive(s_bar + par);
+      CK4(ck_c);
+    }
+    if (COUNT && p.ring_stats) {
+      if (m_pair == 0) {
+        atomicAdd(p.ring_stats + 0, st_slabs);
+        atomicAdd(p.ring_stats + 2, st_rows); atomicAdd(p.ring_stats + 3, st_late);
+      }
+      if (lane == 0) {  // producer: metadata + prefetch, ring issue, waits
+        atomicAdd(p.ring_stats + 5, (unsigned long long)ck_a); atomicAdd(p.ring_stats + 7, (unsigned long long)ck_b);
+        atomicAdd(p.ring_stats + 9, (unsigned long long)ck_c);
+      }
+    }
+    return;
+  }
+
+  // ============================================= CONSUMER =============================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 " CB200_STR(CB200_W4_CREG) ";\n");
+  double acc[LKH][3];
+#pragma unroll
+  for (int k = 0; k < LKH; k++) acc[k][0] = acc[k][1] = acc[k][2] = 0.0;
+  const unsigned ring_lane = smem_u32(ring) + li * 16 + lh * 128;  // shared-space address
+  const int lc = li + 8 * lh;
+  CK4(ck_a);
+  for (int t = 0; t < nslab; t++) {
+    const int par = t % W4_NST;
+    const int n_base = n_lo + t * S;
+    long long tw0 = 0;
+    if (COUNT) tw0 = clock64();
+    mbar_wait(s_bar + par, (t / W4_NST) & 1);
+    if (COUNT && p.ring_stats && tid == 0) {
+      const long long tw1 = clock64(), ta = (long long)s_bar[16 + par];
+      st_wait_all += tw1 - tw0;
+      if (ta > tw0) st_wait_prod += ta - tw0;   // part of the wait spent before the last producer thread arrived
+    }
+    CK4(ck_b);
+    const unsigned char* mb = meta_base + (size_t)par * NPAIR * 48;
+    const double2* m_af = reinterpret_cast<const double2*>(mb);
+    const double2* m_s01 = reinterpret_cast<const double2*>(mb + NPAIR * 16);
+    const Proj4Rec* m_rec = reinterpret_cast<const Proj4Rec*>(mb + NPAIR * 32);
+    // quarter-warp r works on pair (q_r, n); every lane covers LK multipoles
+#pragma unroll 1
+    for (int nn = 0; nn < S; nn++) {
+      const int n = n_base + nn;
+      const int pr = nn * QC + myqi;
+      const Proj4Rec rec = m_rec[pr];
+      const double2 af = m_af[pr];
+      const double2 s01 = m_s01[pr];
+      // this lane's octets k with jlo <= lc + 16 k <= jhi (lc = li + 8 lh: the lane's first l-slot)
+      const int klo = max((int)((rec.jr & 0xff) + 15 - lc) >> 4, 0);
+      const int khi1 = ((rec.jr >> 8) + 15 - lc) >> 4;  // khi + 1 >= 0
+      const unsigned m = ((1u << khi1) - 1u) & ~((1u << klo) - 1u);
+      if (COUNT) {
+        unsigned mx = 0;
+#pragma unroll
+        for (int k = 0; k < LKH; k++) {
+          const unsigned tt = (unsigned)n - (win[k] & 0xffffu);
+          mx |= (tt <= (win[k] >> 16)) ? (1u << k) : 0u;
+        }
+        if (mx != m) st_mismatch++;
+      }
+      // cubic-spline value of j_l between the two nodes (cmbmain.f90:1515-1516), weights expanded:
+      //   J = a j0 + b j1 + g0 p0 + g1 p1,  b = 1-a, g0 = -b fac (a+1), g1 = -b fac (2-a)
+      const double a2 = af.x, b2 = 1 - a2, t2 = -(b2 * af.y);
+      const double g0 = t2 * (a2 + 1), g1 = t2 * (2 - a2);
+      if (COUNT && p.triples) my_triples += __popc(m);
+      // octets in batches of KB: the loads of a batch are in flight together; the next batch's address is made to
+      // depend on this batch's values (a true PTX-level dependency: ptxas does the scheduling, an empty asm would
+      // vanish), so that at most 2 KB loads (8 KB registers) are live at a time
+      constexpr int KB = CB200_W4_KB;
+      {
+        unsigned rp = ring_lane + rec.off;
+        const unsigned U = __reduce_or_sync(0xffffffffu, m);  // octets with an active lane anywhere in the warp
+#pragma unroll
+        for (int k0 = 0; k0 < LKH; k0 += KB) {
+          if (!(U & (((1u << KB) - 1u) << k0))) continue;  // warp-uniform: no loads, no FP64 issue
+          double2 N0[KB], N1[KB];
+#pragma unroll
+          for (int kk = 0; kk < KB; kk++) {
+            const int k = k0 + kk;
+            if (k < LKH) {
+              const bool act = (m >> k) & 1u;
+              N0[kk] = lds128_if(rp + k * 256, act);
+              N1[kk] = lds128_if(rp + k * 256 + rb, act);
+            }
+          }
+          int jbits = 0;
+#pragma unroll
+          for (int kk = 0; kk < KB; kk++) {
+            const int k = k0 + kk;
+            if (k < LKH) {
+              const bool act = (m >> k) & 1u;
+              double Jv = fma(g1, N1[kk].y, fma(g0, N0[kk].y, fma(b2, N1[kk].x, a2 * N0[kk].x)));
+              Jv = act ? Jv : 0.0;
+              acc[k][0] = fma(s01.x, Jv, acc[k][0]);
+              acc[k][1] = fma(s01.y, Jv, acc[k][1]);
+              acc[k][2] = fma(rec.s2, Jv, acc[k][2]);
+              jbits |= __double2hiint(Jv);
+            }
+          }
+          if (k0 + KB < LKH)
+            asm volatile("{\n .reg .b32 t;\n and.b32 t, %1, %2;\n add.u32 %0, %0, t;\n}\n" : "+r"(rp) : "r"(jbits), "r"(p.zero));
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(s_bar + W4_NST + par);
+    CK4(ck_c);
+  }
+
+  if (COUNT && p.triples) {
+    unsigned long long t = my_triples;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0 && t) atomicAdd(p.triples, t);
+  }
+  if (COUNT && p.ring_stats && st_mismatch) atomicAdd(p.ring_stats + 1, st_mismatch);
+  if (COUNT && p.ring_stats && tid == 0) { atomicAdd(p.ring_stats + 10, (unsigned long long)st_wait_all); atomicAdd(p.ring_stats + 11, (unsigned long long)st_wait_prod); }
+  if (COUNT && p.ring_stats && lane == 0) {  // consumer: prologue, wait for the producer, accumulate
+    atomicAdd(p.ring_stats + 4, (unsigned long long)ck_a); atomicAdd(p.ring_stats + 6, (unsigned long long)ck_b);
+    atomicAdd(p.ring_stats + 8, (unsigned long long)ck_c);
+  }
+#undef CK4
+  // all consumer warps are done with the ring: it is reused for the contraction partials
+  asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W4_NCW) : "memory");
+
+  // The block's context is re-derived here from laundered special-register reads, so that none of it has to stay
+  // in registers across the time loop (the loop needs every register for accumulators and loads in flight).
+  {
+  unsigned e_tid, e_bx, e_by;
+  asm volatile("mov.u32 %0, %%tid.x;\n" : "=r"(e_tid));
+  asm volatile("mov.u32 %0, %%ctaid.x;\n" : "=r"(e_bx));
+  asm volatile("mov.u32 %0, %%ctaid.y;\n" : "=r"(e_by));
+  const int tid = (int)e_tid, lane = tid & 31, warp = tid >> 5;
+  const int lp = (int)e_by, pt = p.p0 + lp, qb = (int)e_bx, q0 = qb * QC;
+  const int qr = lane >> 3, li = lane & 7, wg = warp % NQG, lh = (warp / NQG) & 1;
+  const double tau0 = v.thermo[(size_t)pt * 5];
+  const double* tau = v.tau + (size_t)pt * v.NT;
+  const LinSegs& tseg = v.tseg[pt];
+  const size_t row_stride = (size_t)v.NK;
+  const size_t tau_stride = (size_t)v.NSRC * v.NK;
+  const double* src = v.src + (size_t)pt * v.NT * tau_stride;
+  const double* dds = p.ddsrc + (size_t)lp * v.NT * tau_stride;
+  const int noct = (p.nl + 7) >> 3;
+  const int myqi = wg * 4 + qr;
+  const ProjQ3& myq = reinterpret_cast<const ProjQ3*>(smem_raw + (size_t)(p.R + 1) * rb + W4_META_BYTES)[myqi];
+  // ---- Limber value of the lensing source (cmbmain.f90:1546-1556) and the partial k-contraction ----
+  double* red = reinterpret_cast<double*>(smem_raw);  // [wavenumber group][6][PROJ_LP]
+#pragma unroll
+  for (int k = 0; k < LKH; k++) {
+    double cl[6];
+#pragma unroll
+    for (int X = 0; X < 6; X++) cl[X] = 0.0;
+    const int j = li + 8 * (2 * k + lh);
+    const int l = (j < p.nl) ? p.ls[j] : 0;
+    if (2 * k + lh >= LK) continue;  // octet outside the row (odd LK)
+    if (myq.valid && 2 * k + lh < noct) {
+      if (!p.tensors && j < p.nl && ((reached >> k) & 1u)) {
+        const bool use_limber = l > 400;
+        if (!((doint >> k) & 1u) || use_limber) {
+          double xf = __dsub_rn(tau0, __ddiv_rn((double)l + 0.5, myq.q));
+          double s3 = 0;
+          if (xf < tseg.highest && xf > tau[0]) {
+            const int n = lin_index_of(tseg, xf);
+            xf = __ddiv_rn(__dsub_rn(xf, tau[n - 1]), __dsub_rn(tau[n], tau[n - 1]));
+            double sa2 = 0, sb2 = 0;
+            const double* S2p = src + 2 * row_stride + (myq.klo - 1);
+            const double* D2p = dds + 2 * row_stride + (myq.klo - 1);
+            if (n >= 2 && n <= myq.steps) {
+              const double* a = S2p + (size_t)(n - 1) * tau_stride;
+              const double* d = D2p + (size_t)(n - 1) * tau_stride;
+              sa2 = myq.a0 * a[0] + myq.b0 * a[1] + (myq.a03h * d[0] + myq.b03h * d[1]) * myq.ho2o6;
+            }
+            if (n + 1 >= 2 && n + 1 <= myq.steps) {
+              const double* a = S2p + (size_t)n * tau_stride;
+              const double* d = D2p + (size_t)n * tau_stride;
+              sb2 = myq.a0 * a[0] + myq.b0 * a[1] + (myq.a03h * d[0] + myq.b03h * d[1]) * myq.ho2o6;
+            }
+            s3 = (sa2 * (1 - xf) + xf * sb2) * sqrt(kPi / 2 / ((double)l + 0.5)) / myq.q;
+          }
+          acc[k][2] = s3;
+        }
+      }
+      const double d0 = acc[k][0], d1 = acc[k][1], d2 = acc[k][2];
+      if (p.delta) {
+        double* dp = p.delta + (((size_t)lp * v.NQ + (q0 + myqi)) * PROJ_LP + j) * 3;
+        dp[0] = d0; dp[1] = d1; dp[2] = d2;
+      }
+      const double w = myq.w;
+      if (p.tensors) {
+        cl[0] = w * d0 * d0; cl[1] = w * d1 * d1; cl[2] = w * d2 * d2; cl[3] = w * d0 * d1;
+      } else {
+        cl[0] = w * d0 * d0; cl[1] = w * d1 * d1; cl[2] = w * d0 * d1;
+        cl[3] = w * d2 * d2; cl[4] = w * d2 * d0; cl[5] = w * d2 * d1;
+      }
+    }
+    // sum over the warp's four wavenumbers (quarters); warps are added below in a fixed order
+#pragma unroll
+    for (int X = 0; X < 6; X++) {
+      double s = cl[X];
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      if (qr == 0) red[((size_t)wg * 6 + X) * PROJ_LP + j] = s;
+    }
+  }
+  asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W4_NCW) : "memory");
+  {
+    double* pp = p.part + (((size_t)lp * p.NQB + qb) * 6) * PROJ_LP;
+    for (int e = tid; e < 6 * PROJ_LP; e += 32 * NCW) {
+      const int X = e / PROJ_LP, j = e - X * PROJ_LP;
+      double s = 0;
+      if (j < 8 * LK) {
+#pragma unroll
+        for (int w = 0; w < NQG; w++) s += red[((size_t)w * 6 + X) * PROJ_LP + j];
+      }
+      pp[e] = s;
+    }
+  }
+  }
+}
+
+}  // namespace cb200

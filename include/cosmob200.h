@@ -215,10 +215,12 @@ typedef struct cb200_timing {
   long long ring_slabs, ring_direct, ring_rows, ring_pairs; /* windowed projection statistics (option "ring_stats") */
   long long phase_cycles[6]; /* per-warp clock64 sums: prologue, prefetch, barrier wait, ring fill, accumulate, metadata */
   float ms_background;       /* K5 distance kernels */
+  long long proj_mask_mismatch; /* proj_kernel 4 with "ring_stats": (pair, lane) activity masks that differ from the exact windows; must be 0 */
 } cb200_timing;
 int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset);
 int cb200_sync(cb200_handle* h);
-/* options: "count_triples" (0/1), "keep_transfers" (0/1), "ring_stats" (0/1), "proj_kernel" (1 = L2-gather v1, 2 = windowed) */
+/* options: "count_triples" (0/1), "keep_transfers" (0/1), "ring_stats" (0/1), "proj_kernel" (1 = L2 gathers, 2 = windowed warp-per-pair,
+ * 3 = quarter-warp pairs per 32-multipole chunk, 4 = all multipoles per quarter-warp, producer/consumer warps; default) */
 int cb200_set_option(cb200_handle* h, const char* name, double value);
 /* CUDA-event stopwatch on the library's stream (device-side timing of whole calls) */
 int cb200_timer_start(cb200_handle* h);

@@ -12,7 +12,7 @@ th = syn.draw_thermo(n, 5); ip, al, cal, pert = syn.draw_params(n, 5)
 tau, dtau, n_tau, k, n_k = syn.build_grids(h, th)
 src = syn.make_sources(th, tau, k, pert).numpy()
 h.upload_sources(th, n_k, k, src)
-for pk in (3, 2):
+for pk in (4, 3):
     h.set_option("proj_kernel", pk)
     h.set_option("ring_stats", 1); h.set_option("count_triples", 1)
     h.powers_resident(ip, al); h.timing(reset=True)
@@ -23,6 +23,7 @@ for pk in (3, 2):
     if pc.sum() > 0:
         print("  PHASES prologue/prefetch/barrier/ring/accumulate/metadata %%: %s" % np.round(100 * pc / pc.sum(), 1))
     if t["ring_slabs"]:
+        print("  (v4: ring_pairs = slabs whose fill could not be issued ahead)")
         print("  direct frac %.4f rows/slab %.1f pairs/row %.2f triples/pair %.1f" % (t["ring_direct"] / t["ring_slabs"], t["ring_rows"] / t["ring_slabs"], t["ring_pairs"] / max(1, t["ring_rows"]), t["proj_triples"] / max(1, t["ring_pairs"])))
     h.set_option("ring_stats", 0); h.set_option("count_triples", 0)
     h.powers_resident(ip, al); h.timing(reset=True)

@@ -138,7 +138,7 @@ def test_triple_count_matches_oracle(setup):
     """The instrumented unit-of-work count is an integer artefact: identical in both kernels."""
     h, orc = setup["h"], setup["orc"]
     want = sum(o["triples"] for o in orc)
-    for pk in (1, 2, 3):
+    for pk in (1, 2, 3, 4):
         h.set_option("proj_kernel", pk)
         h.set_option("count_triples", 1)
         h.timing(reset=True)
@@ -146,12 +146,23 @@ def test_triple_count_matches_oracle(setup):
         t = h.timing()
         h.set_option("count_triples", 0)
         assert t["proj_triples"] == want, (pk, t["proj_triples"], want)
+    # kernel 4 ships the active multipoles of a (q, tau) pair as ONE run of l-slots; with "ring_stats" on it
+    # re-derives every lane's mask from the exact integration windows and counts the differences
+    h.set_option("proj_kernel", 4)
+    h.set_option("ring_stats", 1)
+    h.timing(reset=True)
+    h.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
+    t = h.timing()
+    h.set_option("ring_stats", 0)
     h.set_option("proj_kernel", 3)
+    assert t["ring_slabs"] > 0 and t["proj_mask_mismatch"] == 0, t
 
 
-@pytest.mark.parametrize("pk", [1, 2])
+@pytest.mark.parametrize("pk", [1, 2, 4])
 def test_earlier_projection_kernels_agree(setup, pk):
-    """The earlier projection kernels (1: direct L2 gathers, 2: windowed, warp-per-pair) stay as cross-checks."""
+    """The other projection kernels (1: direct L2 gathers, 2: windowed warp-per-pair, 4: all multipoles per
+    quarter-warp with producer/consumer warps, TMA-filled ring and mbarriers) stay as cross-checks of the default
+    (3: quarter-warp pairs per 32-multipole chunk)."""
     h, orc = setup["h"], setup["orc"]
     h.set_option("proj_kernel", pk)
     cls, derived, status = h.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
