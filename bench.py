@@ -247,11 +247,15 @@ def main():
         return tot
 
     def step_e2e():
+        # block i+1 is uploaded (copy stream) while block i is being evaluated (compute stream): the public calls
+        # are the same three - upload_sources / powers / loglike_batch - with the "async_upload" option on
+        h.set_option("async_upload", 1)
         for a in range(0, P, stage_n):
             b = min(P, a + stage_n)
             h.upload_sources(W["thermo"][a:b], W["n_k"][a:b], W["k"][a:b], None, first=a,
                              src_host_ptr=stage.data_ptr())
-        h.powers_resident(W["initpower"], W["alens"])
+            h.powers_resident(W["initpower"][a:b], W["alens"][a:b], first=a)
+        h.set_option("async_upload", 0)
         ll, tot, st = h.loglike_batch(P, nuis)
         return tot
 
@@ -312,7 +316,8 @@ def main():
         d2h = P * (8 + 8 + 4)
         e2e = {"value": world * P * args.steps / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms2 / args.steps,
-               "note": "pinned %d-point host staging buffer re-sent %d x per step per GPU" % (stage_n, -(-P // stage_n))}
+               "note": "pinned %d-point host staging buffer re-sent %d x per step per GPU; the upload of block i+1 "
+                       "(copy stream) overlaps the evaluation of block i" % (stage_n, -(-P // stage_n))}
 
     # ---- roofline of the dominant kernel (K1 projection; launched once per %d-point chunk)
     n_launch_k1 = args.steps * (-(-P // min(args.chunk, P)))

@@ -96,6 +96,14 @@ struct cb200_handle {
   cb200_info info{};
   std::string err;
   cudaStream_t stream = nullptr;
+  // uploads run on their own stream so that the host->device copy of one block of points overlaps the kernels of
+  // the previous one; ev_upload orders `stream` behind the latest upload, `busy` lists the point ranges that
+  // in-flight cb200_powers calls still read (an upload into such a range waits for that call)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_upload = nullptr;
+  bool upload_pending = false, async_upload = false;
+  struct BusyRange { int kind, first, npts; cudaEvent_t done; };
+  std::vector<BusyRange> busy;
   KindSet kind[2];
   PointStore store[2];
   bool have_templates = false;
@@ -382,6 +390,8 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
       throw std::runtime_error("cosmob200: no CUDA device available (there is no CPU fallback)");
     CB_CUDA(cudaSetDevice(c.device));
     CB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CB_CUDA(cudaEventCreateWithFlags(&h->ev_upload, cudaEventDisableTiming));
     if (c.accuracy_level != 1) throw std::runtime_error("only accuracy_level = 1 is supported");
     if (!c.cmb_lensing) throw std::runtime_error("only CMB_lensing = T is supported");
     if (c.n_tau_max <= 0) c.n_tau_max = 768;
@@ -458,7 +468,10 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
 void cb200_destroy(cb200_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->ev_upload) cudaEventDestroy(h->ev_upload);
+  for (auto& b : h->busy) cudaEventDestroy(b.done);
   for (auto& v : h->ev) for (auto& p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -603,7 +616,14 @@ int cb200_upload_sources(cb200_handle* h, int kind, int first, int npts, const d
       tseg[i] = to_linsegs(gt);
     }
   });
-  cudaStream_t s = h->stream;
+  cudaStream_t s = h->copy_stream;
+  // an in-flight cb200_powers call that still reads this point range has to finish first
+  for (size_t i = 0; i < h->busy.size();) {
+    cb200_handle::BusyRange& br = h->busy[i];
+    if (cudaEventQuery(br.done) == cudaSuccess) { cudaEventDestroy(br.done); h->busy.erase(h->busy.begin() + i); continue; }
+    if (br.kind == kind && br.first < first + npts && first < br.first + br.npts) CB_CUDA(cudaStreamWaitEvent(s, br.done, 0));
+    i++;
+  }
   const size_t f = first;
   CB_CUDA(cudaMemcpyAsync(S.thermo.p + f * 5, thermo, sizeof(double) * npts * 5, cudaMemcpyHostToDevice, s));
   CB_CUDA(cudaMemcpyAsync(S.tau.p + f * S.NT, tau.data(), sizeof(double) * tau.size(), cudaMemcpyHostToDevice, s));
@@ -615,12 +635,19 @@ int cb200_upload_sources(cb200_handle* h, int kind, int first, int npts, const d
   CB_CUDA(cudaMemcpyAsync(S.n_q.p + f, nq.data(), sizeof(int) * npts, cudaMemcpyHostToDevice, s));
   CB_CUDA(cudaMemcpyAsync(S.n_k.p + f, n_k, sizeof(int) * npts, cudaMemcpyHostToDevice, s));
   CB_CUDA(cudaMemcpyAsync(S.tseg.p + f, tseg.data(), sizeof(LinSegs) * npts, cudaMemcpyHostToDevice, s));
+  // the grid vectors above live in pageable memory: the runtime stages them before returning, so they may go out
+  // of scope; the (large) source block goes last and, from a pinned buffer, is a true asynchronous DMA
   const size_t per = (size_t)S.NT * 3 * S.NK;
   if (src)
     CB_CUDA(cudaMemcpyAsync(S.src.p + f * per, src, sizeof(double) * per * npts,
                             src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
   for (int i = 0; i < npts; i++) { S.h_nq[first + i] = nq[i]; S.h_ntau[first + i] = ntau[i]; }
-  CB_CUDA(cudaStreamSynchronize(s));  // host staging vectors go out of scope
+  CB_CUDA(cudaEventRecord(h->ev_upload, s));
+  h->upload_pending = true;
+  // default: the caller may reuse its buffers as soon as this returns.  With option "async_upload" the call
+  // returns with the source copy in flight (the buffer must stay untouched until cb200_sync or any call that
+  // returns results); the next cb200_powers is ordered behind it on the device.
+  if (!h->async_upload) CB_CUDA(cudaStreamSynchronize(s));
   return 0;
   CB_API_END(h)
 }
@@ -878,6 +905,7 @@ int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, 
   ensure_work(h);
   cudaStream_t s = h->stream;
   if (h->keep_transfers) h->w_delta.alloc((size_t)h->chunk * S.NQ * PROJ_LP * 3);
+  if (h->upload_pending) { CB_CUDA(cudaStreamWaitEvent(s, h->ev_upload, 0)); h->upload_pending = false; }
 
   for (int c0 = 0; c0 < npts; c0 += h->chunk) {
     const int np = std::min(h->chunk, npts - c0);
@@ -897,6 +925,18 @@ int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, 
                               cudaMemcpyDeviceToDevice, s));
     }
     lens_chunk(h, p0, np, tens ? h->w_clt.p : nullptr, 0, aphiphi != nullptr);
+  }
+  {  // the sources of [first, first + npts) are in use until here
+    cb200_handle::BusyRange br{0, first, npts, nullptr};
+    CB_CUDA(cudaEventCreateWithFlags(&br.done, cudaEventDisableTiming));
+    CB_CUDA(cudaEventRecord(br.done, s));
+    h->busy.push_back(br);
+    if (tens) {
+      cb200_handle::BusyRange bt{1, first, npts, nullptr};
+      CB_CUDA(cudaEventCreateWithFlags(&bt.done, cudaEventDisableTiming));
+      CB_CUDA(cudaEventRecord(bt.done, s));
+      h->busy.push_back(bt);
+    }
   }
   return powers_finish(h, first, npts, cls_out, derived_out, status);
   CB_API_END(h)
@@ -921,6 +961,7 @@ int cb200_powers_shared(cb200_handle* h, int src_point, int first, int npts, con
   CB_CUDA(cudaSetDevice(h->cfg.device));
   ensure_work(h);
   cudaStream_t s = h->stream;
+  if (h->upload_pending) { CB_CUDA(cudaStreamWaitEvent(s, h->ev_upload, 0)); h->upload_pending = false; }
   // ---- transfer functions of the source point, once per perturbation type
   std::vector<double> ip1(10, 0.0);
   ip1[0] = 1; ip1[1] = 1; ip1[7] = 0.05; ip1[8] = 0.05;
@@ -1607,6 +1648,7 @@ int cb200_set_option(cb200_handle* h, const char* name, double value) {
   if (n == "count_triples") h->count_triples = value != 0;
   else if (n == "keep_transfers") h->keep_transfers = value != 0;
   else if (n == "ring_stats") h->ring_stats = value != 0;
+  else if (n == "async_upload") h->async_upload = value != 0;
   else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 4) ? (int)value : 3;
   else return fail(h, "set_option: unknown option " + n);
   return 0;
@@ -1640,6 +1682,7 @@ int cb200_sync(cb200_handle* h) {
   if (!h) return -1;
   CB_API_BEGIN
   CB_CUDA(cudaSetDevice(h->cfg.device));
+  CB_CUDA(cudaStreamSynchronize(h->copy_stream));
   CB_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
   CB_API_END(h)

@@ -221,3 +221,28 @@ def test_lensing2018_real_data_golden_chi2(setup):
         b = plan.binned_theory(gold[i], cal=cal[i, 0])
         x = (b - plan.chat.reshape(9, 1)).ravel()
         assert abs(ll[i, 0] - 0.5 * (x @ plan.invcov @ x)) < 1e-8
+
+
+def test_async_upload_matches(setup):
+    """Option "async_upload": the source copy of one block is left in flight on the copy stream while the previous
+    block is evaluated; results must be identical to the blocking path (same kernels, same inputs)."""
+    import torch
+    from cosmomc_b200 import lib
+    b = setup["batch"]
+    h2 = lib.Handle(max_points=4, chunk_points=2, lmax_out=H.LMAX_OUT)
+    h2.set_templates(setup["T"]["highl_unlensed"], setup["T"]["highl_lensed"])
+    pinned = torch.from_numpy(np.ascontiguousarray(b["src"])).pin_memory()
+    per = pinned[0].numel() * 8
+    h2.set_option("async_upload", 1)
+    for a, e in ((0, 2), (2, NPTS)):  # two blocks: block 2 is uploaded while block 1 is evaluated
+        h2.upload_sources(b["thermo"][a:e], b["n_k"][a:e], b["k"][a:e], None, first=a,
+                          src_host_ptr=pinned.data_ptr() + a * per)
+        h2.powers_resident(b["initpower"][a:e], b["alens"][a:e], first=a)
+    h2.set_option("async_upload", 0)
+    h2.sync()
+    setup["h"].set_option("proj_kernel", 3)
+    setup["h"].powers(b["initpower"], b["alens"])  # blocking path, same (default) kernels
+    for i in range(NPTS):
+        got = h2.debug_fetch(2, i)
+        want = setup["h"].debug_fetch(2, i)
+        assert np.array_equal(got, want), i
