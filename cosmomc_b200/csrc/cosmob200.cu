@@ -1543,6 +1543,115 @@ int cb200_loglike_cls(cb200_handle* h, int npts, const double* cls, const double
   CB_API_END(h)
 }
 
+int cb200_eval_batch(cb200_handle* h, const cb200_param_layout* L, int first, int npts, const double* params,
+                     double* loglike, double* likelihoods, double* prior, int* status) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (!L || !params || !loglike || npts <= 0 || L->num_params <= 0) return fail(h, "eval_batch: bad arguments");
+  const double logZero = 1e30;
+  const int np_ = L->num_params;
+  const double T = L->temperature > 0 ? L->temperature : 1.0;
+  const int n_like = (int)h->likes.size();
+  if (n_like == 0) return fail(h, "eval_batch: no likelihood registered");
+  if (L->i_nuis_first + L->n_nuis > np_) return fail(h, "eval_batch: nuisance columns outside the parameter vector");
+  auto col = [&](const double* P, int i, double def) { return i >= 0 ? P[i] : def; };
+  std::vector<double> ip((size_t)npts * 10), al(npts), ap(npts), nuis((size_t)npts * std::max(L->n_nuis, 1), 0.0), pr(npts, 0.0);
+  std::vector<int> st(npts, 0), stp(npts, 0), stl(npts, 0);
+  for (int i = 0; i < npts; i++) {
+    const double* P = params + (size_t)i * np_;
+    // GetLogLikeBounds (calclike.f90:97-109)
+    for (int j = 0; j < np_; j++)
+      if ((L->pmax && P[j] > L->pmax[j]) || (L->pmin && P[j] < L->pmin[j])) { st[i] = 1; break; }
+    // GetLogPriors (calclike.f90:111-134)
+    double lp = 0;
+    if (L->prior_std)
+      for (int j = 0; j < np_; j++)
+        if ((!L->use_prior || L->use_prior[j]) && L->prior_std[j] != 0) {
+          const double d = (P[j] - (L->prior_mean ? L->prior_mean[j] : 0.0)) / L->prior_std[j];
+          lp += d * d;
+        }
+    for (int c = 0; c < L->n_lincomb; c++)
+      if (L->lincomb_std[c] != 0) {
+        double dot = 0;
+        for (int j = 0; j < np_; j++) dot += L->lincomb[(size_t)c * np_ + j] * P[j];
+        const double d = (dot - L->lincomb_mean[c]) / L->lincomb_std[c];
+        lp += d * d;
+      }
+    pr[i] = lp / 2;
+    // CAMBCalc_SetCAMBInitPower (Calculator_CAMB.f90:839-877)
+    double* q = &ip[(size_t)i * 10];
+    q[0] = 1e-10 * std::exp(col(P, L->i_logA, L->def_logA));
+    q[1] = col(P, L->i_ns, L->def_ns);
+    q[2] = col(P, L->i_nrun, L->def_nrun);
+    q[3] = col(P, L->i_nrunrun, L->def_nrunrun);
+    q[4] = col(P, L->i_r, L->def_r);
+    q[5] = col(P, L->i_nt, L->def_nt);
+    q[6] = col(P, L->i_ntrun, L->def_ntrun);
+    q[7] = L->pivot_scalar; q[8] = L->pivot_tensor; q[9] = L->inflation_consistency ? 1.0 : 0.0;
+    al[i] = col(P, L->i_Alens, L->def_Alens);
+    ap[i] = col(P, L->i_Aphiphi, L->def_Aphiphi);
+    for (int j = 0; j < L->n_nuis; j++) nuis[(size_t)i * L->n_nuis + j] = P[L->i_nuis_first + j];
+  }
+  int rc = 0;
+  if (h->n_cmb_likes > 0 || h->kind[0].active) {
+    if (h->kind[0].active) {
+      rc = cb200_powers(h, first, npts, ip.data(), al.data(), ap.data(), nullptr, nullptr, stp.data());
+      if (rc) return rc;
+    }
+  }
+  std::vector<double> ll((size_t)npts * n_like), tot(npts);
+  rc = cb200_loglike_batch(h, first, npts, L->n_nuis ? nuis.data() : nullptr, L->n_nuis, ll.data(), tot.data(), stl.data());
+  if (rc) return rc;
+  for (int i = 0; i < npts; i++) {
+    double v;
+    if (st[i] == 1) v = logZero;                        // out of bounds: nothing else is looked at
+    else {
+      if (stp[i] != 0) st[i] = 1 + stp[i];
+      else if (stl[i] != 0) st[i] = 1 + stl[i];
+      bool zero = st[i] != 0;
+      double sum = 0;
+      for (int k = 0; k < n_like; k++) {
+        const double x = ll[(size_t)i * n_like + k];
+        if (!(x < logZero)) zero = true;                // logZero (or NaN) from a likelihood rejects the point
+        sum += x;
+      }
+      v = zero ? logZero : sum / T + pr[i] / T;
+    }
+    loglike[i] = v;
+    if (status) status[i] = st[i];
+    if (prior) prior[i] = pr[i];
+  }
+  if (likelihoods) std::copy(ll.begin(), ll.end(), likelihoods);
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_test_like_batch(cb200_handle* h, int npts, int n, const double* x, const double* center, const double* covinv,
+                          double* loglike) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (npts <= 0 || n <= 0 || !x || !covinv || !loglike) return fail(h, "test_like_batch: bad arguments");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->stream;
+  std::vector<double> d((size_t)npts * n);
+  for (int i = 0; i < npts; i++)
+    for (int j = 0; j < n; j++) d[(size_t)i * n + j] = x[(size_t)i * n + j] - (center ? center[j] : 0.0);
+  DevBuf<double> dX, dC, dT, dO;
+  dX.upload(d.data(), d.size(), s);
+  dC.upload(covinv, (size_t)n * n, s);
+  dT.alloc((size_t)npts * n);
+  dO.alloc(npts);
+  cb200_handle::Scope sc(h, PH_LIKE);
+  dgemm(s, false, false, npts, n, n, 1.0, dX.p, n, dC.p, n, dT.p, n, &h->n_launches);   // T = X covinv
+  rowdot_kernel<<<(npts + 3) / 4, 128, 0, s>>>(npts, n, dT.p, dX.p, 0.5, dO.p, 1, 0);
+  CB_LAUNCH_CHECK();
+  h->n_launches += 1;
+  CB_CUDA(cudaMemcpyAsync(loglike, dO.p, sizeof(double) * npts, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+  CB_API_END(h)
+}
+
 int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset) {
   if (!h || !t) return -1;
   CB_API_BEGIN

@@ -19,6 +19,9 @@
 
 namespace cb200 {
 
+#ifndef CB200_W3_USKIP
+#define CB200_W3_USKIP 0
+#endif
 #ifndef CB200_W3_S
 #define CB200_W3_S 8
 #endif
@@ -360,10 +363,13 @@ __global__ void __launch_bounds__(32 * W3_NW, CB200_W3_MINB) project3_kernel(con
       const double g0 = t * (a2 + 1), g1 = t * (2 - a2);
 #pragma unroll
       for (int k = 0; k < LK; k++) {
-        const double Jv = (a2 * N0[k].x + b2 * N1[k].x) + (g0 * N0[k].y + g1 * N1[k].y);  // 0 when !act
-        acc[k][0] += s01.x * Jv;
-        acc[k][1] += s01.y * Jv;
-        acc[k][2] += s2 * Jv;
+#if CB200_W3_USKIP
+        if (!__any_sync(0xffffffffu, act[k])) continue;  // no lane of the warp integrates this octet at this step
+#endif
+        const double Jv = fma(g1, N1[k].y, fma(g0, N0[k].y, fma(b2, N1[k].x, a2 * N0[k].x)));  // 0 when !act
+        acc[k][0] = fma(s01.x, Jv, acc[k][0]);
+        acc[k][1] = fma(s01.y, Jv, acc[k][1]);
+        acc[k][2] = fma(s2, Jv, acc[k][2]);
         if (COUNT && p.triples && act[k]) my_triples++;
       }
       if (COUNT && p.ring_stats && li == 0 && ((vm >> pr) & 1u)) st_pairs++;

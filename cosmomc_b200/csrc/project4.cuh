@@ -346,14 +346,14 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   // Register re-balancing: the four producer warps (one warp group, one warp per SM sub-partition) give registers
   // back, the consumers take them.  The pool is what the CTA was launched with (64 K / threads, per thread), so
   // NPW x (launch - PREG) must cover NCW x (CREG - launch).
-  static_assert(W4_NPW == 4 && W4_NCW % 4 == 0 && W4_NPW * (65536 / W4_NT / 8 * 8 - CB200_W4_PREG) >= W4_NCW * (CB200_W4_CREG - 65536 / W4_NT / 8 * 8), "setmaxnreg works on aligned groups of 4 warps");
+  static_assert(W4_NPW % 4 == 0 && W4_NCW % 4 == 0 && W4_NPW * (65536 / W4_NT / 8 * 8 - CB200_W4_PREG) >= W4_NCW * (CB200_W4_CREG - 65536 / W4_NT / 8 * 8), "setmaxnreg works on aligned groups of 4 warps");
   if (!consumer) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 " CB200_STR(CB200_W4_PREG) ";\n");
     // =========================================== PRODUCER ===========================================
     const int m_pair = tid - 32 * NCW;               // pair of the slab owned by this thread
     const bool m_live = m_pair < QC * W4_PNN;        // spare producer threads only take part in the barriers
     const int m_qi = m_live ? m_pair % QC : 0, m_nn = m_pair / QC;
-    const ProjQ3 pc = qc[m_qi];
+    const ProjQ3& pc = qc[m_qi];  // read from shared memory where needed: the producer runs on few registers
     const int pw1 = (pc.valid && m_live) ? max(s_q1[m_qi], 1) : 0x7fffffff;
     const int pw2 = pc.valid ? min(s_q2[m_qi], pc.steps) : 0;
     const double* Sp0 = src + (pc.klo - 1);

@@ -26,6 +26,7 @@ EXPORTS = [
     "cb200_loglike_batch", "cb200_loglike_cls", "cb200_get_timing", "cb200_sync", "cb200_set_option",
     "cb200_timer_start", "cb200_timer_stop", "cb200_measure_fp64_peaks",
     "cb200_powers_shared", "cb200_like_set_bk_foregrounds", "cb200_background", "cb200_set_background", "cb200_like_add_bao", "cb200_like_add_hst", "cb200_like_add_sn",
+    "cb200_eval_batch", "cb200_test_like_batch",
 ]
 
 
@@ -44,6 +45,20 @@ class Info(C.Structure):
                 ["max_l", "max_eta_k", "max_l_tensor", "max_eta_k_tensor", "n_lsamp", "n_lsamp_tensor", "num_xx",
                  "lmax_lensed", "lens_lmax", "lens_npoints", "lens_jmax", "n_tau_max", "n_k_max", "n_q_max",
                  "max_points", "chunk_points", "num_xx_tensor"]]
+
+
+class ParamLayout(C.Structure):
+    """cb200_param_layout (include/cosmob200.h): bounds, priors and the CosmoMC columns that feed the initial power."""
+    _fields_ = ([("num_params", C.c_int), ("pmin", C.POINTER(C.c_double)), ("pmax", C.POINTER(C.c_double)),
+                 ("prior_mean", C.POINTER(C.c_double)), ("prior_std", C.POINTER(C.c_double)),
+                 ("use_prior", C.POINTER(C.c_ubyte)), ("n_lincomb", C.c_int), ("lincomb", C.POINTER(C.c_double)),
+                 ("lincomb_mean", C.POINTER(C.c_double)), ("lincomb_std", C.POINTER(C.c_double)),
+                 ("temperature", C.c_double)] +
+                [(n, C.c_int) for n in ["i_logA", "i_ns", "i_nrun", "i_nrunrun", "i_r", "i_nt", "i_ntrun", "i_Alens",
+                                        "i_Aphiphi"]] +
+                [(n, C.c_double) for n in ["def_logA", "def_ns", "def_nrun", "def_nrunrun", "def_r", "def_nt",
+                                           "def_ntrun", "def_Alens", "def_Aphiphi", "pivot_scalar", "pivot_tensor"]] +
+                [("inflation_consistency", C.c_int), ("i_nuis_first", C.c_int), ("n_nuis", C.c_int)])
 
 
 class Timing(C.Structure):
@@ -110,6 +125,8 @@ def load():
     L.cb200_like_add_hst.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, c_ip]
     L.cb200_like_add_sn.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, C.c_int, C.POINTER(c_dp), C.c_int, C.c_int,
                                     c_ip]
+    L.cb200_eval_batch.argtypes = [C.c_void_p, C.POINTER(ParamLayout), C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_ip]
+    L.cb200_test_like_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp]
     _lib = L
     return L
 
@@ -422,6 +439,61 @@ class Handle:
         d = {n: getattr(t, n) for n, _ in Timing._fields_}
         d["phase_cycles"] = list(t.phase_cycles)
         return d
+
+    def eval_batch(self, params, pmin, pmax, columns, prior_mean=None, prior_std=None, use_prior=None, lincomb=None,
+                   lincomb_mean=None, lincomb_std=None, temperature=1.0, defaults=None, pivot_scalar=0.05,
+                   pivot_tensor=0.05, inflation_consistency=True, nuis_first=0, n_nuis=0, first=0):
+        """TLikeCalculator%GetLogLike for a batch (source/calclike.f90:97-151): params [npts][num_params];
+        columns: dict name -> column index for logA, ns, nrun, nrunrun, r, nt, ntrun, Alens, Aphiphi (missing: default).
+        Returns (loglike[npts], likelihoods[npts][n_like], prior[npts], status[npts])."""
+        P = _d(params)
+        npts, npar = P.shape
+        keep = []
+
+        def ptr(a):
+            if a is None:
+                return None
+            a = _d(a)
+            keep.append(a)
+            return _pd(a)
+        L = ParamLayout()
+        L.num_params = npar
+        L.pmin, L.pmax = ptr(pmin), ptr(pmax)
+        L.prior_mean, L.prior_std = ptr(prior_mean), ptr(prior_std)
+        if use_prior is not None:
+            up = np.ascontiguousarray(use_prior, dtype=np.uint8)
+            keep.append(up)
+            L.use_prior = up.ctypes.data_as(C.POINTER(C.c_ubyte))
+        if lincomb is not None:
+            lc = _d(lincomb).reshape(-1, npar)
+            L.n_lincomb = len(lc)
+            L.lincomb, L.lincomb_mean, L.lincomb_std = ptr(lc), ptr(lincomb_mean), ptr(lincomb_std)
+        L.temperature = temperature
+        dflt = dict(logA=3.044, ns=0.965, nrun=0.0, nrunrun=0.0, r=0.0, nt=0.0, ntrun=0.0, Alens=1.0, Aphiphi=1.0)
+        dflt.update(defaults or {})
+        for name in dflt:
+            setattr(L, "i_" + name, int(columns.get(name, -1)))
+            setattr(L, "def_" + name, float(dflt[name]))
+        L.pivot_scalar, L.pivot_tensor = pivot_scalar, pivot_tensor
+        L.inflation_consistency = int(inflation_consistency)
+        L.i_nuis_first, L.n_nuis = nuis_first, n_nuis
+        ll = np.zeros(npts)
+        likes = np.zeros((npts, max(self.n_like, 1)))
+        pr = np.zeros(npts)
+        st = np.zeros(npts, dtype=np.int32)
+        self._check(self.L.cb200_eval_batch(self.h, C.byref(L), first, npts, _pd(P), _pd(ll), _pd(likes), _pd(pr),
+                                            _pi(st)), "eval_batch")
+        return ll, likes[:, :self.n_like], pr, st
+
+    def test_like_batch(self, x, center, covinv):
+        """test_likelihood = T analogue (source/calclike.f90:180-199): (x-c)^T covinv (x-c) / 2 per row of x."""
+        x = _d(x)
+        npts, n = x.shape
+        c = _d(center)
+        ci = _d(covinv)
+        out = np.zeros(npts)
+        self._check(self.L.cb200_test_like_batch(self.h, npts, n, _pd(x), _pd(c), _pd(ci), _pd(out)), "test_like_batch")
+        return out
 
     def sync(self):
         self._check(self.L.cb200_sync(self.h), "sync")

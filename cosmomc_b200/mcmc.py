@@ -1,0 +1,176 @@
+"""Batched adaptive Metropolis driver: many chains stepped in lockstep, ONE batched likelihood call per step.
+
+CosmoMC runs one chain per MPI rank and evaluates one parameter point per call (`source/driver.F90:54-57`,
+`source/calclike.f90:136`).  The B200 library wants batches, so here K chains advance together and the K proposals of
+a step are one call of `loglike_fn(P[K, n]) -> -lnL[K]` (`Handle.eval_batch`, `Handle.test_like_batch`, ...).  With
+torch.distributed initialised, every rank owns K local chains; the only communication is the all-gather of the
+per-chain (count, mean, covariance) records behind the proposal-covariance update and the R-1 convergence test
+(`cosmomc_b200/chains.py`) - NCCL on the GPU box, gloo in the CPU tests.
+
+Reference behaviour mirrored (host logic, not a kernel):
+  * RandDirectionProposer%ProposeVec / Propose_r  (`source/propose.f90:97-134`): cycle through the columns of a random
+    rotation, step length r = exponential (prob. 0.33) or sqrt(chi2_min(n,2) / min(n,2)), times propose_scale;
+  * BlockProposer%UpdateParams                     (`source/propose.f90:137-144`): P += mapping_matrix . vec with
+    mapping_matrix = sigma_i chol(corr) (`chains.proposal_mapping`, propose.f90:210-244);
+  * TChainSampler_MetropolisAccept                 (`source/MCMC.f90:119-131`): accept if the new -lnL is lower, else
+    with probability exp(-(Like - CurLike)); logZero (1e30) is never accepted;
+  * chain rows: a point is written with its multiplicity when the chain leaves it (`source/MCMC.f90:133-180`,
+    `(*(E16.7))` rows [weight, -lnL, params], `source/GeneralTypes.f90:254-274`);
+  * TMpiChainCollector_UpdateCovAndCheckConverge    (`source/SampleCollector.f90:212-322`): every
+    `update_every` stored samples, pooled covariance -> new proposal (MPI_LearnPropose), R-1 < converge_test stops.
+The random streams are numpy Generators (one per chain), not CosmoMC's ranmar: chains are statistically, not
+bit-wise, the reference's.
+"""
+import os
+
+import numpy as np
+
+from . import chains as _chains
+
+LOG_ZERO = 1e30
+
+
+class RandDirectionProposer:
+    """source/propose.f90:97-134 for one block of n parameters."""
+
+    def __init__(self, n, rng):
+        self.n, self.rng = n, rng
+        self.loopix = 0
+        self.R = None
+
+    def _rotation(self):
+        n = self.n
+        if n == 1:
+            return np.array([[1.0 if self.rng.random() >= 0.5 else -1.0]])
+        q, r = np.linalg.qr(self.rng.normal(size=(n, n)))
+        return q * np.sign(np.diag(r))[None, :]          # Haar-distributed rotation (RandRotation)
+
+    def propose_r(self):
+        if self.rng.random() < 0.33:
+            return self.rng.exponential()
+        m = min(self.n, 2)
+        return np.sqrt((self.rng.normal(size=m) ** 2).sum() / m)
+
+    def propose_vec(self, wid):
+        if self.loopix % self.n == 0:
+            self.R = self._rotation()
+            self.loopix = 0
+        self.loopix += 1
+        return self.R[:, self.loopix - 1] * (self.propose_r() * wid)
+
+
+class BatchedMetropolis:
+    def __init__(self, loglike_fn, start, propose_cov, pmin=None, pmax=None, propose_scale=2.4, seed=0, rank=0,
+                 update_every=None, converge_test=0.01, learn_propose=True, chain_root=None, names=None):
+        """start [K][n]: starting points of this rank's K chains (all n parameters vary)."""
+        self.f = loglike_fn
+        self.P = np.array(start, dtype=np.float64)
+        self.K, self.n = self.P.shape
+        self.pmin = None if pmin is None else np.asarray(pmin, dtype=np.float64)
+        self.pmax = None if pmax is None else np.asarray(pmax, dtype=np.float64)
+        self.scale = propose_scale
+        self.set_covariance(propose_cov)
+        self.rngs = [np.random.default_rng([seed, rank, k]) for k in range(self.K)]
+        self.prop = [RandDirectionProposer(self.n, r) for r in self.rngs]
+        self.like = self._eval(self.P)
+        if np.any(self.like >= LOG_ZERO):
+            raise ValueError("a starting point is rejected (logZero)")
+        self.mult = np.ones(self.K)
+        self.samples = [[self.P[k].copy()] for k in range(self.K)]   # every step's current point (thinning 1)
+        self.update_every = update_every or 50 * self.n               # MPI_Sample_update_freq x n
+        self.converge_test = converge_test
+        self.learn = learn_propose
+        self.R_history = []
+        self.n_steps = 0
+        self.n_accept = np.zeros(self.K, dtype=np.int64)
+        self.rank = rank
+        self.files = None
+        if chain_root is not None:
+            os.makedirs(os.path.dirname(os.path.abspath(chain_root)), exist_ok=True)
+            self.files = [open("%s_%d.txt" % (chain_root, rank * self.K + k + 1), "w") for k in range(self.K)]
+            if rank == 0 and names is not None:
+                write_paramnames(chain_root + ".paramnames", names)
+                write_ranges(chain_root + ".ranges", names, self.pmin, self.pmax)
+
+    def set_covariance(self, cov):
+        self.cov = np.array(cov, dtype=np.float64)
+        self.mapping = _chains.proposal_mapping(self.cov)
+
+    def _eval(self, P):
+        out = np.asarray(self.f(P), dtype=np.float64).copy()
+        if self.pmin is not None:
+            out[np.any(P < self.pmin[None, :], axis=1)] = LOG_ZERO   # GetLogLikeBounds
+        if self.pmax is not None:
+            out[np.any(P > self.pmax[None, :], axis=1)] = LOG_ZERO
+        return out
+
+    def step(self):
+        trial = np.empty_like(self.P)
+        for k in range(self.K):
+            trial[k] = self.P[k] + self.mapping @ self.prop[k].propose_vec(self.scale)
+        like = self._eval(trial)
+        for k in range(self.K):
+            ok = like[k] < LOG_ZERO and (self.like[k] > like[k] or self.rngs[k].exponential() > like[k] - self.like[k])
+            if ok:
+                if self.files is not None:
+                    self.files[k].write(_chains.format_chain_row(self.mult[k], self.like[k], self.P[k]) + "\n")
+                self.P[k], self.like[k], self.mult[k] = trial[k], like[k], 1.0
+                self.n_accept[k] += 1
+            else:
+                self.mult[k] += 1.0
+            self.samples[k].append(self.P[k].copy())
+        self.n_steps += 1
+
+    def update(self):
+        """SampleCollector.f90:212-322 on this rank's chains + all-gather.  Returns the pooled statistics dict."""
+        st = _chains.update_cov_and_check_converge([np.asarray(s) for s in self.samples], self.n)
+        if st.get("ready"):
+            if st.get("R") is not None:
+                self.R_history.append(st["R"])
+            if self.learn:
+                self.set_covariance(st["cov"])
+        return st
+
+    def run(self, max_steps, min_steps=0):
+        """Step until R-1 < converge_test (checked every update_every steps) or max_steps.  Returns True if converged."""
+        while self.n_steps < max_steps:
+            self.step()
+            if self.n_steps % self.update_every == 0:
+                st = self.update()
+                if (st.get("ready") and st.get("R") is not None and st["R"] < self.converge_test
+                        and self.n_steps >= min_steps):
+                    self.close()
+                    return True
+        self.close()
+        return False
+
+    def close(self):
+        if self.files is not None:
+            for k, f in enumerate(self.files):
+                f.write(_chains.format_chain_row(self.mult[k], self.like[k], self.P[k]) + "\n")
+                f.close()
+            self.files = None
+
+
+# ---- chain-side files GetDist reads (source/GeneralTypes.f90:618-736, source/ParamNames.f90, IO.f90) --------------
+def write_paramnames(path, names, labels=None, derived=()):
+    """`<root>.paramnames`: one `name<TAB>label` line per column after [weight, -lnL]; derived names end with `*`."""
+    with open(path, "w") as f:
+        for i, n in enumerate(names):
+            lab = labels[i] if labels is not None else n
+            f.write("%s%s\t%s\n" % (n, "*" if n in derived else "", lab))
+
+
+def write_ranges(path, names, pmin, pmax):
+    """`<root>.ranges`: `name  min  max` with N for an open end (source/ParamNames / getdist ParamBounds)."""
+    with open(path, "w") as f:
+        for i, n in enumerate(names):
+            lo = "N" if pmin is None or not np.isfinite(pmin[i]) else "%.7E" % pmin[i]
+            hi = "N" if pmax is None or not np.isfinite(pmax[i]) else "%.7E" % pmax[i]
+            f.write("%-22s %16s %16s\n" % (n, lo, hi))
+
+
+def read_chain(path):
+    """Inverse of the row writer: returns (weights, loglikes, params[rows][n])."""
+    a = np.atleast_2d(np.loadtxt(path))
+    return a[:, 0], a[:, 1], a[:, 2:]

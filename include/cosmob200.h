@@ -207,6 +207,41 @@ int cb200_loglike_batch(cb200_handle* h, int first, int npts, const double* nuis
 int cb200_loglike_cls(cb200_handle* h, int npts, const double* cls, const double* nuisance, int n_nuis,
                       double* loglikes, double* total, int* status);
 
+/* ---- batch entry: bounds + priors + theory + likelihoods ------------------------------------------------
+ * The reference evaluates ONE parameter point per call (TLikeCalculator%GetLogLike, source/calclike.f90:136-151);
+ * this is the same control flow for a batch of points whose sources are resident (cb200_upload_sources):
+ *   hard bounds (GetLogLikeBounds :97-109) -> logZero = 1e30, else sum of the registered likelihoods / temperature
+ *   (TheoryLike_GetLogLikeMain :293-318, AddLikeTemp :80-94; any soft error or logZero likelihood -> logZero) +
+ *   Gaussian and linear-combination priors / temperature (GetLogPriors :111-134).
+ * The columns of `params` that feed the initial power spectrum follow CAMBCalc_SetCAMBInitPower
+ * (source/Calculator_CAMB.f90:839-877): A_s = 1e-10 exp(logA); a column index of -1 takes the def_* value. */
+typedef struct cb200_param_layout {
+  int num_params;
+  const double* pmin;           /* [num_params] BaseParams%PMin */
+  const double* pmax;           /* [num_params] BaseParams%PMax */
+  const double* prior_mean;     /* [num_params] GaussPriors%mean (NULL: no Gaussian priors) */
+  const double* prior_std;      /* [num_params] GaussPriors%std, 0 = none */
+  const unsigned char* use_prior; /* [num_params] varying(i) .or. include_fixed_parameter_priors; NULL = all */
+  int n_lincomb;                /* BaseParams%LinearCombinations */
+  const double* lincomb;        /* [n_lincomb][num_params] */
+  const double* lincomb_mean;   /* [n_lincomb] */
+  const double* lincomb_std;    /* [n_lincomb], 0 = none */
+  double temperature;           /* TLikeCalculator%Temperature */
+  int i_logA, i_ns, i_nrun, i_nrunrun, i_r, i_nt, i_ntrun, i_Alens, i_Aphiphi;
+  double def_logA, def_ns, def_nrun, def_nrunrun, def_r, def_nt, def_ntrun, def_Alens, def_Aphiphi;
+  double pivot_scalar, pivot_tensor;
+  int inflation_consistency;
+  int i_nuis_first, n_nuis;     /* nuisance parameters of the likelihoods = params[:, i_nuis_first : +n_nuis] */
+} cb200_param_layout;
+/* params [npts][num_params]; loglike [npts] (-ln L incl. priors, 1e30 = rejected); likelihoods [npts][n_like] (may be
+ * NULL); prior [npts] (may be NULL; the un-tempered prior term); status [npts] 0 ok / 1 out of bounds / >1 soft error */
+int cb200_eval_batch(cb200_handle* h, const cb200_param_layout* layout, int first, int npts, const double* params,
+                     double* loglike, double* likelihoods, double* prior, int* status);
+/* TLikeCalculator_TestLikelihoodFunction (source/calclike.f90:180-199): -ln L = (x - c)^T covinv (x - c) / 2 for
+ * x [npts][n]; used by `test_likelihood = T` runs and by the adaptive-MCMC tests (one DMMA GEMM + row dots) */
+int cb200_test_like_batch(cb200_handle* h, int npts, int n, const double* x, const double* center, const double* covinv,
+                          double* loglike);
+
 /* ---- timing / counters (DebugMsgs timings of camb/cmbmain.f90:152-165,265-269, lensing.f90:516) ------- */
 typedef struct cb200_timing {
   float ms_spline, ms_project, ms_contract, ms_interp, ms_lens, ms_like, ms_total;

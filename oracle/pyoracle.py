@@ -261,6 +261,43 @@ def set_powers(cl_lensed, cl_phi, lmax_computed_cl, cl_lmax, highl, Aphiphi=1.0,
     return out, hn.value, rms.value
 
 
+def get_loglike(P, likes, pmin=None, pmax=None, prior_mean=None, prior_std=None, use_prior=None, lincomb=None,
+                lincomb_mean=None, lincomb_std=None, temperature=1.0, soft_error=None):
+    """TLikeCalculator%GetLogLike for rows of P given the per-likelihood -lnL (source/calclike.f90:97-151): hard bounds
+    -> logZero, sum of likelihoods / Temperature (AddLikeTemp :80-94, logZero propagates), Gaussian and linear-
+    combination priors / Temperature (GetLogPriors :111-134).  Returns (loglike, prior, status)."""
+    P = np.atleast_2d(np.asarray(P, dtype=np.float64))
+    likes = np.atleast_2d(np.asarray(likes, dtype=np.float64))
+    npts, n = P.shape
+    logZero = 1e30
+    out = np.zeros(npts)
+    prior = np.zeros(npts)
+    st = np.zeros(npts, dtype=np.int32)
+    for i in range(npts):
+        lp = 0.0
+        if prior_std is not None:
+            for j in range(n):
+                if (use_prior is None or use_prior[j]) and prior_std[j] != 0:
+                    lp += ((P[i, j] - (prior_mean[j] if prior_mean is not None else 0.0)) / prior_std[j]) ** 2
+        if lincomb is not None:
+            for c, comb in enumerate(np.atleast_2d(lincomb)):
+                if lincomb_std[c] != 0:
+                    lp += ((np.dot(comb, P[i]) - lincomb_mean[c]) / lincomb_std[c]) ** 2
+        prior[i] = lp / 2
+        oob = (pmax is not None and np.any(P[i] > np.asarray(pmax))) or (pmin is not None and np.any(P[i] < np.asarray(pmin)))
+        if oob:
+            st[i] = 1
+            out[i] = logZero
+            continue
+        if soft_error is not None and soft_error[i]:
+            st[i] = 1 + int(soft_error[i])
+        if st[i] != 0 or np.any(~(likes[i] < logZero)):
+            out[i] = logZero
+        else:
+            out[i] = likes[i].sum() / temperature + prior[i] / temperature
+    return out, prior, st
+
+
 def quadform(M, v):
     M = _d(M)
     v = _d(v)

@@ -246,3 +246,37 @@ def test_async_upload_matches(setup):
         got = h2.debug_fetch(2, i)
         want = setup["h"].debug_fetch(2, i)
         assert np.array_equal(got, want), i
+
+
+def test_eval_batch_matches_get_loglike(setup):
+    """cb200_eval_batch = GetLogLike of the reference for a batch (bounds -> logZero, likelihood sum / T, priors / T):
+    composed here from the same library calls + the oracle's control-flow restatement."""
+    import pyoracle as o
+    from cosmomc_b200 import lib, synthetic as syn
+    b, T = setup["batch"], setup["T"]
+    h2 = lib.Handle(max_points=4, chunk_points=2, lmax_out=H.LMAX_OUT)
+    h2.set_templates(T["highl_unlensed"], T["highl_lensed"])
+    h2.upload_sources(b["thermo"], b["n_k"], b["k"], b["src"])
+    fid = np.zeros((5, H.LMAX_OUT + 1))
+    fid[:3] = T["theory_cl"][:, :3].T
+    d = syn.synthetic_pliklite(H.LMAX_OUT, fiducial_cls=fid)
+    h2.add_pliklite(d["nb"], d["blmin"], d["blmax"], d["weights"], d["invcov"], d["x_data"], 0)
+    ip = b["initpower"]
+    # CosmoMC-style parameter rows: [logA, ns, nrun, Alens, calPlanck]
+    P = np.stack([np.log(1e10 * ip[:, 0]), ip[:, 1], ip[:, 2], b["alens"], b["cal"]], axis=1)
+    P[1, 1] = 1.5                                   # point 1 leaves the prior box in ns
+    pmin, pmax = [1.0, 0.8, -1.0, 0.0, 0.9], [5.0, 1.2, 1.0, 3.0, 1.1]
+    kw = dict(prior_mean=[0, 0.96, 0, 0, 1.0], prior_std=[0, 0.02, 0, 0, 0.0025], lincomb=[[0, 1, 1, 0, 0]],
+              lincomb_mean=[0.95], lincomb_std=[0.05], temperature=1.5)
+    ll, likes, pr, st = h2.eval_batch(P, pmin, pmax, dict(logA=0, ns=1, nrun=2, Alens=3), nuis_first=4, n_nuis=1,
+                                      pivot_scalar=ip[0, 7], pivot_tensor=ip[0, 8], inflation_consistency=bool(ip[0, 9]),
+                                      defaults=dict(nrunrun=ip[0, 3], r=ip[0, 4], nt=ip[0, 5], ntrun=ip[0, 6]), **kw)
+    # the same likelihood values through the separate calls
+    ip2 = ip.copy()
+    ip2[:, 1] = P[:, 1]
+    h2.powers_resident(ip2, b["alens"])
+    want_likes, tot, st2 = h2.loglike_batch(NPTS, b["cal"].reshape(-1, 1))
+    want, wprior, wst = o.get_loglike(P, want_likes, pmin=pmin, pmax=pmax, **kw)
+    assert st.tolist() == wst.tolist() == [0, 1, 0]
+    assert np.allclose(likes, want_likes, rtol=1e-12) and np.allclose(pr, wprior, rtol=1e-13)
+    assert ll[1] == 1e30 and np.allclose(ll, want, rtol=1e-12)

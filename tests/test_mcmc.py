@@ -1,0 +1,123 @@
+"""Host logic of the batched adaptive Metropolis driver (BASELINE configs[4] first stage: the
+`test_likelihood = T` Gaussian, source/calclike.f90:180-199): CPU tests with a numpy likelihood, the world_size-2 gloo
+path, chain files; the GPU tests run the same driver on the library's batched likelihood calls."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+
+def _target(n, seed=3):
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=(n, n))
+    C = A @ A.T / n + np.eye(n)
+    s = np.linspace(0.5, 2.0, n)
+    C = C * np.outer(s, s)
+    return C, np.linalg.inv(C), rng.normal(size=n)
+
+
+def _gauss(Ci, c):
+    return lambda P: 0.5 * np.einsum("ki,ij,kj->k", P - c, Ci, P - c)
+
+
+def test_metropolis_recovers_gaussian(tmp_path):
+    from cosmomc_b200 import mcmc
+    n, K = 4, 16
+    C, Ci, c = _target(n)
+    rng = np.random.default_rng(0)
+    start = c + rng.normal(size=(K, n)) * np.sqrt(np.diag(C))
+    root = str(tmp_path / "chains" / "test")
+    names = ["p%d" % i for i in range(n)]
+    m = mcmc.BatchedMetropolis(_gauss(Ci, c), start, np.diag(np.diag(C)) * 4.0, seed=1, update_every=400,
+                               converge_test=0.02, chain_root=root, names=names)
+    conv = m.run(max_steps=12000, min_steps=2000)
+    assert conv and m.R_history[-1] < 0.02
+    # the learned proposal covariance is the pooled sample covariance: close to the target
+    assert np.abs(m.cov - C).max() < 0.15 * np.abs(C).max()
+    acc = m.n_accept.sum() / (m.K * m.n_steps)
+    assert 0.1 < acc < 0.6, acc
+    # chain files: weights sum to steps + 1 per chain, rows re-read exactly at E16.7 precision, sample mean ~ centre
+    w, ll, P = mcmc.read_chain(root + "_1.txt")
+    assert abs(w.sum() - (m.n_steps + 1)) < 1e-9
+    assert np.allclose(ll, _gauss(Ci, c)(P), rtol=2e-6, atol=2e-6)
+    allP = np.concatenate([np.repeat(np.asarray(s), 1, axis=0) for s in m.samples])
+    assert np.abs(allP[len(allP) // 2:].mean(axis=0) - c).max() < 0.15 * np.sqrt(np.diag(C)).max()
+    lines = open(root + ".paramnames").read().split("\n")
+    assert lines[0] == "p0\tp0" and len(open(root + ".ranges").read().split("\n")) == n + 1
+
+
+def test_bounds_reject_and_logzero_never_accepted():
+    from cosmomc_b200 import mcmc
+    n, K = 2, 8
+    C, Ci, c = np.eye(2), np.eye(2), np.zeros(2)
+    m = mcmc.BatchedMetropolis(_gauss(Ci, c), np.zeros((K, n)) + 0.1, C, pmin=[-0.5, -10], pmax=[0.5, 10], seed=5)
+    for _ in range(300):
+        m.step()
+    allP = np.concatenate([np.asarray(s) for s in m.samples])
+    assert allP[:, 0].min() >= -0.5 and allP[:, 0].max() <= 0.5       # hard prior box (GetLogLikeBounds)
+    assert np.abs(allP[:, 1]).max() > 0.6                            # the unbounded direction does move
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch.distributed as dist
+from cosmomc_b200 import mcmc
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2,
+                        init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"])
+rank = dist.get_rank()
+n, K = 3, 4
+C = np.array([[1.0, 0.3, 0.0], [0.3, 2.0, -0.4], [0.0, -0.4, 0.5]]); Ci = np.linalg.inv(C)
+f = lambda P: 0.5 * np.einsum("ki,ij,kj->k", P, Ci, P)
+rng = np.random.default_rng(7 + rank)
+m = mcmc.BatchedMetropolis(f, rng.normal(size=(K, n)), np.eye(n), seed=11, rank=rank, update_every=300, converge_test=0.03)
+conv = m.run(max_steps=9000, min_steps=1500)
+np.savez(os.environ["OUT"] + str(rank) + ".npz", cov=m.cov, R=np.array(m.R_history), conv=conv, steps=m.n_steps)
+dist.destroy_process_group()
+"""
+
+
+def test_gloo_two_ranks_share_the_learned_covariance(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER % H.ROOT)
+    env = dict(os.environ, PORT="29741", OUT=str(tmp_path / "r"))
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r))) for r in range(2)]
+    assert all(p.wait(timeout=240) == 0 for p in procs)
+    a, b = np.load(str(tmp_path / "r0.npz")), np.load(str(tmp_path / "r1.npz"))
+    # both ranks saw all 8 chains: identical pooled covariance and R-1 history, same stopping step
+    assert np.array_equal(a["cov"], b["cov"]) and np.array_equal(a["R"], b["R"]) and int(a["steps"]) == int(b["steps"])
+    C = np.array([[1.0, 0.3, 0.0], [0.3, 2.0, -0.4], [0.0, -0.4, 0.5]])
+    assert bool(a["conv"]) and np.abs(a["cov"] - C).max() < 0.3
+
+
+def test_eval_batch_control_flow_restatement():
+    """numpy restatement of GetLogLike (calclike.f90:97-151) used as the checker of cb200_eval_batch in the GPU tests."""
+    sys.path.insert(0, os.path.join(H.ROOT, "oracle"))
+    import pyoracle as o
+    P = np.array([[1.0, 2.0], [5.0, 2.0], [1.0, 2.5]])
+    likes = np.array([[3.0, 4.0], [3.0, 4.0], [1e30, 4.0]])
+    out, prior, st = o.get_loglike(P, likes, pmin=[0, 0], pmax=[2, 3], prior_mean=[1, 2], prior_std=[0, 0.5],
+                                   lincomb=[[1.0, 1.0]], lincomb_mean=[3.0], lincomb_std=[0.1], temperature=2.0)
+    assert st.tolist() == [0, 1, 0]
+    assert out[0] == pytest.approx((7.0 + 0.0) / 2.0) and out[1] == 1e30 and out[2] == 1e30
+    assert prior[2] == pytest.approx(0.5 * (1.0 + 25.0))
+
+
+@pytest.mark.gpu
+def test_gpu_test_likelihood_and_driver():
+    from cosmomc_b200 import lib, mcmc
+    n, K = 6, 64
+    C, Ci, c = _target(n, seed=9)
+    h = lib.Handle(lmax_computed_cl=0, max_points=K)  # background-only handle: no CMB tables needed
+    rng = np.random.default_rng(2)
+    X = c + rng.normal(size=(K, n))
+    got = h.test_like_batch(X, c, Ci)
+    assert np.allclose(got, _gauss(Ci, c)(X), rtol=1e-12, atol=1e-12)
+    m = mcmc.BatchedMetropolis(lambda P: h.test_like_batch(P, c, Ci), X, np.eye(n), seed=3, update_every=300,
+                               converge_test=0.02)
+    assert m.run(max_steps=6000, min_steps=900)
+    assert np.abs(m.cov - C).max() < 0.12 * np.abs(C).max()
