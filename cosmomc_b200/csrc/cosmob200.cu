@@ -123,6 +123,7 @@ struct cb200_handle {
   DevBuf<unsigned long long> d_triples;
   bool count_triples = false, ring_stats = false;
   int proj_kernel = 3;
+  int spline_kernel = 2;  // 1: one thread per row straight from global memory, 2: tiled through shared memory
   DevBuf<unsigned long long> d_ring_stats;
   DevBuf<unsigned char> w_fallback;  // [chunk][NQB] blocks left to the chunked kernel by project4_kernel
   // resident outputs
@@ -323,7 +324,7 @@ void ensure_work(cb200_handle* h) {
   const size_t NTK = std::max((size_t)h->cfg.n_tau_max * h->cfg.n_k_max,
                               tens ? (size_t)h->cfg.n_tau_max_tensor * h->cfg.n_k_max_tensor : (size_t)0);
   const int NQB = (NQ + PROJ_Q - 1) / PROJ_Q;  // v1 needs the larger partial buffer
-  h->w_coef.alloc((size_t)C * 4 * NK);
+  h->w_coef.alloc((size_t)C * 5 * NK);
   h->w_ddsrc.alloc((size_t)C * NTK * 3);
   h->w_part.alloc((size_t)C * NQB * 6 * PROJ_LP);
   h->w_fallback.alloc((size_t)C * NQB);
@@ -679,7 +680,18 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
     spline_setup_kernel<<<(np + 63) / 64, 64, 0, s>>>(v, p0, np, h->w_coef.p);
     CB_LAUNCH_CHECK();
     const long long rows = (long long)np * S.NT * 3;
-    source_spline_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(v, p0, np, h->w_coef.p, h->w_ddsrc.p);
+    if (h->spline_kernel == 2 && S.NK % 2 == 0) {
+      const int tiles = (S.NT * 3 + SPL_ROWS - 1) / SPL_ROWS;
+      const size_t smem = sizeof(double) * ((size_t)5 * S.NK + (size_t)SPL_ROWS * (S.NK + 1));
+      static bool attr_set = false;
+      if (!attr_set) {
+        CB_CUDA(cudaFuncSetAttribute(source_spline_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+      }
+      source_spline_tiled_kernel<<<(unsigned)(tiles * np), SPL_THREADS, smem, s>>>(v, p0, np, h->w_coef.p, h->w_ddsrc.p);
+    } else {
+      source_spline_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(v, p0, np, h->w_coef.p, h->w_ddsrc.p);
+    }
     CB_LAUNCH_CHECK();
     h->n_launches += 2;
   }
@@ -1758,6 +1770,7 @@ int cb200_set_option(cb200_handle* h, const char* name, double value) {
   else if (n == "keep_transfers") h->keep_transfers = value != 0;
   else if (n == "ring_stats") h->ring_stats = value != 0;
   else if (n == "async_upload") h->async_upload = value != 0;
+  else if (n == "spline_kernel") h->spline_kernel = (value == 1) ? 1 : 2;
   else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 4) ? (int)value : 3;
   else return fail(h, "set_option: unknown option " + n);
   return 0;
