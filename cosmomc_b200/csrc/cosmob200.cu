@@ -122,7 +122,7 @@ struct cb200_handle {
   int last_chunk_p0 = 0, last_chunk_np = 0;
   DevBuf<unsigned long long> d_triples;
   bool count_triples = false, ring_stats = false;
-  int proj_kernel = 3;
+  int proj_kernel = 4;
   int spline_kernel = 2;  // 1: one thread per row straight from global memory, 2: tiled through shared memory
   DevBuf<unsigned long long> d_ring_stats;
   DevBuf<unsigned char> w_fallback;  // [chunk][NQB] blocks left to the chunked kernel by project4_kernel
@@ -1692,7 +1692,7 @@ int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset) {
   t->ring_slabs = (long long)rs[0]; t->ring_direct = (long long)rs[1]; t->ring_rows = (long long)rs[2];
   t->ring_pairs = (long long)rs[3];
   t->proj_mask_mismatch = (h->proj_kernel == 4) ? (long long)rs[1] : 0;
-  if (getenv("CB200_DEBUG_WAIT")) fprintf(stderr, "[cb200] consumer warp0 wait cycles: all %llu, before producer arrive %llu\n", rs[10], rs[11]);
+  if (getenv("CB200_DEBUG_WAIT")) fprintf(stderr, "[cb200] consumer warp0 wait cycles: all %llu, before last metadata arrive %llu, before ring-warp arrive %llu\n", rs[10], rs[11], rs[12]);
   if (reset) {
     for (int p = 0; p < PH_COUNT; p++) {
       for (auto& e : h->ev[p]) { h->ev_pool.push_back(e.first); h->ev_pool.push_back(e.second); }
@@ -1771,7 +1771,7 @@ int cb200_set_option(cb200_handle* h, const char* name, double value) {
   else if (n == "ring_stats") h->ring_stats = value != 0;
   else if (n == "async_upload") h->async_upload = value != 0;
   else if (n == "spline_kernel") h->spline_kernel = (value == 1) ? 1 : 2;
-  else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 4) ? (int)value : 3;
+  else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 4) ? (int)value : 4;
   else return fail(h, "set_option: unknown option " + n);
   return 0;
 }

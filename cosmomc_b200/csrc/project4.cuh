@@ -43,13 +43,18 @@ constexpr int W4_NPAIR = W4_QC * W4_S;
 #endif
 constexpr int W4_NPW = CB200_W4_NPW;  // producer warps
 constexpr int W4_NT = 32 * (W4_NCW + W4_NPW);  // threads per CTA
+#ifndef CB200_W4_MG
+#define CB200_W4_MG 1
+#endif
+constexpr int W4_MG = CB200_W4_MG;              // metadata groups: group g computes the slabs t = g (mod MG)
+constexpr int W4_MW = (W4_NPW - 1) / W4_MG;     // warps per metadata group (producer warp 0 keeps the ring filled)
 constexpr int w4_pnn() {  // largest divisor of S that the producer threads cover in one sweep
   int best = 1;
   for (int d = 1; d <= W4_S; d++)
-    if (W4_S % d == 0 && d * W4_QC <= 32 * W4_NPW) best = d;
+    if (W4_S % d == 0 && d * W4_QC <= 32 * W4_MW) best = d;
   return best;
 }
-constexpr int W4_PNN = w4_pnn();               // time samples covered by one sweep of the producer threads
+constexpr int W4_PNN = w4_pnn();               // time samples covered by one sweep of the metadata threads
 constexpr int W4_PPT = W4_S / W4_PNN;          // (q, tau) pairs per producer thread: same q, samples W4_PNN apart
 static_assert(W4_PNN >= 1 && W4_S % W4_PNN == 0, "slab shape");
 #ifndef CB200_W4_CREG
@@ -88,7 +93,13 @@ struct Proj4Params {
 };
 
 #ifndef CB200_W4_KB
-#define CB200_W4_KB 6
+#define CB200_W4_KB 2
+#endif
+#ifndef CB200_W4_UNSAFE_NORINGWAIT
+#define CB200_W4_UNSAFE_NORINGWAIT 0  // timing experiment only: WRONG results
+#endif
+#ifndef CB200_W4_CHAIN
+#define CB200_W4_CHAIN 0
 #endif
 #ifndef CB200_W4_NST
 #define CB200_W4_NST 4
@@ -96,7 +107,7 @@ struct Proj4Params {
 constexpr int W4_NST = CB200_W4_NST;  // metadata buffers = slabs the producer may run ahead of the consumers
 constexpr size_t W4_META_BYTES = (size_t)W4_NST * W4_NPAIR * 48;
 constexpr size_t W4_QC_BYTES = sizeof(ProjQ3) * W4_QC;
-constexpr size_t W4_MISC_BYTES = 512;
+constexpr size_t W4_MISC_BYTES = 768;
 inline size_t w4_slab_table_bytes(int NT) { return (size_t)8 * ((NT + W4_S - 1) / W4_S + 2); }
 // per-(wavenumber, multipole slot) integration windows {n1, n2} as 2 x u16, rows padded to an odd word count
 inline size_t w4_wtab_bytes(int LK) { return (size_t)4 * W4_QC * (8 * LK + 1); }
@@ -204,8 +215,17 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
       const double dqv = v.dq[(size_t)pt * v.NQ + qi];
       c.q = qv;
       c.w = (p.tensors ? tensor_power_dev(ip, qv) : scalar_power_dev(ip, qv)) * (dqv / qv);
-      int klo = 1;
-      while ((qv > ksrc[klo]) && (klo < (nk - 1))) klo++;
+      // klo = first index in [1, nk-1] with qv <= ksrc[klo] (else nk-1): the reference's linear scan
+      // (cmbmain.f90:1313-1316) as a binary search - same result on the ascending source grid, 8 loads instead of ~100
+      int klo = nk - 1;
+      {
+        int lo_ = 1, hi_ = nk - 1;
+        while (lo_ < hi_) {
+          const int mid = (lo_ + hi_) >> 1;
+          if (qv > ksrc[mid]) lo_ = mid + 1; else hi_ = mid;
+        }
+        klo = lo_;
+      }
       c.klo = klo;
       const double ho = ksrc[klo] - ksrc[klo - 1];
       c.a0 = (ksrc[klo] - qv) / ho;
@@ -231,7 +251,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   if (tid == 0) {
     s_misc[0] = 0x7fffffff; s_misc[1] = 0; s_misc[2] = 0;
     for (int i = 0; i < W4_NST; i++) {
-      mbar_init(s_bar + i, 32 * W4_NPW);     // full: every producer thread arrives (+ the bytes of its bulk copies)
+      mbar_init(s_bar + i, 32 * (1 + W4_MW)); // full: ring warp + one metadata group arrive (+ the bytes of the bulk copies)
       mbar_init(s_bar + W4_NST + i, NCW);    // empty: one lane per consumer warp
     }
   }
@@ -339,7 +359,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   if (s_misc[2] != 0) return;
 
   unsigned long long my_triples = 0, st_slabs = 0, st_rows = 0, st_late = 0, st_mismatch = 0;
-  long long st_wait_all = 0, st_wait_prod = 0;
+  long long st_wait_all = 0, st_wait_prod = 0, st_wait_ring = 0;
   long long ck_a = 0, ck_b = 0, ck_c = 0, ck_t0 = clock64(), ck_t;
 #define CK4(var) do { if (COUNT) { ck_t = clock64(); var += ck_t - ck_t0; ck_t0 = ck_t; } } while (0)
 
@@ -350,11 +370,18 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   if (!consumer) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 " CB200_STR(CB200_W4_PREG) ";\n");
     // =========================================== PRODUCER ===========================================
-    const int m_pair = tid - 32 * NCW;               // pair of the slab owned by this thread
-    const bool m_live = m_pair < QC * W4_PNN;        // spare producer threads only take part in the barriers
+    // producer warp 0 keeps the ring filled (TMA bulk copies); the other producer warps compute the pair metadata.
+    // The two roles only meet the consumers (full / empty barriers), never each other: the metadata runs ahead as far
+    // as the NST buffers allow even while the ring warp waits for room.
+    const bool ring_warp = (warp == NCW);
+    const int m_tid = tid - 32 * (NCW + 1);          // metadata thread index
+    const int m_grp = ring_warp ? 0 : min(m_tid / (32 * W4_MW), W4_MG);  // == MG: spare warp (exits)
+    const int m_pair = m_tid - m_grp * 32 * W4_MW;   // pair of the slab owned by this (metadata) thread
+    const bool m_live = !ring_warp && m_pair < QC * W4_PNN;  // spare threads only take part in the barriers
+    if (!ring_warp && m_grp >= W4_MG) return;
     const int m_qi = m_live ? m_pair % QC : 0, m_nn = m_pair / QC;
     const ProjQ3& pc = qc[m_qi];  // read from shared memory where needed: the producer runs on few registers
-    const int pw1 = (pc.valid && m_live) ? max(s_q1[m_qi], 1) : 0x7fffffff;
+    const int pw1 = (pc.valid && m_live) ? max(s_q1[m_qi], 1) : 0x7fffffff;  // (ring warp: never valid)
     const int pw2 = pc.valid ? min(s_q2[m_qi], pc.steps) : 0;
     const double* Sp0 = src + (pc.klo - 1);
     const double* Dp0 = dds + (pc.klo - 1);
@@ -384,14 +411,14 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     // rows [a, b] of the table -> ring by TMA bulk copies (one per row; slot 0 is mirrored behind slot R-1);
     // their bytes are accounted on the slab's `full` barrier, so nobody waits for them but the consumers
     auto fetch_rows = [&](int a, int b, unsigned long long* bar) {
-      for (int row = a + m_pair; row <= b; row += 32 * W4_NPW) {
+      for (int row = a + lane; row <= b; row += 32) {
         const int slot = row % R;
         const double2* g = p.bes + (size_t)row * PROJ_LP;
         mbar_expect_tx(bar, slot == 0 ? 2 * rb : rb);
         bulk_g2s(ring + (size_t)slot * rb, g, rb, bar);
         if (slot == 0) bulk_g2s(ring + (size_t)R * rb, g, rb, bar);
       }
-      if (COUNT && p.ring_stats && m_pair == 0 && b >= a) st_rows += b - a + 1;
+      if (COUNT && p.ring_stats && lane == 0 && b >= a) st_rows += b - a + 1;
     };
     int rlo = 0x7fffffff;      // lowest resident row (identical in every producer thread by construction)
     int released = -1;         // slabs <= released have been released by every consumer warp
@@ -399,9 +426,9 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
 #pragma unroll
     for (int u = 0; u < PPT; u++) { jlo[u] = NJ; jhi[u] = NJ - 1; }
     const unsigned* wrow = s_wtab + m_qi * NJP;
-    if (nslab > 0) prefetch(n_lo);
+    if (!ring_warp && m_grp < nslab) prefetch(n_lo + m_grp * S);
     CK4(ck_a);
-    for (int t = 0; t < nslab; t++) {
+    for (int t = ring_warp ? 0 : m_grp; t < nslab; t += ring_warp ? 1 : W4_MG) {
       const int par = t % W4_NST;
       // metadata buffer `par` is free once the consumers have released slab t - NST (slabs are released in order)
       if (t >= W4_NST) {
@@ -409,23 +436,26 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         released = max(released, t - W4_NST);
       }
       CK4(ck_c);
-      const int2 w = s_win[t];
-      // The windows slide towards lower rows (x falls with tau).  Rows [w.x, ...] may overwrite ring slots only if
-      // the highest row still needed by the oldest slab not yet released stays within R rows of w.x.
-      while (released + 1 < t && s_win[released + 1].y - w.x + 1 > R) {
-        const int r = released + 1;
-        mbar_wait(s_bar + W4_NST + (r % W4_NST), (r / W4_NST) & 1);
-        released = r;
-        if (COUNT && p.ring_stats && m_pair == 0) st_late++;
-      }
-      CK4(ck_c);
-      {
+      if (ring_warp) {
+        const int2 w = s_win[t];
+        // The windows slide towards lower rows (x falls with tau).  Rows [w.x, ...] may overwrite ring slots only
+        // if the highest row still needed by the oldest slab not yet released stays within R rows of w.x.
+        while (!CB200_W4_UNSAFE_NORINGWAIT && released + 1 < t && s_win[released + 1].y - w.x + 1 > R) {
+          const int r = released + 1;
+          mbar_wait(s_bar + W4_NST + (r % W4_NST), (r / W4_NST) & 1);
+          released = r;
+          if (COUNT && p.ring_stats && lane == 0) st_late++;
+        }
+        CK4(ck_c);
         const int f_hi = (rlo <= w.y) ? rlo - 1 : w.y;  // rows >= rlo are resident (fetched for earlier slabs)
         if (w.x <= f_hi) fetch_rows(w.x, f_hi, s_bar + par);
         rlo = min(rlo, w.x);
+        if (COUNT && p.ring_stats && lane == 0) st_slabs++;
+        CK4(ck_b);
+        if (COUNT && lane == 0) s_bar[24 + par] = (unsigned long long)clock64();
+        mbar_arrive(s_bar + par);
+        continue;
       }
-      if (COUNT && p.ring_stats && m_pair == 0) st_slabs++;
-      CK4(ck_b);
       // ---- metadata of this thread's pairs ----
 #pragma unroll
       for (int u = 0; u < PPT; u++) {
@@ -464,14 +494,14 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
           m_rec[pidx] = rec;
         }
       }
-      if (t + 1 < nslab) prefetch(n_lo + (t + 1) * S);
+      if (t + W4_MG < nslab) prefetch(n_lo + (t + W4_MG) * S);
       CK4(ck_a);
-      if (COUNT && m_pair == 0) s_bar[16 + par] = (unsigned long long)clock64();
+      if (COUNT) atomicMax(s_bar + 16 + par, (unsigned long long)clock64());
       mbar_arrive(s_bar + par);
       CK4(ck_c);
     }
     if (COUNT && p.ring_stats) {
-      if (m_pair == 0) {
+      if (ring_warp && lane == 0) {
         atomicAdd(p.ring_stats + 0, st_slabs);
         atomicAdd(p.ring_stats + 2, st_rows); atomicAdd(p.ring_stats + 3, st_late);
       }
@@ -498,9 +528,11 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     if (COUNT) tw0 = clock64();
     mbar_wait(s_bar + par, (t / W4_NST) & 1);
     if (COUNT && p.ring_stats && tid == 0) {
-      const long long tw1 = clock64(), ta = (long long)s_bar[16 + par];
+      const long long tw1 = clock64(), ta = (long long)s_bar[16 + par], tr = (long long)s_bar[24 + par];
       st_wait_all += tw1 - tw0;
-      if (ta > tw0) st_wait_prod += ta - tw0;   // part of the wait spent before the last producer thread arrived
+      if (ta > tw0) st_wait_prod += ta - tw0;   // part of the wait spent before the last metadata thread arrived
+      if (tr > tw0) st_wait_ring += tr - tw0;   // ... before the ring warp had issued this slab's copies
+      s_bar[16 + par] = 0;
     }
     CK4(ck_b);
     const unsigned char* mb = meta_base + (size_t)par * NPAIR * 48;
@@ -567,8 +599,12 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
               jbits |= __double2hiint(Jv);
             }
           }
+#if CB200_W4_CHAIN
           if (k0 + KB < LKH)
             asm volatile("{\n .reg .b32 t;\n and.b32 t, %1, %2;\n add.u32 %0, %0, t;\n}\n" : "+r"(rp) : "r"(jbits), "r"(p.zero));
+#else
+          (void)jbits;
+#endif
         }
       }
     }
@@ -583,7 +619,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     if (lane == 0 && t) atomicAdd(p.triples, t);
   }
   if (COUNT && p.ring_stats && st_mismatch) atomicAdd(p.ring_stats + 1, st_mismatch);
-  if (COUNT && p.ring_stats && tid == 0) { atomicAdd(p.ring_stats + 10, (unsigned long long)st_wait_all); atomicAdd(p.ring_stats + 11, (unsigned long long)st_wait_prod); }
+  if (COUNT && p.ring_stats && tid == 0) { atomicAdd(p.ring_stats + 10, (unsigned long long)st_wait_all); atomicAdd(p.ring_stats + 11, (unsigned long long)st_wait_prod); atomicAdd(p.ring_stats + 12, (unsigned long long)st_wait_ring); }
   if (COUNT && p.ring_stats && lane == 0) {  // consumer: prologue, wait for the producer, accumulate
     atomicAdd(p.ring_stats + 4, (unsigned long long)ck_a); atomicAdd(p.ring_stats + 6, (unsigned long long)ck_b);
     atomicAdd(p.ring_stats + 8, (unsigned long long)ck_c);

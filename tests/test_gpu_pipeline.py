@@ -154,19 +154,18 @@ def test_triple_count_matches_oracle(setup):
     h.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
     t = h.timing()
     h.set_option("ring_stats", 0)
-    h.set_option("proj_kernel", 3)
     assert t["ring_slabs"] > 0 and t["proj_mask_mismatch"] == 0, t
 
 
-@pytest.mark.parametrize("pk", [1, 2, 4])
+@pytest.mark.parametrize("pk", [1, 2, 3])
 def test_earlier_projection_kernels_agree(setup, pk):
-    """The other projection kernels (1: direct L2 gathers, 2: windowed warp-per-pair, 4: all multipoles per
-    quarter-warp with producer/consumer warps, TMA-filled ring and mbarriers) stay as cross-checks of the default
-    (3: quarter-warp pairs per 32-multipole chunk)."""
+    """The earlier projection kernels (1: direct L2 gathers, 2: windowed warp-per-pair, 3: quarter-warp pairs per
+    32-multipole chunk - also the fallback pass of the default) stay as cross-checks of the default (4: all multipoles
+    per quarter-warp, producer/consumer warps, TMA-filled ring on mbarriers)."""
     h, orc = setup["h"], setup["orc"]
     h.set_option("proj_kernel", pk)
     cls, derived, status = h.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
-    h.set_option("proj_kernel", 3)
+    h.set_option("proj_kernel", 4)
     for i in range(NPTS):
         o = orc[i]["cls_out"]
         for X in (0, 2, 4):
@@ -240,7 +239,7 @@ def test_async_upload_matches(setup):
         h2.powers_resident(b["initpower"][a:e], b["alens"][a:e], first=a)
     h2.set_option("async_upload", 0)
     h2.sync()
-    setup["h"].set_option("proj_kernel", 3)
+    setup["h"].set_option("proj_kernel", 4)
     setup["h"].powers(b["initpower"], b["alens"])  # blocking path, same (default) kernels
     for i in range(NPTS):
         got = h2.debug_fetch(2, i)
