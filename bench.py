@@ -323,16 +323,28 @@ def main():
     n_launch_k1 = args.steps * (-(-P // min(args.chunk, P)))
     k1_ms = tm["ms_project"] / n_launch_k1
     pts_per_launch = P / (-(-P // min(args.chunk, P)))
-    bytes_pt = float(np.mean(W["n_tau"].astype(np.float64) * 3 * W["n_k"] * 8 * 2)) + (NQ_MAX // 8) * 6 * 96 * 8 * 0.95
+    # algorithmic HBM bytes per point: Src + ddSrc read once, one partial-sum block [6][96] written per 24 wavenumbers
+    bytes_pt = float(np.mean(W["n_tau"].astype(np.float64) * 3 * W["n_k"] * 8 * 2)) + (2910 / 24.0) * 6 * 96 * 8
     trip_pt = triples / P
-    flop_per_triple = 14  # 8 FP64 ops for the cubic j_l interpolation (5 of them FMA) + 3 FMA accumulations
-    roof = {"kernel": "project_kernel (K1+K2 fused: line-of-sight projection + partial k-contraction)",
+    flop_per_triple = 13  # cubic j_l interpolation: 1 mul + 3 FMA; 3 FMA accumulations (T, E, lensing potential)
+    # ncu --set full capture of this kernel (profiles/r01_project_v4_ncu_full.txt, 64 points): DRAM read + write and
+    # shared-memory wavefronts per point; the kernel's own bound is the shared-memory pipe (1 wavefront / clock / SM)
+    NCU_DRAM_BYTES_PER_POINT = (355.31e6 + 36.54e6) / 64
+    NCU_SMEM_WAVEFRONTS_PER_POINT = 1496548128 / 64
+    sm_clock_hz = 1e6 * float(clocks.get("sm_mhz") or 1965.0)
+    roof = {"kernel": "project4_kernel (K1+K2 fused: line-of-sight projection + partial k-contraction)",
             "bound": "hbm", "achieved": bytes_pt * pts_per_launch / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak,
-            "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+            "unit": "GB/s", "peak_source": peak_src, "traffic": NCU_DRAM_BYTES_PER_POINT * pts_per_launch,
+            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of a 64-point launch, scaled per point",
+            "smem_lsu": {"achieved": NCU_SMEM_WAVEFRONTS_PER_POINT * pts_per_launch / (k1_ms * 1e-3) / 1e9,
+                         "peak": 148 * sm_clock_hz / 1e9, "unit": "Gwavefronts/s",
+                         "wavefronts_per_point": NCU_SMEM_WAVEFRONTS_PER_POINT,
+                         "note": "l1tex__data_pipe_lsu_wavefronts_mem_shared per point (ncu) / launch time, against one "
+                                 "128-byte wavefront per clock per SM"},
             "algorithmic_bytes_per_point": bytes_pt, "points_per_launch": pts_per_launch, "ms_per_launch": k1_ms,
             "share_of_step": tm["ms_project"] / tm["ms_total"],
-            "note": "the kernel is NOT HBM-bound (SURVEY 8d): its bound is the L2/L1 gather of the Bessel table and "
-                    "the FP64 pipe; see fp64 and table_gather",
+            "note": "the kernel is NOT HBM-bound (SURVEY 8d): DRAM traffic equals the algorithmic bytes; its bounds are the "
+                    "shared-memory pipe (table gather out of the ring) and FP64 issue; see smem_lsu, fp64, table_gather",
             "fp64": {"achieved": trip_pt * flop_per_triple * pts_per_launch / (k1_ms * 1e-3) / 1e12,
                      "peak": dfma_peak, "peak_dmma": dmma_peak, "unit": "TFLOP/s", "peak_source": "measured live "
                      "(cb200_measure_fp64_peaks: DFMA / DMMA micro-kernels)", "flop_per_triple": flop_per_triple,
@@ -340,6 +352,7 @@ def main():
             "table_gather": {"achieved": trip_pt * 32 * pts_per_launch / (k1_ms * 1e-3) / 1e9, "unit": "GB/s",
                              "bytes_per_triple": 32}}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["smem_lsu"]["frac"] = roof["smem_lsu"]["achieved"] / roof["smem_lsu"]["peak"]
     roof["fp64"]["frac"] = roof["fp64"]["achieved"] / max(dfma_peak, 1e-9)
 
     cpu = None

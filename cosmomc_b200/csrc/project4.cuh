@@ -98,6 +98,10 @@ struct Proj4Params {
 #ifndef CB200_W4_UNSAFE_NORINGWAIT
 #define CB200_W4_UNSAFE_NORINGWAIT 0  // timing experiment only: WRONG results
 #endif
+#ifndef CB200_W4_UNROLL
+#define CB200_W4_UNROLL 1
+#endif
+constexpr int W4_UNROLL = CB200_W4_UNROLL;
 #ifndef CB200_W4_CHAIN
 #define CB200_W4_CHAIN 0
 #endif
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     const double2* m_s01 = reinterpret_cast<const double2*>(mb + NPAIR * 16);
     const Proj4Rec* m_rec = reinterpret_cast<const Proj4Rec*>(mb + NPAIR * 32);
     // quarter-warp r works on pair (q_r, n); every lane covers LK multipoles
-#pragma unroll 1
+#pragma unroll W4_UNROLL
     for (int nn = 0; nn < S; nn++) {
       const int n = n_base + nn;
       const int pr = nn * QC + myqi;
