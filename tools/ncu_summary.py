@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep: key raw metrics + top stall reasons + hottest source lines. Usage: tools_ncu_summary.py rep [out.txt]"""
+"""Summarise an .ncu-rep: key raw metrics + top stall reasons + hottest source lines. Usage: tools/ncu_summary.py rep [out.txt]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
