@@ -279,3 +279,37 @@ def test_eval_batch_matches_get_loglike(setup):
     assert st.tolist() == wst.tolist() == [0, 1, 0]
     assert np.allclose(likes, want_likes, rtol=1e-12) and np.allclose(pr, wprior, rtol=1e-13)
     assert ll[1] == 1e30 and np.allclose(ll, want, rtol=1e-12)
+
+
+def test_kernel4_twelve_octets_and_error_paths():
+    """lmax_computed_cl = 2700 -> Max_l 2850 -> 92 sampled multipoles: the 12-octet instantiation of the default
+    projection kernel, against the chunked kernel 3 (itself checked against the oracle above) on the same inputs.
+    Also the soft/hard error conventions of the C ABI: usage errors come back as rc < 0 with a message, never abort."""
+    from cosmomc_b200 import lib, synthetic as syn
+    T = H.load_templates()
+    h = lib.Handle(max_points=2, chunk_points=2, lmax_computed_cl=2700, lmax_out=2700, n_q_max=4096)
+    assert h.info.n_lsamp > 88 and h.info.n_lsamp <= 96
+    h.set_templates(T["highl_unlensed"], T["highl_lensed"])
+    th = syn.draw_thermo(2, 21)
+    ip, al, cal, pert = syn.draw_params(2, 21)
+    tau, dtau, n_tau, k, n_k = syn.build_grids(h, th)
+    src = syn.make_sources(th, tau, k, pert).numpy()
+    h.upload_sources(th, n_k, k, src)
+    out = {}
+    for pk in (3, 4):
+        h.set_option("proj_kernel", pk)
+        out[pk] = h.powers(ip, al)[0]
+    for X in (0, 2, 3, 4):
+        nz = out[3][:, X] != 0
+        assert np.abs(out[4][:, X][nz] / out[3][:, X][nz] - 1).max() < 1e-9, X
+    # ---- error conventions
+    with pytest.raises(lib.CB200Error, match="max_points"):
+        h.upload_sources(np.tile(th, (2, 1)), np.tile(n_k, 2), np.tile(k, (2, 1)), None)      # 4 points > max_points
+    bad_nk = n_k.copy(); bad_nk[0] = 2
+    with pytest.raises(lib.CB200Error, match="n_k"):
+        h.upload_sources(th, bad_nk, k, src)
+    h3 = lib.Handle(max_points=2, lmax_out=H.LMAX_OUT)
+    with pytest.raises(lib.CB200Error, match="templates"):
+        h3.powers(ip, al)
+    with pytest.raises(lib.CB200Error, match="no likelihood|likelihood"):
+        h.eval_batch(np.zeros((2, 3)), [0, 0, 0], [1, 1, 1], dict(logA=0))
