@@ -65,6 +65,23 @@
     real(c_double), intent(out) :: cls_out(*), derived_out(*)
     integer(c_int), intent(out) :: status(*)
     end function
+    integer(c_int) function cb200_set_option(h, name, value) bind(C, name='cb200_set_option')
+    !"async_upload" = 1: uploads overlap the evaluation of the previous block (INTEGRATION.md section 7)
+    import :: c_ptr, c_int, c_double, c_char
+    type(c_ptr), value :: h
+    character(kind=c_char), intent(in) :: name(*)
+    real(c_double), value :: value
+    end function
+    integer(c_int) function cb200_eval_batch(h, layout, first, npts, params, loglike, likelihoods, prior, status) &
+        bind(C, name='cb200_eval_batch')
+    !TLikeCalculator%GetLogLike (source/calclike.f90:97-151) for npts points at once; layout = cb200_param_layout
+    import :: c_ptr, c_int, c_double
+    type(c_ptr), value :: h, layout
+    integer(c_int), value :: first, npts
+    real(c_double), intent(in) :: params(*)
+    real(c_double), intent(out) :: loglike(*), likelihoods(*), prior(*)
+    integer(c_int), intent(out) :: status(*)
+    end function
     end interface
 
     Type, extends(CAMB_Calculator) :: B200_Calculator
