@@ -57,6 +57,11 @@ constexpr int w4_pnn() {  // largest divisor of S that the producer threads cove
 constexpr int W4_PNN = w4_pnn();               // time samples covered by one sweep of the metadata threads
 constexpr int W4_PPT = W4_S / W4_PNN;          // (q, tau) pairs per producer thread: same q, samples W4_PNN apart
 static_assert(W4_PNN >= 1 && W4_S % W4_PNN == 0, "slab shape");
+#ifndef CB200_W4_MS
+#define CB200_W4_MS 1
+#endif
+constexpr int W4_MS = CB200_W4_MS;  // slabs per metadata iteration: their independent chains overlap in one thread
+static_assert(W4_MS == 1 || W4_PPT == 1, "several slabs per metadata iteration need one pair per thread and slab");
 #ifndef CB200_W4_CREG
 #define CB200_W4_CREG 144
 #endif
@@ -389,13 +394,13 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     const int pw2 = pc.valid ? min(s_q2[m_qi], pc.steps) : 0;
     const double* Sp0 = src + (pc.klo - 1);
     const double* Dp0 = dds + (pc.klo - 1);
-    constexpr int PPT = W4_PPT, PNN = W4_PNN;
-    double f_tau[PPT], f_dtau[PPT], f_s[PPT][3][4];
-    bool f_valid[PPT];
+    constexpr int PPT = W4_PPT, PNN = W4_PNN, MS = W4_MS, NU = PPT * MS;
+    double f_tau[NU], f_dtau[NU], f_s[NU][3][4];
+    bool f_valid[NU];
     auto prefetch = [&](int nb) {
 #pragma unroll
-      for (int u = 0; u < PPT; u++) {
-        const int n = nb + m_nn + u * PNN;
+      for (int u = 0; u < NU; u++) {
+        const int n = nb + (u / PPT) * S + m_nn + (u % PPT) * PNN;   // slab u / PPT of the iteration
         f_valid[u] = (n >= pw1) && (n <= pw2);
         if (f_valid[u]) {
           f_tau[u] = __ldg(tau + n - 1);
@@ -415,8 +420,8 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     // rows [a, b] of the table -> ring by TMA bulk copies (one per row; slot 0 is mirrored behind slot R-1);
     // their bytes are accounted on the slab's `full` barrier, so nobody waits for them but the consumers
     auto fetch_rows = [&](int a, int b, unsigned long long* bar) {
-      for (int row = a + lane; row <= b; row += 32) {
-        const int slot = row % R;
+      int slot = (a + lane) % R;
+      for (int row = a + lane; row <= b; row += 32, slot = (slot + 32) % R) {
         const double2* g = p.bes + (size_t)row * PROJ_LP;
         mbar_expect_tx(bar, slot == 0 ? 2 * rb : rb);
         bulk_g2s(ring + (size_t)slot * rb, g, rb, bar);
@@ -426,25 +431,23 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     };
     int rlo = 0x7fffffff;      // lowest resident row (identical in every producer thread by construction)
     int released = -1;         // slabs <= released have been released by every consumer warp
-    int jlo[PPT], jhi[PPT];    // active multipole slots of this thread's pairs (both only ever move down)
+    int jlo[NU], jhi[NU];      // active multipole slots of this thread's pairs (both only ever move down)
 #pragma unroll
-    for (int u = 0; u < PPT; u++) { jlo[u] = NJ; jhi[u] = NJ - 1; }
+    for (int u = 0; u < NU; u++) { jlo[u] = NJ; jhi[u] = NJ - 1; }
     const unsigned* wrow = s_wtab + m_qi * NJP;
-    if (!ring_warp && m_grp < nslab) prefetch(n_lo + m_grp * S);
-    CK4(ck_a);
-    for (int t = ring_warp ? 0 : m_grp; t < nslab; t += ring_warp ? 1 : W4_MG) {
-      const int par = t % W4_NST;
-      // metadata buffer `par` is free once the consumers have released slab t - NST (slabs are released in order)
-      if (t >= W4_NST) {
-        mbar_wait(s_bar + W4_NST + par, ((t - W4_NST) / W4_NST) & 1);
-        released = max(released, t - W4_NST);
-      }
-      CK4(ck_c);
-      if (ring_warp) {
+    if (ring_warp) {
+      for (int t = 0; t < nslab; t++) {
+        const int par = t % W4_NST;
+        // the barrier phase of slab t - NST must be over before anything is signalled on it again
+        if (t >= W4_NST) {
+          mbar_wait(s_bar + W4_NST + par, ((t - W4_NST) / W4_NST) & 1);
+          released = max(released, t - W4_NST);
+        }
+        CK4(ck_c);
         const int2 w = s_win[t];
         // The windows slide towards lower rows (x falls with tau).  Rows [w.x, ...] may overwrite ring slots only
         // if the highest row still needed by the oldest slab not yet released stays within R rows of w.x.
-        while (!CB200_W4_UNSAFE_NORINGWAIT && released + 1 < t && s_win[released + 1].y - w.x + 1 > R) {
+        while (released + 1 < t && s_win[released + 1].y - w.x + 1 > R) {
           const int r = released + 1;
           mbar_wait(s_bar + W4_NST + (r % W4_NST), (r / W4_NST) & 1);
           released = r;
@@ -456,15 +459,26 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         rlo = min(rlo, w.x);
         if (COUNT && p.ring_stats && lane == 0) st_slabs++;
         CK4(ck_b);
-        if (COUNT && lane == 0) s_bar[24 + par] = (unsigned long long)clock64();
         mbar_arrive(s_bar + par);
-        continue;
       }
+    }
+    if (!ring_warp && m_grp * MS < nslab) prefetch(n_lo + m_grp * MS * S);
+    CK4(ck_a);
+    for (int t = m_grp * MS; !ring_warp && t < nslab; t += W4_MG * MS) {
+      // metadata buffers are free once the consumers have released the slabs that used them NST slabs ago
+#pragma unroll
+      for (int us = 0; us < MS; us++) {
+        const int tu = t + us;
+        if (tu < nslab && tu >= W4_NST) mbar_wait(s_bar + W4_NST + (tu % W4_NST), ((tu - W4_NST) / W4_NST) & 1);
+      }
+      CK4(ck_c);
       // ---- metadata of this thread's pairs ----
 #pragma unroll
-      for (int u = 0; u < PPT; u++) {
-        const int n = n_lo + t * S + m_nn + u * PNN;
-        const int pidx = m_pair + u * QC * PNN;
+      for (int u = 0; u < NU; u++) {
+        const int tu = t + u / PPT;
+        const int n = n_lo + tu * S + m_nn + (u % PPT) * PNN;
+        const int pidx = m_pair + (u % PPT) * QC * PNN;
+        const int par = tu % W4_NST;
         unsigned char* mb = meta_base + (size_t)par * NPAIR * 48;
         double2* m_af = reinterpret_cast<double2*>(mb);
         double2* m_s01 = reinterpret_cast<double2*>(mb + NPAIR * 16);
@@ -491,17 +505,18 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
           moff = ((bi - 1) % R) * rb;
           if (jlo[u] <= jhi[u]) jr = jlo[u] | ((jhi[u] + 1) << 8);
         }
-        if (m_live) {
+        if (m_live && tu < nslab) {
           m_af[pidx] = make_double2(ma, mfac);
           m_s01[pidx] = make_double2(ms0, ms1);
           Proj4Rec rec; rec.s2 = ms2; rec.off = moff; rec.jr = jr;
           m_rec[pidx] = rec;
         }
       }
-      if (t + W4_MG < nslab) prefetch(n_lo + (t + W4_MG) * S);
+      if (t + W4_MG * MS < nslab) prefetch(n_lo + (t + W4_MG * MS) * S);
       CK4(ck_a);
-      if (COUNT) atomicMax(s_bar + 16 + par, (unsigned long long)clock64());
-      mbar_arrive(s_bar + par);
+#pragma unroll
+      for (int us = 0; us < MS; us++)
+        if (t + us < nslab) mbar_arrive(s_bar + ((t + us) % W4_NST));
       CK4(ck_c);
     }
     if (COUNT && p.ring_stats) {
