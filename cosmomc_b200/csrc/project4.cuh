@@ -8,15 +8,21 @@
 //     pair per step, but each lane now carries LK = ceil(n_l / 8) multipoles (l-slots li + 8k), so the 48 B of
 //     per-pair metadata are read once per 88 multipoles instead of once per 32, the pair metadata is computed
 //     once (not once per multipole chunk) and the ring is filled once per wavenumber block;
-//   * warp specialisation: 8 CONSUMER warps do nothing but the accumulation (shared-memory loads + FP64 FMAs);
-//     4 PRODUCER warps compute the (q, tau)-pair metadata of the next slab (table row, spline weights,
-//     k-interpolated d-tau-weighted sources; global loads software-pipelined one more slab ahead) and cp.async
-//     the table rows that slab needs into the ring.  The two sides meet only on two pairs of mbarriers
-//     (full / empty per metadata buffer); there is no CTA-wide barrier inside the time loop;
+//   * warp specialisation: 12 CONSUMER warps (6 wavenumber groups x 2 multipole halves = even / odd octets) do nothing
+//     but the accumulation (shared-memory loads + FP64 FMAs).  4 PRODUCER warps: warp 0 keeps the ring filled with
+//     TMA bulk copies (cp.async.bulk, one per table row, byte count on the slab's `full` mbarrier); warps 1-3 compute
+//     the (q, tau)-pair metadata of the coming slabs (table row, spline weights, k-interpolated d-tau-weighted
+//     sources; global loads software-pipelined one more slab ahead).  The two producer roles run in separate loops
+//     and meet only the consumers (full / empty mbarriers per metadata buffer): the metadata runs up to NST slabs
+//     ahead even while the ring warp waits for room, and there is no CTA-wide barrier inside the time loop.
+//     setmaxnreg moves registers from the producer warps to the consumers;
 //   * the ring holds whole table rows [row][n_l] (16 B nodes {j_l, j_l''}); the rows of a slab are known
-//     analytically (x = q (tau0 - tau) is monotone in q and tau) and are tabulated once per CTA, so the producer
-//     fills slab s+1 while slab s is consumed whenever both windows fit (else it waits for slab s to drain);
-//   * multipole octets with no active lane anywhere in the warp are skipped (no loads, no FP64 issue).
+//     analytically (x = q (tau0 - tau) is monotone in q and tau) and are tabulated once per CTA; a slab's rows are
+//     fetched as soon as the highest row still needed by the oldest unreleased slab leaves room for them;
+//   * the active multipoles of a pair are one run of l-slots, tracked by the producer and shipped with the metadata;
+//     octet batches with no active lane anywhere in the warp are skipped (no loads, no FP64 issue);
+//   * wavenumber blocks whose table window exceeds the ring are flagged and left to project3_kernel (host launches
+//     it right after, on the flagged blocks only).
 #pragma once
 #include "common.cuh"
 #include "project.cuh"

@@ -1,7 +1,7 @@
 """Dev utility: compare the windowed projection kernel against the L2-gather kernel on one point."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import helpers as H
 from cosmomc_b200 import lib, synthetic as syn
