@@ -313,3 +313,32 @@ def test_kernel4_twelve_octets_and_error_paths():
         h3.powers(ip, al)
     with pytest.raises(lib.CB200Error, match="no likelihood|likelihood"):
         h.eval_batch(np.zeros((2, 3)), [0, 0, 0], [1, 1, 1], dict(logA=0))
+
+
+def test_size_independent_properties():
+    """Properties that hold at any batch size (checked here at 96 points, 3 chunks of 32): the sampled unlensed C_l are
+    linear in A_s; a point's result does not depend on its position in the batch or on its neighbours (bitwise:
+    fixed-order reductions, no atomics on the data path); repeating the call reproduces every bit."""
+    from cosmomc_b200 import lib, synthetic as syn
+    T = H.load_templates()
+    n = 96
+    h = lib.Handle(max_points=n, chunk_points=32, lmax_out=H.LMAX_OUT, n_tau_max=576, n_k_max=224)
+    h.set_templates(T["highl_unlensed"], T["highl_lensed"])
+    th = syn.draw_thermo(4, 31)
+    ip, al, cal, pert = syn.draw_params(4, 31)
+    tau, dtau, n_tau, k, n_k = syn.build_grids(h, th)
+    src = syn.make_sources(th, tau, k, pert).numpy()
+    idx = np.arange(n) % 4                      # 4 distinct points repeated through the batch
+    h.upload_sources(th[idx], n_k[idx], k[idx], src[idx])
+    ip_b = ip[idx].copy()
+    ip_b[n // 2:, 0] *= 2.0                     # second half of the batch: twice the scalar amplitude
+    cls1 = h.powers(ip_b, al[idx])[0]
+    icl = np.stack([h.debug_fetch(0, i) for i in range(n)])
+    cls2 = h.powers(ip_b, al[idx])[0]
+    assert np.array_equal(cls1, cls2)                                   # run-to-run determinism
+    for i in range(4, n // 2):
+        assert np.array_equal(cls1[i], cls1[i % 4]), i                  # position / neighbours do not matter
+    for i in range(n // 2, n):
+        a, b = icl[i], icl[i % 4]
+        nz = b != 0
+        assert np.abs(a[nz] / b[nz] - 2.0).max() < 1e-13, i             # linearity in A_s
