@@ -174,3 +174,30 @@ def read_chain(path):
     """Inverse of the row writer: returns (weights, loglikes, params[rows][n])."""
     a = np.atleast_2d(np.loadtxt(path))
     return a[:, 0], a[:, 1], a[:, 2:]
+
+
+def write_likelihoods(path, likelihoods):
+    """`<root>.likelihoods` (TLikelihoodList%OutputDescription, source/GeneralTypes.f90:796-817): one TAB-joined line
+    `1 <LikelihoodType> <tag> <name> <version>` per likelihood, in the original (registration) order.
+    likelihoods: iterable of dicts / tuples (type, tag, name, version)."""
+    with open(path, "w") as f:
+        for L in likelihoods:
+            if isinstance(L, dict):
+                L = (L.get("type", ""), L.get("tag", ""), L.get("name", ""), L.get("version", ""))
+            f.write("\t".join(["1"] + [str(x).strip() for x in L]) + "\n")
+
+
+def likelihood_derived_params(likelihoods, loglike, type_indices=(), derived=None):
+    """addLikelihoodDerivedParams (source/GeneralTypes.f90:751-795) for a batch: appends to `derived` [npts][nd]
+    chi2 of every likelihood (2 x -lnL, original order), chi2_prior = 2 (logLike - sum of the likelihoods), and the
+    total chi2 of every likelihood type (type_indices: list of index lists).  logLike is the un-tempered total -lnL
+    including priors (what cb200_eval_batch returns at temperature 1)."""
+    likes = np.atleast_2d(np.asarray(likelihoods, dtype=np.float64))
+    ll = np.asarray(loglike, dtype=np.float64).reshape(-1)
+    cols = [likes * 2, (2 * (ll - likes.sum(axis=1)))[:, None]]
+    for idx in type_indices:
+        cols.append((2 * likes[:, list(idx)].sum(axis=1))[:, None])
+    out = np.concatenate(cols, axis=1)
+    if derived is not None:
+        out = np.concatenate([np.atleast_2d(np.asarray(derived, dtype=np.float64)), out], axis=1)
+    return out

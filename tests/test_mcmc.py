@@ -121,3 +121,77 @@ def test_gpu_test_likelihood_and_driver():
                                converge_test=0.02)
     assert m.run(max_steps=6000, min_steps=900)
     assert np.abs(m.cov - C).max() < 0.12 * np.abs(C).max()
+
+
+@pytest.mark.gpu
+def test_gpu_chains_on_the_theory_plus_likelihood_path():
+    """BASELINE configs[4] in miniature: 64 chains in lockstep over (logA, n_s, calPlanck) at fixed cosmology - every
+    step is ONE batched call of the hot path (shared transfer functions -> k-contraction GEMM -> lensing ->
+    plik-lite-shaped chi^2) plus the Gaussian calibration prior; the proposal covariance is learned from the pooled
+    chain statistics.  The posterior is close to Gaussian, so the learned covariance must approach the Fisher estimate
+    obtained by finite differences of the same -lnL."""
+    from cosmomc_b200 import lib, mcmc, synthetic as syn
+    T = H.load_templates()
+    K = 64
+    h = lib.Handle(max_points=K + 8, chunk_points=K + 8, lmax_out=H.LMAX_OUT)
+    h.set_templates(T["highl_unlensed"], T["highl_lensed"])
+    b = H.small_batch(1, seed=5, NT=h.info.n_tau_max, NK=h.info.n_k_max)
+    h.upload_sources(b["thermo"], b["n_k"], b["k"], b["src"])
+    ip0 = b["initpower"][0].copy()
+    c0 = np.array([np.log(1e10 * ip0[0]), ip0[1], 1.0])
+
+    def theory(P):
+        ip = np.tile(ip0, (len(P), 1))
+        ip[:, 0] = 1e-10 * np.exp(P[:, 0])
+        ip[:, 1] = P[:, 1]
+        return ip
+
+    # data = the model's own band powers at the centre (no noise): the posterior peaks at c0
+    cls0 = h.powers_shared(theory(c0[None, :]), np.ones(1), src_point=0, first=1)[0][0]
+    fid = np.zeros((5, H.LMAX_OUT + 1))
+    fid[:3] = cls0[:3]
+    d = syn.synthetic_pliklite(H.LMAX_OUT, fiducial_cls=fid, seed=99)
+    x_data = d["x_model"] if "x_model" in d else d["x_data"]
+    h.add_pliklite(d["nb"], d["blmin"], d["blmax"], d["weights"], d["invcov"], x_data, 0)
+
+    def nll(P):
+        P = np.atleast_2d(P)
+        h.powers_shared(theory(P), np.ones(len(P)), src_point=0, first=1, want_cls=False)
+        ll, tot, st = h.loglike_batch(len(P), P[:, 2:3].copy(), first=1)
+        out = tot + 0.5 * ((P[:, 2] - 1.0) / 0.0025) ** 2          # Gaussian prior on calPlanck (planck_calibration.ini)
+        out[st != 0] = 1e30
+        return out
+
+    # Fisher matrix by central differences of -lnL around the best fit of this (noisy) data realisation
+    steps = np.array([2e-3, 1e-3, 5e-4])
+    f0 = nll(c0)[0]
+    Hm = np.zeros((3, 3))
+    for i in range(3):
+        for j in range(i, 3):
+            ei, ej = np.eye(3)[i] * steps[i], np.eye(3)[j] * steps[j]
+            v = nll(np.stack([c0 + ei + ej, c0 + ei - ej, c0 - ei + ej, c0 - ei - ej]))
+            Hm[i, j] = Hm[j, i] = (v[0] - v[1] - v[2] + v[3]) / (4 * steps[i] * steps[j])
+    C_fisher = np.linalg.inv(Hm)
+    assert np.all(np.linalg.eigvalsh(Hm) > 0) and np.isfinite(f0)
+    rng = np.random.default_rng(1)
+    start = c0 + rng.normal(size=(K, 3)) * np.sqrt(np.diag(C_fisher))
+    m = mcmc.BatchedMetropolis(nll, start, np.diag(np.diag(C_fisher)), seed=4, update_every=100, converge_test=0.05)
+    m.run(max_steps=600, min_steps=300)
+    acc = m.n_accept.sum() / (m.K * m.n_steps)
+    assert 0.08 < acc < 0.7, acc
+    assert m.R_history and m.R_history[-1] < 0.2, m.R_history
+    sd_f, sd_c = np.sqrt(np.diag(C_fisher)), np.sqrt(np.diag(m.cov))
+    assert np.all(np.abs(sd_c / sd_f - 1) < 0.35), (sd_c, sd_f)
+
+
+def test_likelihood_derived_columns_and_description(tmp_path):
+    from cosmomc_b200 import mcmc
+    likes = np.array([[3.0, 4.0, 5.0], [1.0, 2.0, 3.0]])
+    ll = np.array([12.5, 6.25])                       # includes 0.5 / 0.25 of prior
+    d = mcmc.likelihood_derived_params(likes, ll, type_indices=[[0, 1], [2]], derived=[[7.0], [8.0]])
+    assert d.shape == (2, 1 + 3 + 1 + 2)
+    assert d[0].tolist() == [7.0, 6.0, 8.0, 10.0, 1.0, 14.0, 10.0]
+    assert d[1].tolist() == [8.0, 2.0, 4.0, 6.0, 0.5, 6.0, 6.0]
+    p = str(tmp_path / "c.likelihoods")
+    mcmc.write_likelihoods(p, [("CMB", "lensing", "smicadx12_Dec5", "v1"), dict(type="BAO", tag="DR12", name="DR12", version="")])
+    assert open(p).read() == "1\tCMB\tlensing\tsmicadx12_Dec5\tv1\n1\tBAO\tDR12\tDR12\t\n"
