@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--points", type=int, default=int(os.environ.get("CB200_BENCH_POINTS", 16384)),
                     help="parameter points per GPU per step")
     ap.add_argument("--chunk", type=int, default=1024)
-    ap.add_argument("--stage-points", type=int, default=2048, help="points in the pinned host staging buffer (e2e)")
+    ap.add_argument("--stage-points", type=int, default=512, help="points in the pinned host staging buffer (e2e)")
     ap.add_argument("--cpu-sample", type=int, default=192, help="points of the same workload timed on the CPU oracle")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
