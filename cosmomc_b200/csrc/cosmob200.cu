@@ -123,6 +123,7 @@ struct cb200_handle {
   DevBuf<unsigned long long> d_triples;
   bool count_triples = false, ring_stats = false;
   int proj_kernel = 4;
+  int sn_preassemble = 1;  // V(alpha, beta) assembled by its own coalesced kernel ahead of the Cholesky
   int spline_kernel = 2;  // 1: one thread per row straight from global memory, 2: tiled through shared memory
   DevBuf<unsigned long long> d_ring_stats;
   DevBuf<unsigned char> w_fallback;  // [chunk][NQB] blocks left to the chunked kernel by project4_kernel
@@ -1493,8 +1494,16 @@ static int loglike_device(cb200_handle* h, int bg_first, int npts, const double*
                                              h->w_nuis.p + (size_t)a * n_nuis, n_nuis, L.sn_ia, L.sn_ib,
                                              h->w_snW.p + (size_t)n * ld, pst, ld, 1);
             CB_LAUNCH_CHECK();
+            const bool pre = h->sn_preassemble != 0;
+            if (pre) {
+              dim3 ga((n + 7) / 8, m);
+              sn_assemble_kernel<<<ga, 256, 0, s>>>(L.sn, m, h->w_nuis.p + (size_t)a * n_nuis, n_nuis, L.sn_ia, L.sn_ib,
+                                                    h->w_snW.p, pst, ld);
+              CB_LAUNCH_CHECK();
+              h->n_launches += 1;
+            }
             CholParams cp;
-            cp.n = n; cp.nr = nr; cp.ld = ld; cp.np = m; cp.assemble = 1; cp.S = L.sn;
+            cp.n = n; cp.nr = nr; cp.ld = ld; cp.np = m; cp.assemble = pre ? 0 : 1; cp.S = L.sn;
             cp.nuis = h->w_nuis.p + (size_t)a * n_nuis; cp.n_nuis = n_nuis; cp.ia = L.sn_ia; cp.ib = L.sn_ib;
             cp.W = h->w_snW.p; cp.pt_stride = pst; cp.status = h->w_snbad.p;
             sn_chol_kernel<<<m, 256, CH_SMEM, s>>>(cp);
@@ -1770,6 +1779,7 @@ int cb200_set_option(cb200_handle* h, const char* name, double value) {
   else if (n == "keep_transfers") h->keep_transfers = value != 0;
   else if (n == "ring_stats") h->ring_stats = value != 0;
   else if (n == "async_upload") h->async_upload = value != 0;
+  else if (n == "sn_preassemble") h->sn_preassemble = value != 0;
   else if (n == "spline_kernel") h->spline_kernel = (value == 1) ? 1 : 2;
   else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 4) ? (int)value : 4;
   else return fail(h, "set_option: unknown option " + n);

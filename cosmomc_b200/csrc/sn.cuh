@@ -71,6 +71,31 @@ __global__ void __launch_bounds__(256) sn_prep_kernel(SnData S, int np, const do
   }
 }
 
+// ---- V(alpha, beta) of every point, lower triangle, coalesced (supernovae_JLA.f90:1074-1096) -----------------------
+// One warp per matrix row, lanes over the columns: the six constant blocks (26 MB, L2-resident across the batch) are
+// read 256 B at a time and the row goes to W[pt][row][0..row].  Doing this ahead of the factorisation takes the six
+// dependent, poorly coalesced loads per element out of the Cholesky's latency chain (ncu: 15 % of its samples).
+__global__ void __launch_bounds__(256) sn_assemble_kernel(SnData S, int np, const double* __restrict__ nuis, int n_nuis,
+                                                          int ia, int ib, double* __restrict__ W, size_t pt_stride, int ld) {
+  const int pt = blockIdx.y, row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int n = S.nsn;
+  if (pt >= np || row >= n) return;
+  const double alpha = ia >= 0 ? nuis[(size_t)pt * n_nuis + ia] : 0.0;
+  const double beta = ib >= 0 ? nuis[(size_t)pt * n_nuis + ib] : 0.0;
+  const double cf[6] = {1.0, alpha * alpha, beta * beta, 2.0 * alpha, -2.0 * beta, -2.0 * alpha * beta};
+  double* out = W + (size_t)pt * pt_stride + (size_t)row * ld;
+  const int cmax = min(n - 1, row | 31);  // through the end of the row's diagonal block (the factorisation loads whole blocks)
+  for (int col = lane; col <= cmax; col += 32) {
+    const size_t o = (size_t)row * n + col;
+    double av = 0.0;
+#pragma unroll
+    for (int m = 0; m < 6; m++)
+      if (S.cov[m]) av += cf[m] * S.cov[m][o];
+    if (row == col) av += sn_diag(S, row, alpha, beta);
+    out[col] = av;
+  }
+}
+
 // ---- blocked Cholesky with ride-along right-hand sides ----------------------------------------------------
 // W[pt]: (n + nr) rows x ld, row-major.  Rows 0..n-1: lower triangle of V (assembled on the fly when S != null,
 // else read from W), rows n..n+nr-1: right-hand sides.  On exit rows 0..n-1 hold L (lower), rows n.. hold (L^-1 rhs)^T.
@@ -115,26 +140,45 @@ __global__ void __launch_bounds__(256, 2) sn_chol_kernel(CholParams p) {
       for (int i = 0; i < 2; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-      for (int k0 = 0; k0 < c0; k0 += CH_KC) {
-        __syncthreads();
-        // stage L[r0 .. r0+128)[k0 .. k0+32) and L[c0 .. c0+32)[k0 .. k0+32)
-        for (int e = tid; e < CH_ROWS * (CH_KC / 2); e += 256) {
+      // The two L panels of chunk k0 + KC are loaded into registers while chunk k0 is multiplied (the global-load
+      // latency used to sit exposed between the two barriers of every chunk: ncu long-scoreboard 12.8).
+      constexpr int NA = CH_ROWS * (CH_KC / 2) / 256, NB2 = CH_NB * (CH_KC / 2) / 256;
+      double2 pa[NA], pb[NB2];
+      auto fetch = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < NA; i++) {
+          const int e = tid + i * 256;
           const int rr = e / (CH_KC / 2), kk = (e % (CH_KC / 2)) * 2;
           const int row = r0 + rr;
-          double2 v = make_double2(0.0, 0.0);
-          if (row < nrows) v = *reinterpret_cast<const double2*>(W + (size_t)row * ld + k0 + kk);
-          As[rr * CH_AS + kk] = v.x;
-          As[rr * CH_AS + kk + 1] = v.y;
+          pa[i] = (row < nrows) ? *reinterpret_cast<const double2*>(W + (size_t)row * ld + k0 + kk) : make_double2(0.0, 0.0);
         }
-        for (int e = tid; e < CH_NB * (CH_KC / 2); e += 256) {
+#pragma unroll
+        for (int i = 0; i < NB2; i++) {
+          const int e = tid + i * 256;
           const int rr = e / (CH_KC / 2), kk = (e % (CH_KC / 2)) * 2;
           const int row = c0 + rr;
-          double2 v = make_double2(0.0, 0.0);
-          if (row < n) v = *reinterpret_cast<const double2*>(W + (size_t)row * ld + k0 + kk);
-          Bs[rr * CH_AS + kk] = v.x;
-          Bs[rr * CH_AS + kk + 1] = v.y;
+          pb[i] = (row < n) ? *reinterpret_cast<const double2*>(W + (size_t)row * ld + k0 + kk) : make_double2(0.0, 0.0);
+        }
+      };
+      if (c0 > 0) fetch(0);
+      for (int k0 = 0; k0 < c0; k0 += CH_KC) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NA; i++) {
+          const int e = tid + i * 256;
+          const int rr = e / (CH_KC / 2), kk = (e % (CH_KC / 2)) * 2;
+          As[rr * CH_AS + kk] = pa[i].x;
+          As[rr * CH_AS + kk + 1] = pa[i].y;
+        }
+#pragma unroll
+        for (int i = 0; i < NB2; i++) {
+          const int e = tid + i * 256;
+          const int rr = e / (CH_KC / 2), kk = (e % (CH_KC / 2)) * 2;
+          Bs[rr * CH_AS + kk] = pb[i].x;
+          Bs[rr * CH_AS + kk + 1] = pb[i].y;
         }
         __syncthreads();
+        if (k0 + CH_KC < c0) fetch(k0 + CH_KC);
 #pragma unroll
         for (int kk = 0; kk < CH_KC / 4; kk++) {
           double a[2], b[4];
