@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(256, 2) sn_chol_kernel(CholParams p) {
           if (bad && lane == 0) s_bad = 1;
 #pragma unroll
           for (int j = 0; j < CH_NB; j++) Ls[lane * CH_CS + j] = (j <= lane) ? rowv[j] : 0.0;
+          Ls[lane * CH_CS + CH_NB] = 1.0 / rowv[lane];  // rowv[lane] = L_lane,lane (1 beyond wcols)
         }
         __syncthreads();
       }
@@ -253,13 +254,18 @@ __global__ void __launch_bounds__(256, 2) sn_chol_kernel(CholParams p) {
           if (row < c0 + wcols && r0 == c0) {
             for (int c = 0; c < wcols; c++) out[c] = Ls[tid * CH_CS + c];
           } else {
+            // forward substitution, right-looking: once x_k is known every later column is updated independently,
+            // so the dependent chain is 32 multiply-add steps instead of 32 divisions with growing dot products
+            // (1 / L_kk is taken once per column; values, not indices)
             double x[CH_NB];
 #pragma unroll
-            for (int c = 0; c < CH_NB; c++) {
-              double s = Cs[tid * CH_CS + c];
+            for (int c = 0; c < CH_NB; c++) x[c] = Cs[tid * CH_CS + c];
 #pragma unroll
-              for (int k = 0; k < c; k++) s -= x[k] * Ls[c * CH_CS + k];
-              x[c] = s / Ls[c * CH_CS + c];
+            for (int k = 0; k < CH_NB; k++) {
+              const double xk = x[k] * Ls[k * CH_CS + CH_NB];   // column CH_NB of Ls holds 1 / L_kk
+              x[k] = xk;
+#pragma unroll
+              for (int c = k + 1; c < CH_NB; c++) x[c] -= xk * Ls[c * CH_CS + k];
             }
 #pragma unroll
             for (int c = 0; c < CH_NB; c++)
