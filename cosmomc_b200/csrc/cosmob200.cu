@@ -721,7 +721,6 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       static_assert(W3_QC >= W4_QC, "the fallback pass uses the same wavenumber blocks");
       const int noct = (nl + 7) / 8;
       const int LK = noct <= 6 ? 6 : noct <= 11 ? 11 : 12;
-      pp.zero = 0;
       pp.rb = LK * 128;
       pp.R = std::min(w4_ring_rows(LK, S.NT), 4096);
       pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes = K.d_bes.p;

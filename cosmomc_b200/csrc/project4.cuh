@@ -87,7 +87,6 @@ struct __align__(16) Proj4Rec {  // third metadata word of a pair
 struct Proj4Params {
   PointView v;
   int p0, nl, num_xx, NQB, tensors;
-  int zero;                 // always 0: an operand the assembler cannot fold (see the batch chaining in the consumer)
   int R, rb;                // ring capacity in rows (+1 mirror row), row stride in bytes (= 128 * octets)
   double max_eta_k;
   const double* ddsrc;
@@ -113,9 +112,6 @@ struct Proj4Params {
 #define CB200_W4_UNROLL 1
 #endif
 constexpr int W4_UNROLL = CB200_W4_UNROLL;
-#ifndef CB200_W4_CHAIN
-#define CB200_W4_CHAIN 0
-#endif
 #ifndef CB200_W4_NST
 #define CB200_W4_NST 4
 #endif
@@ -167,14 +163,6 @@ __device__ __forceinline__ double2 lds128_if(unsigned saddr, bool pred) {
   asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %3, 0;\n @p ld.shared.v2.f64 {%0, %1}, [%2];\n}\n"
                : "=d"(r.x), "=d"(r.y)
                : "r"(saddr), "r"((unsigned)pred));
-  return r;
-}
-
-__device__ __forceinline__ double2 ldg128_if(unsigned long long gaddr, bool pred) {
-  double2 r;
-  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %3, 0;\n @p ld.global.nc.v2.f64 {%0, %1}, [%2];\n}\n"
-               : "=d"(r.x), "=d"(r.y)
-               : "l"(gaddr), "r"((unsigned)pred));
   return r;
 }
 
@@ -590,9 +578,8 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
       const double a2 = af.x, b2 = 1 - a2, t2 = -(b2 * af.y);
       const double g0 = t2 * (a2 + 1), g1 = t2 * (2 - a2);
       if (COUNT && p.triples) my_triples += __popc(m);
-      // octets in batches of KB: the loads of a batch are in flight together; the next batch's address is made to
-      // depend on this batch's values (a true PTX-level dependency: ptxas does the scheduling, an empty asm would
-      // vanish), so that at most 2 KB loads (8 KB registers) are live at a time
+      // octets in batches of KB: the loads of a batch are in flight together, and a batch with no active lane
+      // anywhere in the warp is skipped altogether (no loads, no FP64 issue)
       constexpr int KB = CB200_W4_KB;
       {
         unsigned rp = ring_lane + rec.off;
@@ -610,7 +597,6 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
               N1[kk] = lds128_if(rp + k * 256 + rb, act);
             }
           }
-          int jbits = 0;
 #pragma unroll
           for (int kk = 0; kk < KB; kk++) {
             const int k = k0 + kk;
@@ -621,15 +607,8 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
               acc[k][0] = fma(s01.x, Jv, acc[k][0]);
               acc[k][1] = fma(s01.y, Jv, acc[k][1]);
               acc[k][2] = fma(rec.s2, Jv, acc[k][2]);
-              jbits |= __double2hiint(Jv);
             }
           }
-#if CB200_W4_CHAIN
-          if (k0 + KB < LKH)
-            asm volatile("{\n .reg .b32 t;\n and.b32 t, %1, %2;\n add.u32 %0, %0, t;\n}\n" : "+r"(rp) : "r"(jbits), "r"(p.zero));
-#else
-          (void)jbits;
-#endif
         }
       }
     }
