@@ -342,3 +342,38 @@ def test_size_independent_properties():
         a, b = icl[i], icl[i % 4]
         nz = b != 0
         assert np.abs(a[nz] / b[nz] - 2.0).max() < 1e-13, i             # linearity in A_s
+
+
+@pytest.mark.parametrize("seed", [101, 202])
+def test_default_kernel_matches_chunked_kernel_on_many_points(seed):
+    """48 random points (tau0, thermo and initial-power draws of the bench workload): the default projection kernel
+    (ring fed by TMA, run-length masks, fallback pass for the first wavenumber block) against kernel 3 on every point
+    and spectrum, plus the integer triple count.  Guards the window / ring / mask logic over many grids."""
+    from cosmomc_b200 import lib, synthetic as syn
+    T = H.load_templates()
+    n = 48
+    h = lib.Handle(max_points=n, chunk_points=32, lmax_out=H.LMAX_OUT, n_tau_max=576, n_k_max=224)
+    h.set_templates(T["highl_unlensed"], T["highl_lensed"])
+    th = syn.draw_thermo(n, seed)
+    ip, al, cal, pert = syn.draw_params(n, seed)
+    tau, dtau, n_tau, k, n_k = syn.build_grids(h, th)
+    src = syn.make_sources(th, tau, k, pert).numpy()
+    h.upload_sources(th, n_k, k, src)
+    out, trip = {}, {}
+    for pk in (3, 4):
+        h.set_option("proj_kernel", pk)
+        h.set_option("count_triples", 1)
+        h.set_option("ring_stats", 1)
+        h.timing(reset=True)
+        out[pk] = h.powers(ip, al)[0]
+        t = h.timing()
+        trip[pk] = t["proj_triples"]
+        if pk == 4:
+            assert t["proj_mask_mismatch"] == 0
+        h.set_option("count_triples", 0)
+        h.set_option("ring_stats", 0)
+    assert trip[3] == trip[4] and trip[4] > 0
+    for X in (0, 1, 2, 3, 4):
+        nz = out[3][:, X] != 0
+        assert np.array_equal(nz, out[4][:, X] != 0)
+        assert np.abs(out[4][:, X][nz] / out[3][:, X][nz] - 1).max() < 1e-9, X
