@@ -451,6 +451,7 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
     CB_CUDA(cudaFuncSetAttribute(project2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
     CB_CUDA(cudaFuncSetAttribute(project3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
     CB_CUDA(cudaFuncSetAttribute(project3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
+    CB_CUDA(cudaFuncSetAttribute(source_spline_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CB_CUDA(cudaFuncSetAttribute(project4_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
     CB_CUDA(cudaFuncSetAttribute(project4_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
     CB_CUDA(cudaFuncSetAttribute(project4_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
@@ -684,11 +685,6 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
     if (h->spline_kernel == 2 && S.NK % 2 == 0) {
       const int tiles = (S.NT * 3 + SPL_ROWS - 1) / SPL_ROWS;
       const size_t smem = sizeof(double) * ((size_t)5 * S.NK + (size_t)SPL_ROWS * (S.NK + 1));
-      static bool attr_set = false;
-      if (!attr_set) {
-        CB_CUDA(cudaFuncSetAttribute(source_spline_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-      }
       source_spline_tiled_kernel<<<(unsigned)(tiles * np), SPL_THREADS, smem, s>>>(v, p0, np, h->w_coef.p, h->w_ddsrc.p);
     } else {
       source_spline_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(v, p0, np, h->w_coef.p, h->w_ddsrc.p);
