@@ -97,6 +97,28 @@ __device__ __forceinline__ int lin_locate(const LinSegs& g, double v, double& x0
   return g.npoints;
 }
 
+// lin_locate with the stretches tried from the last one down: the stretches are disjoint, so the result is the same;
+// the Bessel abscissae of almost every (q, tau) pair lie in the last (coarsest) stretch, found on the first try
+__device__ __forceinline__ int lin_locate_desc(const LinSegs& g, double v, double& x0, double& x1, double& inv_h) {
+#pragma unroll 1
+  for (int r = g.n - 1; r >= 0; r--) {
+    const double lo = g.seg[r][0], hi = g.seg[r][1];
+    if (v < hi && v >= lo) {
+      const double step = g.seg[r][2];
+      const int first = (int)g.seg[r][3];
+      const int j = (int)(__ddiv_rn(__dsub_rn(v, lo), step));
+      const int nseg = ((r + 1 < g.n) ? (int)g.seg[r + 1][3] : g.npoints) - first;
+      x0 = __dadd_rn(lo, __dmul_rn(step, (double)j));
+      x1 = (j + 1 < nseg) ? __dadd_rn(lo, __dmul_rn(step, (double)(j + 1))) : hi;
+      inv_h = g.inv_step[r];
+      return first + j;
+    }
+  }
+  x0 = x1 = g.highest;
+  inv_h = 0;
+  return g.npoints;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

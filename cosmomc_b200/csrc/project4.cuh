@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
 #pragma unroll
     for (int u = 0; u < NU; u++) { jlo[u] = NJ; jhi[u] = NJ - 1; }
     const unsigned* wrow = s_wtab + m_qi * NJP;
+    const float rinvR = 1.0f / (float)R;
     if (ring_warp) {
       for (int t = 0; t < nslab; t++) {
         const int par = t % W4_NST;
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         if (f_valid[u]) {
           const double x = fabs(__dmul_rn(pc.q, __dsub_rn(tau0, f_tau[u])));
           double x0, x1, inv_h;
-          int bi = lin_locate(p.bseg, x, x0, x1, inv_h);
+          int bi = lin_locate_desc(p.bseg, x, x0, x1, inv_h);
           if (bi > p.num_xx - 1) { bi = p.num_xx - 1; x0 = p.bx[bi - 1]; x1 = p.bx[bi]; inv_h = 1.0 / (x1 - x0); }
           // interpolation weights (values, not indices): reciprocal multiplies instead of the reference's divisions
           const double fac = x1 - x0;
@@ -496,7 +497,11 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
             ms1 = (pc.a0 * f_s[u][1][0] + pc.b0 * f_s[u][1][1] + (pc.a03h * f_s[u][1][2] + pc.b03h * f_s[u][1][3]) * pc.ho2o6) * f_dtau[u];
             ms2 = (pc.a0 * f_s[u][2][0] + pc.b0 * f_s[u][2][1] + (pc.a03h * f_s[u][2][2] + pc.b03h * f_s[u][2][3]) * pc.ho2o6) * f_dtau[u];
           }
-          moff = ((bi - 1) % R) * rb;
+          // ring slot of row bi - 1 without an integer division: float estimate of the quotient, corrected by one
+          int sl = (bi - 1) - R * (int)((float)(bi - 1) * rinvR);
+          sl += (sl < 0) ? R : 0;
+          sl -= (sl >= R) ? R : 0;
+          moff = sl * rb;
           if (jlo[u] <= jhi[u]) jr = jlo[u] | ((jhi[u] + 1) << 8);
         }
         if (m_live && tu < nslab) {
