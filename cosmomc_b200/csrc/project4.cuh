@@ -511,12 +511,13 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
           m_rec[pidx] = rec;
         }
       }
-      if (t + W4_MG * MS < nslab) prefetch(n_lo + (t + W4_MG * MS) * S);
-      CK4(ck_a);
+      // publish first, then issue the global loads of the next slab (their issue would only delay the consumers)
 #pragma unroll
       for (int us = 0; us < MS; us++)
         if (t + us < nslab) mbar_arrive(s_bar + ((t + us) % W4_NST));
       CK4(ck_c);
+      if (t + W4_MG * MS < nslab) prefetch(n_lo + (t + W4_MG * MS) * S);
+      CK4(ck_a);
     }
     if (COUNT && p.ring_stats) {
       if (ring_warp && lane == 0) {
