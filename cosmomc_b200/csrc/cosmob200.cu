@@ -40,6 +40,8 @@ struct KindSet {  // per perturbation type (0 scalar, 1 tensor): multipole set +
   DevBuf<double> d_bx;
   DevBuf<double2> d_bes;
   DevBuf<double2> d_bes3;  // [chunk][row][32] layout for the windowed projection
+  DevBuf<double2> d_bes4;  // [row][8 * lk4]: rows packed at the ring's row stride, so that a run of rows is ONE bulk copy (kernel 4)
+  int lk4 = 0;             // octets per packed row
   DevBuf<int> d_llo;  // [max_l+1]
 };
 
@@ -228,6 +230,13 @@ void build_kind(cb200_handle* h, int k, int max_l, double max_eta_k) {
   K.d_bes3.alloc((size_t)PROJ_LW * K.num_xx * 32);
   bessel_relayout_kernel<<<K.num_xx, PROJ_LP, 0, h->stream>>>(K.num_xx, K.d_bes.p, K.d_bes3.p);
   CB_LAUNCH_CHECK();
+  {
+    const int noct = ((int)K.ls.size() + 7) / 8;
+    K.lk4 = w4_octets(noct);
+    K.d_bes4.alloc((size_t)K.num_xx * 8 * K.lk4);
+    CB_CUDA(cudaMemcpy2DAsync(K.d_bes4.p, (size_t)K.lk4 * 128, K.d_bes.p, sizeof(double2) * PROJ_LP, (size_t)K.lk4 * 128,
+                              K.num_xx, cudaMemcpyDeviceToDevice, h->stream));
+  }
   CB_CUDA(cudaStreamSynchronize(h->stream));
   h->n_launches += 3;
 }
@@ -716,10 +725,11 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB = pl.nqb_total; pp.tensors = kind;
       static_assert(W3_QC >= W4_QC, "the fallback pass uses the same wavenumber blocks");
       const int noct = (nl + 7) / 8;
-      const int LK = noct <= 6 ? 6 : noct <= 11 ? 11 : 12;
+      const int LK = w4_octets(noct);
+      if (LK != K.lk4) throw std::runtime_error("packed Bessel table built for another multipole count");
       pp.rb = LK * 128;
       pp.R = std::min(w4_ring_rows(LK, S.NT), 4096);
-      pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes = K.d_bes.p;
+      pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes = K.d_bes4.p;
       pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
       pp.delta = d_delta;
       pp.triples = h->count_triples ? h->d_triples.p : nullptr;

@@ -91,7 +91,7 @@ struct Proj4Params {
   double max_eta_k;
   const double* ddsrc;
   const double* bx;
-  const double2* bes;       // [num_xx][PROJ_LP]
+  const double2* bes;       // [num_xx][rb / 16]: rows packed at the ring's row stride
   const double* initpower;
   double* part;             // [chunk][NQB][6][PROJ_LP]
   double* delta;            // optional [chunk][NQ][PROJ_LP][3]
@@ -119,6 +119,8 @@ constexpr int W4_NST = CB200_W4_NST;  // metadata buffers = slabs the producer m
 constexpr size_t W4_META_BYTES = (size_t)W4_NST * W4_NPAIR * 48;
 constexpr size_t W4_QC_BYTES = sizeof(ProjQ3) * W4_QC;
 constexpr size_t W4_MISC_BYTES = 768;
+// octets per ring row for a multipole set of noct octets (the kernel's template instances)
+inline int w4_octets(int noct) { return noct <= 6 ? 6 : noct <= 11 ? 11 : 12; }
 inline size_t w4_slab_table_bytes(int NT) { return (size_t)8 * ((NT + W4_S - 1) / W4_S + 2); }
 // per-(wavenumber, multipole slot) integration windows {n1, n2} as 2 x u16, rows padded to an odd word count
 inline size_t w4_wtab_bytes(int LK) { return (size_t)4 * W4_QC * (8 * LK + 1); }
@@ -411,17 +413,26 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         }
       }
     };
-    // rows [a, b] of the table -> ring by TMA bulk copies (one per row; slot 0 is mirrored behind slot R-1);
-    // their bytes are accounted on the slab's `full` barrier, so nobody waits for them but the consumers
+    // rows [a, b] of the table -> ring.  The table is packed at the ring's row stride and slot = row mod R, so a run of
+    // rows is ONE TMA bulk copy (two when it wraps around the end of the ring).  Slot 0 is mirrored behind slot R-1
+    // (a pair reads rows i0 and i0 + 1 at a fixed offset): a run that continues through slot 0 simply copies one row
+    // more behind slot R-1; a run that starts at slot 0 mirrors that row with a copy of its own.  The bytes are
+    // accounted on the slab's `full` barrier, so nobody waits for them but the consumers.
     auto fetch_rows = [&](int a, int b, unsigned long long* bar) {
-      int slot = (a + lane) % R;
-      for (int row = a + lane; row <= b; row += 32, slot = (slot + 32) % R) {
-        const double2* g = p.bes + (size_t)row * PROJ_LP;
-        mbar_expect_tx(bar, slot == 0 ? 2 * rb : rb);
-        bulk_g2s(ring + (size_t)slot * rb, g, rb, bar);
+      if (lane == 0) {
+        const int n = b - a + 1;
+        const int slot = a % R;
+        const int n1 = min(n, R - slot);   // rows up to the end of the ring
+        const bool wraps = n > n1;
+        const unsigned char* g = reinterpret_cast<const unsigned char*>(p.bes) + (size_t)a * rb;
+        const unsigned bytes1 = (unsigned)(n1 + (wraps ? 1 : 0)) * rb;
+        const unsigned bytes2 = wraps ? (unsigned)(n - n1) * rb : 0u;
+        mbar_expect_tx(bar, bytes1 + bytes2 + (slot == 0 ? rb : 0));
+        bulk_g2s(ring + (size_t)slot * rb, g, bytes1, bar);
+        if (wraps) bulk_g2s(ring, g + (size_t)n1 * rb, bytes2, bar);
         if (slot == 0) bulk_g2s(ring + (size_t)R * rb, g, rb, bar);
+        if (COUNT && p.ring_stats) st_rows += n;
       }
-      if (COUNT && p.ring_stats && lane == 0 && b >= a) st_rows += b - a + 1;
     };
     int rlo = 0x7fffffff;      // lowest resident row (identical in every producer thread by construction)
     int released = -1;         // slabs <= released have been released by every consumer warp
