@@ -69,10 +69,10 @@ static_assert(W4_PNN >= 1 && W4_S % W4_PNN == 0, "slab shape");
 constexpr int W4_MS = CB200_W4_MS;  // slabs per metadata iteration: their independent chains overlap in one thread
 static_assert(W4_MS == 1 || W4_PPT == 1, "several slabs per metadata iteration need one pair per thread and slab");
 #ifndef CB200_W4_CREG
-#define CB200_W4_CREG 144
+#define CB200_W4_CREG 136
 #endif
 #ifndef CB200_W4_PREG
-#define CB200_W4_PREG 80
+#define CB200_W4_PREG 104
 #endif
 #define CB200_STR2(x) #x
 #define CB200_STR(x) CB200_STR2(x)
@@ -103,7 +103,7 @@ struct Proj4Params {
 };
 
 #ifndef CB200_W4_KB
-#define CB200_W4_KB 2
+#define CB200_W4_KB 3   // 2: 141.7 us/point, 3: 139.9, 1: 150.9
 #endif
 #ifndef CB200_W4_UNSAFE_NORINGWAIT
 #define CB200_W4_UNSAFE_NORINGWAIT 0  // timing experiment only: WRONG results
@@ -393,25 +393,39 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     constexpr int PPT = W4_PPT, PNN = W4_PNN, MS = W4_MS, NU = PPT * MS;
     double f_tau[NU], f_dtau[NU], f_s[NU][3][4];
     bool f_valid[NU];
-    auto prefetch = [&](int nb) {
+    // Source loads of the coming slab(s).  The addresses advance by a fixed stride from one call to the next, so the
+    // thread keeps running byte pointers instead of rebuilding 64-bit addresses from the sample index for each load.
+    const size_t ts_b = tau_stride * sizeof(double);                 // one time sample
+    const unsigned o1 = (unsigned)(row_stride * sizeof(double));     // one source row
+    int pf_n = n_lo + m_grp * MS * S + m_nn;                         // time sample of pair u = 0 at the next call
+    const unsigned char* pf_s = reinterpret_cast<const unsigned char*>(Sp0) + (ptrdiff_t)(pf_n - 1) * (ptrdiff_t)ts_b;
+    const unsigned char* pf_d = reinterpret_cast<const unsigned char*>(Dp0) + (ptrdiff_t)(pf_n - 1) * (ptrdiff_t)ts_b;
+    const size_t pf_step = (size_t)(W4_MG * MS * S) * ts_b;
+    auto prefetch = [&]() {
 #pragma unroll
       for (int u = 0; u < NU; u++) {
-        const int n = nb + (u / PPT) * S + m_nn + (u % PPT) * PNN;   // slab u / PPT of the iteration
+        const int du = (u / PPT) * S + (u % PPT) * PNN;   // slab u / PPT of the iteration (compile-time constant)
+        const int n = pf_n + du;
         f_valid[u] = (n >= pw1) && (n <= pw2);
         if (f_valid[u]) {
           f_tau[u] = __ldg(tau + n - 1);
           f_dtau[u] = __ldg(dtau + n - 1);
-          const double* Sp = Sp0 + (size_t)(n - 1) * tau_stride;
-          const double* Dp = Dp0 + (size_t)(n - 1) * tau_stride;
+          const unsigned char* Sp = pf_s + (size_t)du * ts_b;
+          const unsigned char* Dp = pf_d + (size_t)du * ts_b;
 #pragma unroll
           for (int sI = 0; sI < 3; sI++) {
-            f_s[u][sI][0] = __ldg(Sp + sI * row_stride);
-            f_s[u][sI][1] = __ldg(Sp + sI * row_stride + 1);
-            f_s[u][sI][2] = __ldg(Dp + sI * row_stride);
-            f_s[u][sI][3] = __ldg(Dp + sI * row_stride + 1);
+            const double* sa = reinterpret_cast<const double*>(Sp + sI * o1);
+            const double* da = reinterpret_cast<const double*>(Dp + sI * o1);
+            f_s[u][sI][0] = __ldg(sa);
+            f_s[u][sI][1] = __ldg(sa + 1);
+            f_s[u][sI][2] = __ldg(da);
+            f_s[u][sI][3] = __ldg(da + 1);
           }
         }
       }
+      pf_n += W4_MG * MS * S;
+      pf_s += pf_step;
+      pf_d += pf_step;
     };
     // rows [a, b] of the table -> ring.  The table is packed at the ring's row stride and slot = row mod R, so a run of
     // rows is ONE TMA bulk copy (two when it wraps around the end of the ring).  Slot 0 is mirrored behind slot R-1
@@ -468,7 +482,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         mbar_arrive(s_bar + par);
       }
     }
-    if (!ring_warp && m_grp * MS < nslab) prefetch(n_lo + m_grp * MS * S);
+    if (!ring_warp && m_grp * MS < nslab) prefetch();
     CK4(ck_a);
     for (int t = m_grp * MS; !ring_warp && t < nslab; t += W4_MG * MS) {
       // metadata buffers are free once the consumers have released the slabs that used them NST slabs ago
@@ -527,7 +541,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
       for (int us = 0; us < MS; us++)
         if (t + us < nslab) mbar_arrive(s_bar + ((t + us) % W4_NST));
       CK4(ck_c);
-      if (t + W4_MG * MS < nslab) prefetch(n_lo + (t + W4_MG * MS) * S);
+      if (t + W4_MG * MS < nslab) prefetch();
       CK4(ck_a);
     }
     if (COUNT && p.ring_stats) {
