@@ -327,10 +327,10 @@ def main():
     bytes_pt = float(np.mean(W["n_tau"].astype(np.float64) * 3 * W["n_k"] * 8 * 2)) + (2910 / 24.0) * 6 * 96 * 8
     trip_pt = triples / P
     flop_per_triple = 13  # cubic j_l interpolation: 1 mul + 3 FMA; 3 FMA accumulations (T, E, lensing potential)
-    # ncu --set full capture of this kernel (profiles/r01_project_v4_ncu_full.txt, 64 points): DRAM read + write and
+    # ncu --set full capture of this kernel (profiles/r01_project_v4_final_ncu_full.txt, 64 points): DRAM read + write and
     # shared-memory wavefronts per point; the kernel's own bound is the shared-memory pipe (1 wavefront / clock / SM)
-    NCU_DRAM_BYTES_PER_POINT = (355.31e6 + 36.54e6) / 64
-    NCU_SMEM_WAVEFRONTS_PER_POINT = 1496548128 / 64
+    NCU_DRAM_BYTES_PER_POINT = (353.36e6 + 34.96e6) / 64
+    NCU_SMEM_WAVEFRONTS_PER_POINT = 1482503855 / 64
     sm_clock_hz = 1e6 * float(clocks.get("sm_mhz") or 1965.0)
     roof = {"kernel": "project4_kernel (K1+K2 fused: line-of-sight projection + partial k-contraction)",
             "bound": "hbm", "achieved": bytes_pt * pts_per_launch / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak,
