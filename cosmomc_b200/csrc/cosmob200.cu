@@ -461,12 +461,10 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
     CB_CUDA(cudaFuncSetAttribute(project3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
     CB_CUDA(cudaFuncSetAttribute(project3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
     CB_CUDA(cudaFuncSetAttribute(source_spline_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CB_CUDA(cudaFuncSetAttribute(project4_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
-    CB_CUDA(cudaFuncSetAttribute(project4_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
-    CB_CUDA(cudaFuncSetAttribute(project4_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
-    CB_CUDA(cudaFuncSetAttribute(project4_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
-    CB_CUDA(cudaFuncSetAttribute(project4_kernel<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
-    CB_CUDA(cudaFuncSetAttribute(project4_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL));
+    CB_CUDA((w4_set_smem_attr<6, 6>()));
+    CB_CUDA((w4_set_smem_attr<11, 11>()));
+    CB_CUDA((w4_set_smem_attr<11, W4_KLIM11>()));
+    CB_CUDA((w4_set_smem_attr<12, 12>()));
     const char* pk = std::getenv("CB200_PROJ_KERNEL");
     if (pk && pk[0] >= '1' && pk[0] <= '4') h->proj_kernel = pk[0] - '0';
   } catch (const std::exception& e) {
@@ -740,16 +738,14 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       dim3 grid((nq_max + W4_QC - 1) / W4_QC, np);
       const bool cnt = h->count_triples || h->ring_stats;
       const size_t smem = w4_smem_bytes(LK, S.NT, pp.R);
-      if (LK == 6) {
-        if (cnt) project4_kernel<6, true><<<grid, W4_NT, smem, s>>>(pp);
-        else project4_kernel<6, false><<<grid, W4_NT, smem, s>>>(pp);
-      } else if (LK == 11) {
-        if (cnt) project4_kernel<11, true><<<grid, W4_NT, smem, s>>>(pp);
-        else project4_kernel<11, false><<<grid, W4_NT, smem, s>>>(pp);
-      } else {
-        if (cnt) project4_kernel<12, true><<<grid, W4_NT, smem, s>>>(pp);
-        else project4_kernel<12, false><<<grid, W4_NT, smem, s>>>(pp);
-      }
+      // octets from klim on only hold multipoles above 400: in a scalar run their lensing-potential sum is replaced by the
+      // Limber value (cmbmain.f90:1546-1556), so the kernel instance without those accumulators can be used
+      bool limber_tail = !kind && LK == 11 && W4_KLIM11 < 11;
+      for (int j = 8 * W4_KLIM11; limber_tail && j < nl; j++) limber_tail = K.ls[j] > 400;
+      if (LK == 6) w4_launch<6, 6>(cnt, grid, smem, s, pp);
+      else if (LK == 11 && limber_tail) w4_launch<11, W4_KLIM11>(cnt, grid, smem, s, pp);
+      else if (LK == 11) w4_launch<11, 11>(cnt, grid, smem, s, pp);
+      else w4_launch<12, 12>(cnt, grid, smem, s, pp);
       CB_LAUNCH_CHECK();
       // fallback pass: blocks whose table window does not fit the ring (the first, log-spaced wavenumber block)
       Proj3Params p3;

@@ -103,11 +103,18 @@ struct Proj4Params {
 };
 
 #ifndef CB200_W4_KB
-#define CB200_W4_KB 3   // 2: 141.7 us/point, 3: 139.9, 1: 150.9
+#define CB200_W4_KB 2   // octets per batch of loads in flight (time-split consumers: 1: 136.3 us/point, 2: 132.8, 3: 137.3, 4: 145.6)
 #endif
 #ifndef CB200_W4_UNSAFE_NORINGWAIT
 #define CB200_W4_UNSAFE_NORINGWAIT 0  // timing experiment only: WRONG results
 #endif
+#ifndef CB200_W4_PREDLOAD
+#define CB200_W4_PREDLOAD 0
+#endif
+#ifndef CB200_W4_TSPLIT
+#define CB200_W4_TSPLIT 1  // 1: the two consumer warps of a wavenumber group split the slab's time samples, not the octets
+#endif
+constexpr bool W4_TS = CB200_W4_TSPLIT != 0;
 #ifndef CB200_W4_UNROLL
 #define CB200_W4_UNROLL 1
 #endif
@@ -168,10 +175,29 @@ __device__ __forceinline__ double2 lds128_if(unsigned saddr, bool pred) {
   return r;
 }
 
-template <int LK, bool COUNT>
+// unpredicated 16-byte shared load.  The consumers load the nodes of every lane of an octet batch that has an active
+// lane anywhere in the warp (the address is always inside the ring; the value of an inactive lane is discarded by a
+// select): a predicated load leaves its destination live from the top of the loop, which costs a register pair per
+// load for the whole loop instead of per batch.
+__device__ __forceinline__ double2 lds128(unsigned saddr) {
+  double2 r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(r.x), "=d"(r.y) : "r"(saddr));
+  return r;
+}
+
+template <int LK, bool COUNT, int KLIM>
 __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p) {
   constexpr int NCW = W4_NCW, NQG = W4_NQG, QC = W4_QC, S = W4_S, NPAIR = W4_NPAIR;
-  constexpr int LKH = (LK + 1) / 2;  // octets per consumer lane: k = 2 kk + lh
+  // octets per consumer lane.  W4_TS: every octet (k), the warp pair of a wavenumber group shares the slab's time
+  // samples (lh = 0: samples 0, 2, ..; lh = 1: samples 1, 3, ..) and the two partial sums meet in the epilogue: the
+  // per-pair metadata is read once per 8 LK multipoles instead of once per 4 LK.  Otherwise the pair splits the octets
+  // (k -> 2 k + lh).  K2 = octets that need the lensing-potential accumulator: for a scalar run every multipole above
+  // 400 takes the Limber value in the epilogue (cmbmain.f90:1546-1556), so the host passes KLIM < LK when all octets
+  // >= KLIM lie above 400 (88-multipole set: KLIM = 6) and their third accumulator is never formed.
+  constexpr int LKH = W4_TS ? LK : (LK + 1) / 2;
+  constexpr int K2 = W4_TS ? KLIM : LKH;
+  static_assert(W4_TS || KLIM == LK, "the Limber cut of the accumulators needs the time-split consumers");
+#define W4_OCT(k) (W4_TS ? (k) : 2 * (k) + lh)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int R = p.R;
   constexpr int rb = LK * 128;  // ring row stride in bytes
@@ -194,7 +220,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool consumer = warp < NCW;
   const int qr = lane >> 3, li = lane & 7;   // quarter-warp = wavenumber slot ; octet position
-  const int wg = warp % NQG, lh = (warp / NQG) & 1;  // consumer: wavenumber group, multipole half
+  const int wg = warp % NQG, lh = (warp / NQG) & 1;  // consumer: wavenumber group, half (time samples or octets)
 
   const int nt = v.n_tau[pt], nk = v.n_k[pt];
   const double tau0 = v.thermo[(size_t)pt * 5];
@@ -277,7 +303,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
 #pragma unroll
     for (int k = 0; k < LKH; k++) {
       int n1 = 0, n2 = 0;
-      const int j = li + 8 * (2 * k + lh);
+      const int j = li + 8 * W4_OCT(k);
       const bool lvalid = j < p.nl;
       const int l = lvalid ? p.ls[j] : 0;
       if (myq.valid && lvalid) {
@@ -559,11 +585,14 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
 
   // ============================================= CONSUMER =============================================
   asm volatile("setmaxnreg.inc.sync.aligned.u32 " CB200_STR(CB200_W4_CREG) ";\n");
-  double acc[LKH][3];
+  double acc[LKH][2], acc2[K2];
 #pragma unroll
-  for (int k = 0; k < LKH; k++) acc[k][0] = acc[k][1] = acc[k][2] = 0.0;
-  const unsigned ring_lane = smem_u32(ring) + li * 16 + lh * 128;  // shared-space address
-  const int lc = li + 8 * lh;
+  for (int k = 0; k < LKH; k++) acc[k][0] = acc[k][1] = 0.0;
+#pragma unroll
+  for (int k = 0; k < K2; k++) acc2[k] = 0.0;
+  const unsigned ring_lane = smem_u32(ring) + li * 16 + (W4_TS ? 0 : lh * 128);  // shared-space address
+  const int lc = li + (W4_TS ? 0 : 8 * lh);
+  constexpr int OSH = W4_TS ? 3 : 4, ORND = W4_TS ? 7 : 15, OSTR = W4_TS ? 128 : 256;  // l-slot stride 8 or 16 per k
   CK4(ck_a);
   for (int t = 0; t < nslab; t++) {
     const int par = t % W4_NST;
@@ -585,15 +614,15 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     const Proj4Rec* m_rec = reinterpret_cast<const Proj4Rec*>(mb + NPAIR * 32);
     // quarter-warp r works on pair (q_r, n); every lane covers LK multipoles
 #pragma unroll W4_UNROLL
-    for (int nn = 0; nn < S; nn++) {
+    for (int nn = W4_TS ? lh : 0; nn < S; nn += W4_TS ? 2 : 1) {
       const int n = n_base + nn;
       const int pr = nn * QC + myqi;
       const Proj4Rec rec = m_rec[pr];
       const double2 af = m_af[pr];
       const double2 s01 = m_s01[pr];
       // this lane's octets k with jlo <= lc + 16 k <= jhi (lc = li + 8 lh: the lane's first l-slot)
-      const int klo = max((int)((rec.jr & 0xff) + 15 - lc) >> 4, 0);
-      const int khi1 = ((rec.jr >> 8) + 15 - lc) >> 4;  // khi + 1 >= 0
+      const int klo = max((int)((rec.jr & 0xff) + ORND - lc) >> OSH, 0);
+      const int khi1 = ((rec.jr >> 8) + ORND - lc) >> OSH;  // khi + 1 >= 0
       const unsigned m = ((1u << khi1) - 1u) & ~((1u << klo) - 1u);
       if (COUNT) {
         unsigned mx = 0;
@@ -624,8 +653,14 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
             const int k = k0 + kk;
             if (k < LKH) {
               const bool act = (m >> k) & 1u;
-              N0[kk] = lds128_if(rp + k * 256, act);
-              N1[kk] = lds128_if(rp + k * 256 + rb, act);
+#if CB200_W4_PREDLOAD
+              N0[kk] = lds128_if(rp + k * OSTR, act);
+              N1[kk] = lds128_if(rp + k * OSTR + rb, act);
+#else
+              (void)act;
+              N0[kk] = lds128(rp + k * OSTR);
+              N1[kk] = lds128(rp + k * OSTR + rb);
+#endif
             }
           }
 #pragma unroll
@@ -637,7 +672,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
               Jv = act ? Jv : 0.0;
               acc[k][0] = fma(s01.x, Jv, acc[k][0]);
               acc[k][1] = fma(s01.y, Jv, acc[k][1]);
-              acc[k][2] = fma(rec.s2, Jv, acc[k][2]);
+              if (k < K2) acc2[k] = fma(rec.s2, Jv, acc2[k]);
             }
           }
         }
@@ -685,15 +720,37 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   const ProjQ3& myq = reinterpret_cast<const ProjQ3*>(smem_raw + (size_t)(p.R + 1) * rb + W4_META_BYTES)[myqi];
   // ---- Limber value of the lensing source (cmbmain.f90:1546-1556) and the partial k-contraction ----
   double* red = reinterpret_cast<double*>(smem_raw);  // [wavenumber group][6][PROJ_LP]
+  if (W4_TS) {
+    // the two time halves of a wavenumber group meet: half 1 hands its sums over through the (now free) ring
+    constexpr int NE = 2 * LKH + K2;
+    static_assert((size_t)NQG * 6 * PROJ_LP * 8 <= 32 * 1024 && 32 * 1024 + (size_t)NQG * NE * 32 * 8 <= 128 * 1024, "epilogue scratch inside the ring");
+    double* xs = reinterpret_cast<double*>(smem_raw + 32 * 1024) + (size_t)wg * NE * 32 + lane;  // [wg][entry][lane]
+    if (lh == 1) {
+#pragma unroll
+      for (int k = 0; k < LKH; k++) { xs[(2 * k) * 32] = acc[k][0]; xs[(2 * k + 1) * 32] = acc[k][1]; }
+#pragma unroll
+      for (int k = 0; k < K2; k++) xs[(2 * LKH + k) * 32] = acc2[k];
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W4_NCW) : "memory");
+    if (lh == 0) {
+#pragma unroll
+      for (int k = 0; k < LKH; k++) { acc[k][0] += xs[(2 * k) * 32]; acc[k][1] += xs[(2 * k + 1) * 32]; }
+#pragma unroll
+      for (int k = 0; k < K2; k++) acc2[k] += xs[(2 * LKH + k) * 32];
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W4_NCW) : "memory");  // scratch read before `red` is written next to it
+  }
+  if (!W4_TS || lh == 0) {
 #pragma unroll
   for (int k = 0; k < LKH; k++) {
     double cl[6];
 #pragma unroll
     for (int X = 0; X < 6; X++) cl[X] = 0.0;
-    const int j = li + 8 * (2 * k + lh);
+    const int j = li + 8 * W4_OCT(k);
     const int l = (j < p.nl) ? p.ls[j] : 0;
-    if (2 * k + lh >= LK) continue;  // octet outside the row (odd LK)
-    if (myq.valid && 2 * k + lh < noct) {
+    if (W4_OCT(k) >= LK) continue;  // octet outside the row (odd LK)
+    double d2 = (k < K2) ? acc2[k < K2 ? k : 0] : 0.0;
+    if (myq.valid && W4_OCT(k) < noct) {
       if (!p.tensors && j < p.nl && ((reached >> k) & 1u)) {
         const bool use_limber = l > 400;
         if (!((doint >> k) & 1u) || use_limber) {
@@ -717,10 +774,10 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
             }
             s3 = (sa2 * (1 - xf) + xf * sb2) * sqrt(kPi / 2 / ((double)l + 0.5)) / myq.q;
           }
-          acc[k][2] = s3;
+          d2 = s3;
         }
       }
-      const double d0 = acc[k][0], d1 = acc[k][1], d2 = acc[k][2];
+      const double d0 = acc[k][0], d1 = acc[k][1];
       if (p.delta) {
         double* dp = p.delta + (((size_t)lp * v.NQ + (q0 + myqi)) * PROJ_LP + j) * 3;
         dp[0] = d0; dp[1] = d1; dp[2] = d2;
@@ -742,6 +799,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
       if (qr == 0) red[((size_t)wg * 6 + X) * PROJ_LP + j] = s;
     }
   }
+  }
   asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W4_NCW) : "memory");
   {
     double* pp = p.part + (((size_t)lp * p.NQB + qb) * 6) * PROJ_LP;
@@ -756,6 +814,21 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     }
   }
   }
+#undef W4_OCT
 }
+
+// host side: the template instances in use (octets per row, octets that keep the lensing-potential accumulator)
+template <int LK, int KLIM>
+inline void w4_launch(bool count, dim3 grid, size_t smem, cudaStream_t s, const Proj4Params& pp) {
+  if (count) project4_kernel<LK, true, KLIM><<<grid, W4_NT, smem, s>>>(pp);
+  else project4_kernel<LK, false, KLIM><<<grid, W4_NT, smem, s>>>(pp);
+}
+template <int LK, int KLIM>
+inline cudaError_t w4_set_smem_attr() {
+  cudaError_t e = cudaFuncSetAttribute(project4_kernel<LK, false, KLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(project4_kernel<LK, true, KLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL);
+}
+constexpr int W4_KLIM11 = W4_TS ? 6 : 11;  // 88-multipole scalar set: octets 6..10 are l >= 700 (Limber for the lensing source)
 
 }  // namespace cb200
