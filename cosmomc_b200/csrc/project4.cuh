@@ -8,9 +8,10 @@
 //     pair per step, but each lane now carries LK = ceil(n_l / 8) multipoles (l-slots li + 8k), so the 48 B of
 //     per-pair metadata are read once per 88 multipoles instead of once per 32, the pair metadata is computed
 //     once (not once per multipole chunk) and the ring is filled once per wavenumber block;
-//   * warp specialisation: 12 CONSUMER warps (6 wavenumber groups x 2 multipole halves = even / odd octets) do nothing
+//   * warp specialisation: 12 CONSUMER warps (6 wavenumber groups x 2 time halves: the two warps of a group take
+//     alternate time samples of a slab, every lane all octets; CB200_W4_TSPLIT=0: even / odd octets instead) do nothing
 //     but the accumulation (shared-memory loads + FP64 FMAs).  4 PRODUCER warps: warp 0 keeps the ring filled with
-//     TMA bulk copies (cp.async.bulk, one per table row, byte count on the slab's `full` mbarrier); warps 1-3 compute
+//     TMA bulk copies (cp.async.bulk, one per run of table rows, byte count on the slab's `full` mbarrier); warps 1-3 compute
 //     the (q, tau)-pair metadata of the coming slabs (table row, spline weights, k-interpolated d-tau-weighted
 //     sources; global loads software-pipelined one more slab ahead).  The two producer roles run in separate loops
 //     and meet only the consumers (full / empty mbarriers per metadata buffer): the metadata runs up to NST slabs
