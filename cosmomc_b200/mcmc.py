@@ -201,3 +201,35 @@ def likelihood_derived_params(likelihoods, loglike, type_indices=(), derived=Non
     if derived is not None:
         out = np.concatenate([np.atleast_2d(np.asarray(derived, dtype=np.float64)), out], axis=1)
     return out
+
+
+def _fortran_e(v, width, digits):
+    """Fortran `Ew.d` edit descriptor (0.dddE+ee form, no scale factor), as gfortran / ifort print it."""
+    v = float(v)
+    if v == 0.0 or not np.isfinite(v):
+        s = ("0." + "0" * digits + "E+00") if v == 0.0 else str(v)
+        return s.rjust(width)
+    mant, exp = ("%.*e" % (digits - 1, abs(v))).split("e")   # d.ddd e+xx  ->  0.dddd E+(xx+1)
+    e = int(exp) + 1
+    body = "0." + mant.replace(".", "") + "E%s%02d" % ("+" if e >= 0 else "-", abs(e))
+    return (("-" if v < 0 else "") + body).rjust(width)
+
+
+def write_theory_cl(path, cls, lmax=None, fields=("TT", "TE", "EE", "BB", "PP"), digits=5):
+    """`<root>.theory_cl` (TCosmoTheoryPredictions%WriteTextCls, source/CosmoTheory.f90:197-232): header
+    `#    L    ` + one 15-wide column title per spectrum, then `(1I6,*(E15.5))` rows for L = 2..lmax.
+    cls: [n_spectra][>= lmax+1] in the library's output order (l(l+1)C_l/2pi in muK^2, [L(L+1)]^2 C^pp/2pi for PP).
+    The golden data/base_plikHM_TTTEEE_lowl_lowE.minimum.theory_cl was written with six digits (an older format
+    statement): pass digits=6 to reproduce that file byte for byte."""
+    cls = np.asarray(cls, dtype=np.float64)
+    lmax = cls.shape[1] - 1 if lmax is None else int(lmax)
+    with open(path, "w") as f:
+        f.write(("#    L    " + "".join(t + " " * 13 for t in fields)).rstrip() + "\n")
+        for L in range(2, lmax + 1):
+            f.write("%6d" % L + "".join(_fortran_e(cls[i, L], 15, digits) for i in range(len(fields))) + "\n")
+
+
+def read_theory_cl(path):
+    """Inverse of write_theory_cl: returns (L[int], cls[n_spectra][len(L)])."""
+    a = np.atleast_2d(np.loadtxt(path))
+    return a[:, 0].astype(int), a[:, 1:].T.copy()

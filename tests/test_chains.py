@@ -95,3 +95,28 @@ def test_gloo_world_size_2(tmp_path):
     st = chains.pooled_statistics(chains.pack([chains.chain_record(c) for c in allc], 3), 3)
     assert np.allclose(got["cov"], st["cov"], rtol=1e-13) and abs(float(got["R"]) - st["R"]) < 1e-13
     assert np.array_equal(got["ll"], np.concatenate([np.arange(4.0), np.arange(4.0) + 10]))
+
+
+def test_theory_cl_writer_reproduces_golden_bytes(tmp_path):
+    """WriteTextCls (source/CosmoTheory.f90:197-232): the reference's own
+    data/base_plikHM_TTTEEE_lowl_lowE.minimum.theory_cl, re-written from its parsed values, must come back byte for
+    byte (header, I6 multipole column, E15.6 columns incl. the 0.000000E+00 BB / PP tail above lmax_lensed)."""
+    import os
+    import helpers as H
+    from cosmomc_b200 import mcmc
+    want = open(os.path.join(H.ROOT, "tests", "golden", "data", "theory_cl_excerpt.txt")).read().split("\n")
+    T = H.load_templates()
+    cls = T["theory_cl"].T            # [5][2509], parsed from the same file by tests/golden/make_golden_data.py
+    path = str(tmp_path / "x.theory_cl")
+    mcmc.write_theory_cl(path, cls, lmax=2508, digits=6)
+    got = open(path).read().split("\n")
+    assert len(got) == 2509 and got[-1] == ""          # header + L = 2..2508
+    assert got[:31] == want[:31]
+    assert got[1000:1006] == want[31:37]
+    assert got[2498:2508] == want[37:47]
+    L, back = mcmc.read_theory_cl(path)
+    assert L[0] == 2 and L[-1] == 2508 and np.array_equal(back, cls[:, 2:])
+    # the format statement of the checked-out source is E15.5
+    mcmc.write_theory_cl(path, cls, lmax=4)
+    assert open(path).read().split("\n")[1] == "     2    0.10175E+04    0.26191E+01    0.30894E-01    0.18185E-05    0.50156E-07"
+    assert mcmc._fortran_e(-2.98549, 15, 6) == "  -0.298549E+01" and mcmc._fortran_e(9.99999999, 15, 5) == "    0.10000E+02"
