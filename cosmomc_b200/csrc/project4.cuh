@@ -721,29 +721,35 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   const ProjQ3& myq = reinterpret_cast<const ProjQ3*>(smem_raw + (size_t)(p.R + 1) * rb + W4_META_BYTES)[myqi];
   // ---- Limber value of the lensing source (cmbmain.f90:1546-1556) and the partial k-contraction ----
   double* red = reinterpret_cast<double*>(smem_raw);  // [wavenumber group][6][PROJ_LP]
+  constexpr int KS = (LKH + 1) / 2;  // W4_TS: half 0 finishes the octets below KS, half 1 the others
   if (W4_TS) {
-    // the two time halves of a wavenumber group meet: half 1 hands its sums over through the (now free) ring
-    constexpr int NE = 2 * LKH + K2;
+    // the two time halves of a wavenumber group meet: each hands the sums of the octets the OTHER half finishes over
+    // through the (now free) ring, so the epilogue (Limber values, partial k-contraction) is shared between them
+    constexpr int NE = 3 * LKH;
     static_assert((size_t)NQG * 6 * PROJ_LP * 8 <= 32 * 1024 && 32 * 1024 + (size_t)NQG * NE * 32 * 8 <= 128 * 1024, "epilogue scratch inside the ring");
     double* xs = reinterpret_cast<double*>(smem_raw + 32 * 1024) + (size_t)wg * NE * 32 + lane;  // [wg][entry][lane]
-    if (lh == 1) {
 #pragma unroll
-      for (int k = 0; k < LKH; k++) { xs[(2 * k) * 32] = acc[k][0]; xs[(2 * k + 1) * 32] = acc[k][1]; }
-#pragma unroll
-      for (int k = 0; k < K2; k++) xs[(2 * LKH + k) * 32] = acc2[k];
+    for (int k = 0; k < LKH; k++) {
+      if ((k < KS) == (lh == 1)) {   // not mine to finish
+        xs[(3 * k) * 32] = acc[k][0];
+        xs[(3 * k + 1) * 32] = acc[k][1];
+        if (k < K2) xs[(3 * k + 2) * 32] = acc2[k < K2 ? k : 0];
+      }
     }
     asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W4_NCW) : "memory");
-    if (lh == 0) {
 #pragma unroll
-      for (int k = 0; k < LKH; k++) { acc[k][0] += xs[(2 * k) * 32]; acc[k][1] += xs[(2 * k + 1) * 32]; }
-#pragma unroll
-      for (int k = 0; k < K2; k++) acc2[k] += xs[(2 * LKH + k) * 32];
+    for (int k = 0; k < LKH; k++) {
+      if ((k < KS) == (lh == 0)) {
+        acc[k][0] += xs[(3 * k) * 32];
+        acc[k][1] += xs[(3 * k + 1) * 32];
+        if (k < K2) acc2[k < K2 ? k : 0] += xs[(3 * k + 2) * 32];
+      }
     }
-    asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W4_NCW) : "memory");  // scratch read before `red` is written next to it
   }
-  if (!W4_TS || lh == 0) {
+  {
 #pragma unroll
   for (int k = 0; k < LKH; k++) {
+    if (W4_TS && (k < KS) != (lh == 0)) continue;  // finished by the other half
     double cl[6];
 #pragma unroll
     for (int X = 0; X < 6; X++) cl[X] = 0.0;
