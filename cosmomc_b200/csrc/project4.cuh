@@ -299,10 +299,14 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   // = {0, 0}; cut from below (q >= qmax_int: Limber only) = {0x7fff, 0x7fff}.
   unsigned win[COUNT ? LKH : 1];  // COUNT builds re-derive the mask from the exact windows and compare
   unsigned reached = 0, doint = 0;
+  constexpr int KS = (LKH + 1) / 2;  // W4_TS: half 0 owns the windows / the epilogue of the octets below KS, half 1 the others
   if (consumer) {
     int un1 = 0x7fffffff, un2 = 0;
-#pragma unroll
-    for (int k = 0; k < LKH; k++) {
+    // each half derives the windows of its own octets only (they meet in s_wtab / the atomics below); COUNT builds
+    // need every window in registers.  Not unrolled when split: the body is ~150 instructions
+    const int kb = (W4_TS && !COUNT && lh == 1) ? KS : 0, ke = (W4_TS && !COUNT && lh == 0) ? KS : LKH;
+#pragma unroll(COUNT || !W4_TS ? LKH : 1)
+    for (int k = kb; k < ke; k++) {
       int n1 = 0, n2 = 0;
       const int j = li + 8 * W4_OCT(k);
       const bool lvalid = j < p.nl;
@@ -721,7 +725,6 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   const ProjQ3& myq = reinterpret_cast<const ProjQ3*>(smem_raw + (size_t)(p.R + 1) * rb + W4_META_BYTES)[myqi];
   // ---- Limber value of the lensing source (cmbmain.f90:1546-1556) and the partial k-contraction ----
   double* red = reinterpret_cast<double*>(smem_raw);  // [wavenumber group][6][PROJ_LP]
-  constexpr int KS = (LKH + 1) / 2;  // W4_TS: half 0 finishes the octets below KS, half 1 the others
   if (W4_TS) {
     // the two time halves of a wavenumber group meet: each hands the sums of the octets the OTHER half finishes over
     // through the (now free) ring, so the epilogue (Limber values, partial k-contraction) is shared between them
