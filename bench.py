@@ -329,8 +329,8 @@ def main():
     flop_per_triple = 13  # cubic j_l interpolation: 1 mul + 3 FMA; 3 FMA accumulations (T, E, lensing potential)
     # ncu --set full capture of this kernel (profiles/r01_project_v4_final_ncu_full.txt, 64 points): DRAM read + write and
     # shared-memory wavefronts per point; the kernel's own bound is the shared-memory pipe (1 wavefront / clock / SM)
-    NCU_DRAM_BYTES_PER_POINT = (353.36e6 + 34.96e6) / 64
-    NCU_SMEM_WAVEFRONTS_PER_POINT = 1482503855 / 64
+    NCU_DRAM_BYTES_PER_POINT = (353.15e6 + 34.90e6) / 64
+    NCU_SMEM_WAVEFRONTS_PER_POINT = 1396435361 / 64
     sm_clock_hz = 1e6 * float(clocks.get("sm_mhz") or 1965.0)
     roof = {"kernel": "project4_kernel (K1+K2 fused: line-of-sight projection + partial k-contraction)",
             "bound": "hbm", "achieved": bytes_pt * pts_per_launch / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak,
