@@ -7,7 +7,10 @@
 #include "bessel.cuh"
 #include "dgemm.cuh"
 #include "project.cuh"
-#include "project2.cuh"
+#ifdef CB200_TEST_KERNELS   // superseded generations of K1, only in libcosmob200_test.so (cross-checks of the parity tests)
+#include "project1_test.cuh"
+#include "project2_test.cuh"
+#endif
 #include "project3.cuh"
 #include "project4.cuh"
 #include "lens.cuh"
@@ -104,6 +107,19 @@ struct cb200_handle {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_upload = nullptr;
   bool upload_pending = false, async_upload = false;
+  // results (C_l, derived, status) of cb200_powers go back on a third stream when option "async_results" is on: the
+  // call returns with the copy in flight, cb200_sync / cb200_loglike_batch close it
+  cudaStream_t d2h_stream = nullptr;
+  bool async_results = false, d2h_pending = false;
+  std::vector<cudaEvent_t> d2h_events;
+  // pinned staging of the per-point grids built on the host (two sets: set i is rebuilt while set i-1 is in flight),
+  // so that cb200_upload_sources never blocks on a pageable copy queued behind the previous block's source DMA
+  struct UploadStage {
+    unsigned char* pin = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr; bool used = false;
+  } stage[2];
+  int stage_next = 0;
+  DevBuf<double> w_packed;            // device landing buffer of a packed source block (cb200_upload_sources_packed)
+  DevBuf<long long> w_packed_off;     // [npts] offset of each point's block in it (doubles)
   struct BusyRange { int kind, first, npts; cudaEvent_t done; };
   std::vector<BusyRange> busy;
   KindSet kind[2];
@@ -132,7 +148,7 @@ struct cb200_handle {
   // resident outputs
   DevBuf<double> r_cl_lensed, r_cls_out, r_derived, r_icl, r_cl;
   DevBuf<int> r_status;
-  double saved_highl_norm = 0;
+  DevBuf<double> d_highl_norm;  // device scalar, 0 until the first evaluated point sets it (highl_norm_first_call)
   // likelihoods
   std::vector<std::unique_ptr<LikeEntry>> likes;
   DevBuf<double> w_resid, w_T, w_bc, w_bp, w_bigx, w_quad, w_ll, w_total, w_nuis, w_cls_in, w_binned;
@@ -371,6 +387,7 @@ extern "C" {
 
 void cb200_default_config(cb200_config* c) {
   std::memset(c, 0, sizeof(*c));
+  c->struct_size = (int)sizeof(cb200_config);
   c->device = 0;
   c->lmax_computed_cl = 2500;
   c->cmb_lensing = 1;
@@ -389,9 +406,17 @@ void cb200_default_config(cb200_config* c) {
   c->n_tau_max_tensor = 2304; c->n_k_max_tensor = 128; c->n_q_max_tensor = 1024;
 }
 
+int cb200_config_size(void) { return (int)sizeof(cb200_config); }
+int cb200_abi_version(void) { return CB200_VERSION; }
+
 int cb200_create(const cb200_config* cfg, cb200_handle** out) {
   if (!cfg || !out) return -1;
   *out = nullptr;
+  if (cfg->struct_size != (int)sizeof(cb200_config)) {
+    std::fprintf(stderr, "cosmob200: cb200_config mirror out of step with include/cosmob200.h (caller %d bytes, library %d)\n",
+                 cfg->struct_size, (int)sizeof(cb200_config));
+    return -3;
+  }
   std::unique_ptr<cb200_handle> h(new cb200_handle());
   h->cfg = *cfg;
   cb200_config& c = h->cfg;
@@ -402,6 +427,7 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
     CB_CUDA(cudaSetDevice(c.device));
     CB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CB_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     CB_CUDA(cudaEventCreateWithFlags(&h->ev_upload, cudaEventDisableTiming));
     if (c.accuracy_level != 1) throw std::runtime_error("only accuracy_level = 1 is supported");
     if (!c.cmb_lensing) throw std::runtime_error("only CMB_lensing = T is supported");
@@ -454,10 +480,12 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
     I.chunk_points = h->chunk;
     const char* ct = std::getenv("CB200_COUNT_TRIPLES");
     h->count_triples = ct && ct[0] == '1';
+#ifdef CB200_TEST_KERNELS
     CB_CUDA(cudaFuncSetAttribute(project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CB_CUDA(cudaFuncSetAttribute(project2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
     CB_CUDA(cudaFuncSetAttribute(project2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
+#endif
     CB_CUDA(cudaFuncSetAttribute(project3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
     CB_CUDA(cudaFuncSetAttribute(project3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
     CB_CUDA(cudaFuncSetAttribute(source_spline_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -479,6 +507,9 @@ void cb200_destroy(cb200_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
+  for (auto e : h->d2h_events) cudaEventDestroy(e);
+  for (auto& st : h->stage) { if (st.pin) cudaFreeHost(st.pin); if (st.done) cudaEventDestroy(st.done); }
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->ev_upload) cudaEventDestroy(h->ev_upload);
   for (auto& b : h->busy) cudaEventDestroy(b.done);
@@ -594,38 +625,39 @@ int cb200_get_bessel_table(const cb200_handle* hc, int kind, double* x, double* 
   CB_API_END(h)
 }
 
-int cb200_upload_sources(cb200_handle* h, int kind, int first, int npts, const double* thermo, const int* n_k,
-                         const double* k, const double* src, int src_is_device) {
-  if (!h) return -1;
-  CB_API_BEGIN
+}  // extern "C"
+
+namespace {
+
+// scatter of a packed source block [pt][n_tau][3][n_k] (exact sizes, as CAMB holds Src(k, s, tau)) into the padded
+// resident layout [pt][NT][3][NK]; one warp per (point, time sample, source) row, coalesced both ways
+__global__ void unpack_sources_kernel(int npts, int first, int NT, int NK, const int* __restrict__ n_tau,
+                                      const int* __restrict__ n_k, const long long* __restrict__ off,
+                                      const double* __restrict__ packed, double* __restrict__ src) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (tau, source) row of the point
+  const int i = blockIdx.y, lane = threadIdx.x & 31;
+  if (i >= npts || row >= NT * 3) return;
+  const int nt = n_tau[first + i], nk = n_k[first + i];
+  const int t = row / 3;
+  double* dst = src + ((size_t)(first + i) * NT * 3 + row) * NK;
+  if (t < nt) {
+    const double* from = packed + off[i] + (size_t)row * nk;
+    for (int k = lane; k < nk; k += 32) dst[k] = from[k];
+    for (int k = nk + lane; k < NK; k += 32) dst[k] = 0.0;
+  } else {
+    for (int k = lane; k < NK; k += 32) dst[k] = 0.0;
+  }
+}
+
+// src_mode 0: padded host buffer, 1: padded device buffer, 2: packed host buffer, 3: no sources (grids only)
+int upload_impl(cb200_handle* h, int kind, int first, int npts, const double* thermo, const int* n_tau_in, const int* n_k,
+                const double* k, const double* src, int src_mode) {
   if (kind < 0 || kind > 1 || !h->kind[kind].active) return fail(h, "upload_sources: kind not configured");
   if (first < 0 || npts <= 0 || first + npts > h->cfg.max_points) return fail(h, "upload_sources: point range exceeds max_points");
   CB_CUDA(cudaSetDevice(h->cfg.device));
   ensure_store(h, kind);
   PointStore& S = h->store[kind];
   const KindSet& K = h->kind[kind];
-  std::vector<double> tau((size_t)npts * S.NT, 0.0), dtau((size_t)npts * S.NT, 0.0), q((size_t)npts * S.NQ, 0.0),
-      dq((size_t)npts * S.NQ, 0.0);
-  std::vector<int> ntau(npts), nq(npts);
-  std::vector<LinSegs> tseg(npts);
-  std::string perr;
-  parallel_for(npts, [&](int a, int b) {
-    SampleGrid gt, gq;
-    for (int i = a; i < b; i++) {
-      const double* th = thermo + (size_t)i * 5;
-      make_time_steps(gt, th[1], th[2], th[0], K.max_eta_k, kind == 1, th[3], th[4]);
-      make_q_grid(gq, th[0], K.max_eta_k, K.max_l);
-      if (gt.npoints > S.NT) throw std::runtime_error("n_tau exceeds n_tau_max");
-      if (gq.npoints > S.NQ) throw std::runtime_error("n_q exceeds n_q_max");
-      if (n_k[i] > S.NK || n_k[i] < 4) throw std::runtime_error("n_k out of range");
-      ntau[i] = gt.npoints; nq[i] = gq.npoints;
-      std::copy(gt.x.begin(), gt.x.end(), tau.begin() + (size_t)i * S.NT);
-      std::copy(gt.dx.begin(), gt.dx.end(), dtau.begin() + (size_t)i * S.NT);
-      std::copy(gq.x.begin(), gq.x.end(), q.begin() + (size_t)i * S.NQ);
-      std::copy(gq.dx.begin(), gq.dx.end(), dq.begin() + (size_t)i * S.NQ);
-      tseg[i] = to_linsegs(gt);
-    }
-  });
   cudaStream_t s = h->copy_stream;
   // an in-flight cb200_powers call that still reads this point range has to finish first
   for (size_t i = 0; i < h->busy.size();) {
@@ -634,24 +666,94 @@ int cb200_upload_sources(cb200_handle* h, int kind, int first, int npts, const d
     if (br.kind == kind && br.first < first + npts && first < br.first + br.npts) CB_CUDA(cudaStreamWaitEvent(s, br.done, 0));
     i++;
   }
-  const size_t f = first;
-  CB_CUDA(cudaMemcpyAsync(S.thermo.p + f * 5, thermo, sizeof(double) * npts * 5, cudaMemcpyHostToDevice, s));
-  CB_CUDA(cudaMemcpyAsync(S.tau.p + f * S.NT, tau.data(), sizeof(double) * tau.size(), cudaMemcpyHostToDevice, s));
-  CB_CUDA(cudaMemcpyAsync(S.dtau.p + f * S.NT, dtau.data(), sizeof(double) * dtau.size(), cudaMemcpyHostToDevice, s));
-  CB_CUDA(cudaMemcpyAsync(S.q.p + f * S.NQ, q.data(), sizeof(double) * q.size(), cudaMemcpyHostToDevice, s));
-  CB_CUDA(cudaMemcpyAsync(S.dq.p + f * S.NQ, dq.data(), sizeof(double) * dq.size(), cudaMemcpyHostToDevice, s));
-  CB_CUDA(cudaMemcpyAsync(S.ksrc.p + f * S.NK, k, sizeof(double) * (size_t)npts * S.NK, cudaMemcpyHostToDevice, s));
-  CB_CUDA(cudaMemcpyAsync(S.n_tau.p + f, ntau.data(), sizeof(int) * npts, cudaMemcpyHostToDevice, s));
-  CB_CUDA(cudaMemcpyAsync(S.n_q.p + f, nq.data(), sizeof(int) * npts, cudaMemcpyHostToDevice, s));
-  CB_CUDA(cudaMemcpyAsync(S.n_k.p + f, n_k, sizeof(int) * npts, cudaMemcpyHostToDevice, s));
-  CB_CUDA(cudaMemcpyAsync(S.tseg.p + f, tseg.data(), sizeof(LinSegs) * npts, cudaMemcpyHostToDevice, s));
-  // the grid vectors above live in pageable memory: the runtime stages them before returning, so they may go out
-  // of scope; the (large) source block goes last and, from a pinned buffer, is a true asynchronous DMA
+  // per-point staging layout (bytes), 16-byte aligned sections
+  const size_t per_pt = sizeof(double) * (5 + 2 * (size_t)S.NT + 2 * (size_t)S.NQ + S.NK) + sizeof(int) * 4 +
+                        sizeof(LinSegs) + sizeof(long long);
+  const int SB = 512;   // points per staging pass
   const size_t per = (size_t)S.NT * 3 * S.NK;
-  if (src)
-    CB_CUDA(cudaMemcpyAsync(S.src.p + f * per, src, sizeof(double) * per * npts,
-                            src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-  for (int i = 0; i < npts; i++) { S.h_nq[first + i] = nq[i]; S.h_ntau[first + i] = ntau[i]; }
+  long long packed_done = 0;   // doubles of the caller's packed buffer consumed so far
+  for (int b0 = 0; b0 < npts; b0 += SB) {
+    const int nb = std::min(SB, npts - b0);
+    cb200_handle::UploadStage& st = h->stage[h->stage_next];
+    h->stage_next ^= 1;
+    const size_t need = per_pt * SB + 256;
+    if (st.bytes < need) {
+      if (st.pin) { if (st.used) CB_CUDA(cudaEventSynchronize(st.done)); CB_CUDA(cudaFreeHost(st.pin)); }
+      CB_CUDA(cudaHostAlloc((void**)&st.pin, need, cudaHostAllocDefault));
+      st.bytes = need;
+      if (!st.done) CB_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+      st.used = false;
+    }
+    if (st.used) CB_CUDA(cudaEventSynchronize(st.done));   // the copies issued from this set two passes ago
+    unsigned char* base = st.pin;
+    auto carve = [&](size_t bytes) { unsigned char* r = base; base += (bytes + 15) / 16 * 16; return r; };
+    double* p_thermo = (double*)carve(sizeof(double) * 5 * SB);
+    double* p_tau = (double*)carve(sizeof(double) * (size_t)S.NT * SB);
+    double* p_dtau = (double*)carve(sizeof(double) * (size_t)S.NT * SB);
+    double* p_q = (double*)carve(sizeof(double) * (size_t)S.NQ * SB);
+    double* p_dq = (double*)carve(sizeof(double) * (size_t)S.NQ * SB);
+    double* p_k = (double*)carve(sizeof(double) * (size_t)S.NK * SB);
+    int* p_ntau = (int*)carve(sizeof(int) * SB);
+    int* p_nq = (int*)carve(sizeof(int) * SB);
+    int* p_nk = (int*)carve(sizeof(int) * SB);
+    LinSegs* p_tseg = (LinSegs*)carve(sizeof(LinSegs) * SB);
+    long long* p_off = (long long*)carve(sizeof(long long) * SB);
+    parallel_for(nb, [&](int a, int b) {
+      SampleGrid gt, gq;
+      for (int i = a; i < b; i++) {
+        const double* th = thermo + (size_t)(b0 + i) * 5;
+        make_time_steps(gt, th[1], th[2], th[0], K.max_eta_k, kind == 1, th[3], th[4]);
+        make_q_grid(gq, th[0], K.max_eta_k, K.max_l);
+        const int nki = n_k[b0 + i];
+        if (gt.npoints > S.NT) throw std::runtime_error("n_tau exceeds n_tau_max");
+        if (gq.npoints > S.NQ) throw std::runtime_error("n_q exceeds n_q_max");
+        if (nki > S.NK || nki < 4) throw std::runtime_error("n_k out of range");
+        if (n_tau_in && n_tau_in[b0 + i] != gt.npoints)
+          throw std::runtime_error("packed sources: n_tau differs from the time-step grid the thermal-history scalars give");
+        p_ntau[i] = gt.npoints; p_nq[i] = gq.npoints; p_nk[i] = nki;
+        std::copy(th, th + 5, p_thermo + (size_t)i * 5);
+        double* t = p_tau + (size_t)i * S.NT; double* dt = p_dtau + (size_t)i * S.NT;
+        std::copy(gt.x.begin(), gt.x.end(), t); std::fill(t + gt.npoints, t + S.NT, 0.0);
+        std::copy(gt.dx.begin(), gt.dx.end(), dt); std::fill(dt + gt.npoints, dt + S.NT, 0.0);
+        double* qq = p_q + (size_t)i * S.NQ; double* dqq = p_dq + (size_t)i * S.NQ;
+        std::copy(gq.x.begin(), gq.x.end(), qq); std::fill(qq + gq.npoints, qq + S.NQ, 0.0);
+        std::copy(gq.dx.begin(), gq.dx.end(), dqq); std::fill(dqq + gq.npoints, dqq + S.NQ, 0.0);
+        std::copy(k + (size_t)(b0 + i) * S.NK, k + (size_t)(b0 + i + 1) * S.NK, p_k + (size_t)i * S.NK);
+        p_tseg[i] = to_linsegs(gt);
+      }
+    });
+    const size_t f = (size_t)first + b0;
+    CB_CUDA(cudaMemcpyAsync(S.thermo.p + f * 5, p_thermo, sizeof(double) * nb * 5, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(S.tau.p + f * S.NT, p_tau, sizeof(double) * (size_t)nb * S.NT, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(S.dtau.p + f * S.NT, p_dtau, sizeof(double) * (size_t)nb * S.NT, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(S.q.p + f * S.NQ, p_q, sizeof(double) * (size_t)nb * S.NQ, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(S.dq.p + f * S.NQ, p_dq, sizeof(double) * (size_t)nb * S.NQ, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(S.ksrc.p + f * S.NK, p_k, sizeof(double) * (size_t)nb * S.NK, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(S.n_tau.p + f, p_ntau, sizeof(int) * nb, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(S.n_q.p + f, p_nq, sizeof(int) * nb, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(S.n_k.p + f, p_nk, sizeof(int) * nb, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(S.tseg.p + f, p_tseg, sizeof(LinSegs) * nb, cudaMemcpyHostToDevice, s));
+    for (int i = 0; i < nb; i++) { S.h_nq[f + i] = p_nq[i]; S.h_ntau[f + i] = p_ntau[i]; }
+    if (src_mode == 0 || src_mode == 1) {
+      CB_CUDA(cudaMemcpyAsync(S.src.p + f * per, src + (size_t)b0 * per, sizeof(double) * per * nb,
+                              src_mode == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    } else if (src_mode == 2) {
+      long long tot = 0;
+      for (int i = 0; i < nb; i++) { p_off[i] = tot; tot += (long long)p_ntau[i] * 3 * p_nk[i]; }
+      h->w_packed.alloc((size_t)SB * per);
+      h->w_packed_off.alloc(SB);
+      CB_CUDA(cudaMemcpyAsync(h->w_packed_off.p, p_off, sizeof(long long) * nb, cudaMemcpyHostToDevice, s));
+      CB_CUDA(cudaMemcpyAsync(h->w_packed.p, src + packed_done, sizeof(double) * (size_t)tot, cudaMemcpyHostToDevice, s));
+      dim3 grid((S.NT * 3 + 7) / 8, nb);
+      unpack_sources_kernel<<<grid, 256, 0, s>>>(nb, (int)f, S.NT, S.NK, S.n_tau.p, S.n_k.p, h->w_packed_off.p,
+                                                 h->w_packed.p, S.src.p);
+      CB_LAUNCH_CHECK();
+      h->n_launches += 1;
+      packed_done += tot;
+    }
+    CB_CUDA(cudaEventRecord(st.done, s));
+    st.used = true;
+  }
   CB_CUDA(cudaEventRecord(h->ev_upload, s));
   h->upload_pending = true;
   // default: the caller may reuse its buffers as soon as this returns.  With option "async_upload" the call
@@ -659,6 +761,26 @@ int cb200_upload_sources(cb200_handle* h, int kind, int first, int npts, const d
   // returns results); the next cb200_powers is ordered behind it on the device.
   if (!h->async_upload) CB_CUDA(cudaStreamSynchronize(s));
   return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cb200_upload_sources(cb200_handle* h, int kind, int first, int npts, const double* thermo, const int* n_k,
+                         const double* k, const double* src, int src_is_device) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  return upload_impl(h, kind, first, npts, thermo, nullptr, n_k, k, src, !src ? 3 : (src_is_device ? 1 : 0));
+  CB_API_END(h)
+}
+
+int cb200_upload_sources_packed(cb200_handle* h, int kind, int first, int npts, const double* thermo, const int* n_tau,
+                                const int* n_k, const double* k, const double* src_packed) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (!n_tau || !src_packed) return fail(h, "upload_sources_packed: n_tau and src_packed are required");
+  return upload_impl(h, kind, first, npts, thermo, n_tau, n_k, k, src_packed, 2);
   CB_API_END(h)
 }
 
@@ -702,6 +824,7 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
   ProjLaunch pl{PROJ_Q, (S.NQ + PROJ_Q - 1) / PROJ_Q};
   {  // K1
     cb200_handle::Scope sc(h, PH_PROJECT);
+#ifdef CB200_TEST_KERNELS
     if (h->proj_kernel == 1) {
       ProjParams pp;
       pp.v = v; pp.p0 = p0; pp.nl = nl; pp.num_xx = K.num_xx; pp.NQB = pl.nqb_total; pp.tensors = kind;
@@ -716,7 +839,9 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       const size_t smem = std::max(META, RED) + sizeof(ProjQ) * PROJ_Q;
       dim3 grid((nq_max + PROJ_Q - 1) / PROJ_Q, np);
       project_kernel<PROJ_Q, PROJ_NS, PROJ_SLAB><<<grid, 32 * PROJ_LW * PROJ_NS, smem, s>>>(pp);
-    } else if (h->proj_kernel == 4) {
+    } else
+#endif
+    if (h->proj_kernel == 4) {
       pl.q_per_block = W4_QC;
       pl.nqb_total = (S.NQ + W4_QC - 1) / W4_QC;
       Proj4Params pp;
@@ -734,6 +859,7 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       pp.ring_stats = h->ring_stats ? h->d_ring_stats.p : nullptr;
       pp.fallback = h->w_fallback.p;
       pp.bseg = K.bseg;
+      w4_set_last_stretch(pp);
       for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
       dim3 grid((nq_max + W4_QC - 1) / W4_QC, np);
       const bool cnt = h->count_triples || h->ring_stats;
@@ -780,6 +906,7 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       if (h->count_triples || h->ring_stats) project3_kernel<true><<<grid, 32 * W3_NW, W3_SMEM, s>>>(pp);
       else project3_kernel<false><<<grid, 32 * W3_NW, W3_SMEM, s>>>(pp);
     } else {
+#ifdef CB200_TEST_KERNELS
       pl.q_per_block = W2_QC;
       pl.nqb_total = (S.NQ + W2_QC - 1) / W2_QC;
       Proj2Params pp;
@@ -794,6 +921,9 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       dim3 grid((nq_max + W2_QC - 1) / W2_QC, (nl + 31) / 32, np);
       if (h->count_triples || h->ring_stats) project2_kernel<true><<<grid, 32 * W2_NW, W2_SMEM, s>>>(pp);
       else project2_kernel<false><<<grid, 32 * W2_NW, W2_SMEM, s>>>(pp);
+#else
+      throw std::runtime_error("projection kernels 1 and 2 are test kernels: load libcosmob200_test.so");
+#endif
     }
     CB_LAUNCH_CHECK();
     h->n_launches += 1;
@@ -854,7 +984,14 @@ void lens_chunk(cb200_handle* h, int p0, int np, const double* d_cl_tensor, int 
   fp.highl = h->d_highl.p; fp.aphiphi = have_aphi ? h->w_aphi.p : nullptr;
   fp.cl_lensed = h->r_cl_lensed.p + (size_t)p0 * 4 * h->LS;
   fp.cls_out = h->r_cls_out.p + (size_t)p0 * 5 * (lmax_out + 1);
-  fp.saved_highl_norm = h->cfg.highl_norm_first_call ? h->saved_highl_norm : 0.0;
+  fp.norm_dev = nullptr;
+  if (h->cfg.highl_norm_first_call && h->n_highl > 0) {
+    if (!h->d_highl_norm.p) { h->d_highl_norm.alloc(1); h->d_highl_norm.zero(s); }
+    fp.norm_dev = h->d_highl_norm.p;
+    highl_norm_kernel<<<1, 32, 0, s>>>(fp);
+    CB_LAUNCH_CHECK();
+    h->n_launches += 1;
+  }
   const int lspan = std::max(h->LS, lmax_out + 1);
   dim3 gf((lspan + 127) / 128, np);
   lens_finish_kernel<<<gf, 128, 0, s>>>(fp);
@@ -869,9 +1006,37 @@ void lens_chunk(cb200_handle* h, int p0, int np, const double* d_cl_tensor, int 
                           cudaMemcpyDeviceToDevice, s));
 }
 
+// close the window of asynchronous result copies (option "async_results")
+void finish_results(cb200_handle* h) {
+  if (!h->d2h_pending) return;
+  CB_CUDA(cudaStreamSynchronize(h->d2h_stream));
+  for (auto e : h->d2h_events) cudaEventDestroy(e);
+  h->d2h_events.clear();
+  h->d2h_pending = false;
+}
+
 int powers_finish(cb200_handle* h, int first, int npts, double* cls_out, double* derived_out, int* status) {
   cudaStream_t s = h->stream;
   const int lmax_out = h->cfg.lmax_out;
+  if (h->async_results && (cls_out || derived_out || status)) {
+    // results travel on their own stream behind an event of the compute stream; nothing blocks the host
+    cudaEvent_t e;
+    CB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->d2h_events.push_back(e);
+    CB_CUDA(cudaEventRecord(e, s));
+    cudaStream_t d = h->d2h_stream;
+    CB_CUDA(cudaStreamWaitEvent(d, e, 0));
+    if (cls_out)
+      CB_CUDA(cudaMemcpyAsync(cls_out, h->r_cls_out.p + (size_t)first * 5 * (lmax_out + 1),
+                              sizeof(double) * npts * 5 * (lmax_out + 1), cudaMemcpyDeviceToHost, d));
+    if (derived_out)
+      CB_CUDA(cudaMemcpyAsync(derived_out, h->r_derived.p + (size_t)first * 4, sizeof(double) * npts * 4,
+                              cudaMemcpyDeviceToHost, d));
+    if (status)
+      CB_CUDA(cudaMemcpyAsync(status, h->r_status.p + first, sizeof(int) * npts, cudaMemcpyDeviceToHost, d));
+    h->d2h_pending = true;
+    return 0;
+  }
   if (cls_out)
     CB_CUDA(cudaMemcpyAsync(cls_out, h->r_cls_out.p + (size_t)first * 5 * (lmax_out + 1),
                             sizeof(double) * npts * 5 * (lmax_out + 1), cudaMemcpyDeviceToHost, s));
@@ -881,15 +1046,6 @@ int powers_finish(cb200_handle* h, int first, int npts, double* cls_out, double*
   if (status)
     CB_CUDA(cudaMemcpyAsync(status, h->r_status.p + first, sizeof(int) * npts, cudaMemcpyDeviceToHost, s));
   if (cls_out || derived_out || status) CB_CUDA(cudaStreamSynchronize(s));
-  if (h->cfg.highl_norm_first_call && h->saved_highl_norm == 0 && h->n_highl > 0) {
-    // reference SAVE semantics: the first evaluated point fixes the tail normalisation for the whole run
-    const int lmx = std::min(h->cfg.lmax_computed_cl, lmax_out);
-    double tt = 0;
-    std::vector<double> hl(1);
-    CB_CUDA(cudaMemcpy(&tt, h->r_cls_out.p + (size_t)first * 5 * (lmax_out + 1) + lmx, sizeof(double), cudaMemcpyDeviceToHost));
-    CB_CUDA(cudaMemcpy(hl.data(), h->d_highl.p + lmx, sizeof(double), cudaMemcpyDeviceToHost));
-    h->saved_highl_norm = tt / hl[0];
-  }
   return 0;
 }
 
@@ -1548,8 +1704,10 @@ int cb200_loglike_batch(cb200_handle* h, int first, int npts, const double* nuis
   if (h->n_cmb_likes > 0 && !h->r_cls_out.p) return fail(h, "loglike_batch: no resident Cls");
   CB_CUDA(cudaSetDevice(h->cfg.device));
   const bool have_cls = h->r_cls_out.p != nullptr;
-  return loglike_device(h, first, npts, have_cls ? h->r_cls_out.p + (size_t)first * 5 * (h->cfg.lmax_out + 1) : nullptr,
-                        have_cls ? h->r_status.p + first : nullptr, nuisance, n_nuis, loglikes, total, status);
+  const int rc = loglike_device(h, first, npts, have_cls ? h->r_cls_out.p + (size_t)first * 5 * (h->cfg.lmax_out + 1) : nullptr,
+                                have_cls ? h->r_status.p + first : nullptr, nuisance, n_nuis, loglikes, total, status);
+  finish_results(h);   // asynchronous result copies of earlier cb200_powers calls are complete when -lnL is returned
+  return rc;
   CB_API_END(h)
 }
 
@@ -1780,6 +1938,7 @@ int cb200_set_option(cb200_handle* h, const char* name, double value) {
   else if (n == "keep_transfers") h->keep_transfers = value != 0;
   else if (n == "ring_stats") h->ring_stats = value != 0;
   else if (n == "async_upload") h->async_upload = value != 0;
+  else if (n == "async_results") h->async_results = value != 0;
   else if (n == "sn_preassemble") h->sn_preassemble = value != 0;
   else if (n == "spline_kernel") h->spline_kernel = (value == 1) ? 1 : 2;
   else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 4) ? (int)value : 4;
@@ -1817,6 +1976,7 @@ int cb200_sync(cb200_handle* h) {
   CB_CUDA(cudaSetDevice(h->cfg.device));
   CB_CUDA(cudaStreamSynchronize(h->copy_stream));
   CB_CUDA(cudaStreamSynchronize(h->stream));
+  finish_results(h);
   return 0;
   CB_API_END(h)
 }

@@ -296,8 +296,23 @@ struct FinishParams {
   const double* aphiphi;   // [np] or null
   double* cl_lensed;       // [np][4][LS] dimensionless
   double* cls_out;         // [np][5][lmax_out+1] TT,TE,EE,BB,PP
-  double saved_highl_norm; // >0: use this value (reference SAVE semantics)
+  // reference SAVE semantics (`real(mcp) :: highL_norm = 0`, Calculator_CAMB.f90:358,398-399): the lensed-only TT of the
+  // FIRST point ever evaluated fixes the tail normalisation of every later point and call.  Device scalar, written once
+  // by highl_norm_kernel ahead of lens_finish_kernel; null: every point normalises its own tail.
+  double* norm_dev;
 };
+
+__device__ __forceinline__ double lensed_tt_units(const FinishParams& p, int lp, int ll) {
+  const double cons = (2.7255 * 1e6) * (2.7255 * 1e6);
+  const double fac = ll * (ll + 1) / kTwoPi * p.dtheta * 2 * kPi;
+  return cons * (p.lcon[(size_t)lp * 4 * p.NLL + (ll - 2)] * fac + p.cl[(size_t)lp * 6 * p.LS + ll]);
+}
+
+__global__ void highl_norm_kernel(FinishParams p) {
+  if (threadIdx.x || blockIdx.x || *p.norm_dev != 0) return;
+  const int lmx = min(p.lmax_computed_cl, p.lmax_out);
+  if (lmx < p.n_highl) *p.norm_dev = lensed_tt_units(p, 0, lmx) / p.highl[lmx];
+}
 
 __global__ void lens_finish_kernel(FinishParams p) {
   const int lp = blockIdx.y;
@@ -338,8 +353,8 @@ __global__ void lens_finish_kernel(FinishParams p) {
       const float ratio = ((float)(l + 1) * (float)(l + 1)) / (float)(l * l);
       v[4] = c[3 * (size_t)p.LS + l] * (double)ratio / kTwoPi * (p.aphiphi ? p.aphiphi[lp] : 1.0);
     } else if (l < p.n_highl) {
-      double norm = p.saved_highl_norm;
-      if (!(norm > 0)) {
+      double norm = p.norm_dev ? *p.norm_dev : 0.0;
+      if (!p.norm_dev) {
         double o[4];
         lensed(lmx, o);
         norm = cons * o[0] / p.highl[lmx];

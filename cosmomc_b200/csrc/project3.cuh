@@ -470,4 +470,11 @@ __global__ void __launch_bounds__(32 * W3_NW, CB200_W3_MINB) project3_kernel(con
 
 constexpr size_t W3_SMEM = sizeof(double2) * (W3_R + 1) * 32 + sizeof(ProjMeta3) * W3_NW + sizeof(ProjQ3) * W3_QC;
 
+// re-layout of the node table for the chunked kernel (project3_kernel, the fallback pass of project4_kernel): [row][PROJ_LP] -> [chunk][row][32]
+__global__ void bessel_relayout_kernel(int num_xx, const double2* __restrict__ bes, double2* __restrict__ bes3) {
+  const int i = blockIdx.x, t = threadIdx.x;  // t < PROJ_LP
+  if (i >= num_xx || t >= PROJ_LP) return;
+  bes3[((size_t)(t >> 5) * num_xx + i) * 32 + (t & 31)] = bes[(size_t)i * PROJ_LP + t];
+}
+
 }  // namespace cb200

@@ -41,7 +41,10 @@ namespace cb200 {
 #define CB200_W4_NQG 6
 #endif
 constexpr int W4_NQG = CB200_W4_NQG;  // wavenumber groups (4 wavenumbers = one warp's quarter-warps)
-constexpr int W4_NCW = 2 * W4_NQG;    // consumer warps: wavenumber group x multipole half (even / odd octets)
+#ifndef CB200_W4_OSPLIT
+#define CB200_W4_OSPLIT 0  // 1: on top of the time split, even / odd octets go to different warps (4 warps per wavenumber group)
+#endif
+constexpr int W4_NCW = 2 * W4_NQG * (1 + CB200_W4_OSPLIT);  // consumer warps: wavenumber group x time half (x octet parity)
 constexpr int W4_QC = 4 * W4_NQG;     // wavenumbers per CTA
 constexpr int W4_S = CB200_W4_S;      // time samples per slab
 constexpr int W4_NPAIR = W4_QC * W4_S;
@@ -100,14 +103,62 @@ struct Proj4Params {
   unsigned long long* ring_stats;  // optional [16]
   unsigned char* fallback;  // [chunk][NQB]: 1 = a slab of this block needs more table rows than the ring holds
   LinSegs bseg;
+  // the last (coarsest) stretch of the Bessel abscissa grid, where almost every x = q (tau0 - tau) lies: scalar copies
+  // so that the producers reach them as immediate constant-bank operands (filled by w4_set_last_stretch)
+  double bl_lo, bl_hi, bl_step, bl_inv;
+  int bl_first, bl_nseg;
   int ls[PROJ_LP];
 };
+
+inline void w4_set_last_stretch(Proj4Params& p) {
+  const LinSegs& g = p.bseg;
+  const int r = g.n - 1;
+  p.bl_lo = g.seg[r][0]; p.bl_hi = g.seg[r][1]; p.bl_step = g.seg[r][2]; p.bl_inv = g.inv_step[r];
+  p.bl_first = (int)g.seg[r][3]; p.bl_nseg = g.npoints - p.bl_first;
+}
+
+#ifndef CB200_W4_LEANMETA
+#define CB200_W4_LEANMETA 1  // producers: division-free table lookup in the last stretch, window thresholds kept in registers
+#endif
+#ifndef CB200_W4_OCTSKIP
+#define CB200_W4_OCTSKIP 0   // consumers: inside a batch of KB octets, an octet with no active lane in the warp loads nothing
+#endif
+
+// lin_locate_desc for the Bessel abscissae, with a fast path for the last stretch.  The index is the truncation of the
+// true IEEE quotient (x - lo) / step (camb/utils.F90:81-111).  t = (x - lo) * (1/step) differs from that quotient by a few
+// ulp (< 1e-11 for t < 2e4), so the two truncations agree unless t lies within 1e-7 of an integer - only then is the
+// division carried out.  Everything else (x0, x1 rebuilt without FMA) is lin_locate_desc's arithmetic.
+__device__ __forceinline__ int w4_locate(const Proj4Params& p, double v, double& x0, double& x1, double& inv_h) {
+  if (v < p.bl_hi && v >= p.bl_lo) {
+    const double d = __dsub_rn(v, p.bl_lo);
+    const double t = __dmul_rn(d, p.bl_inv);
+    int j = (int)t;
+    const double fr = __dsub_rn(t, (double)j);
+    if (fr < 1e-7 || fr > 1 - 1e-7) j = (int)(__ddiv_rn(d, p.bl_step));
+    x0 = __dadd_rn(p.bl_lo, __dmul_rn(p.bl_step, (double)j));
+    x1 = (j + 1 < p.bl_nseg) ? __dadd_rn(p.bl_lo, __dmul_rn(p.bl_step, (double)(j + 1))) : p.bl_hi;
+    inv_h = p.bl_inv;
+    return p.bl_first + j;
+  }
+  return lin_locate_desc(p.bseg, v, x0, x1, inv_h);
+}
 
 #ifndef CB200_W4_KB
 #define CB200_W4_KB 2   // octets per batch of loads in flight (time-split consumers: 1: 136.3 us/point, 2: 132.8, 3: 137.3, 4: 145.6)
 #endif
 #ifndef CB200_W4_UNSAFE_NORINGWAIT
 #define CB200_W4_UNSAFE_NORINGWAIT 0  // timing experiment only: WRONG results
+#endif
+#ifndef CB200_W4_PBAL
+#define CB200_W4_PBAL 0   // 1: every producer warp (the ring warp too) computes the metadata of ONE time sample of the slab
+#endif
+constexpr bool W4_PBAL = CB200_W4_PBAL != 0;
+static_assert(!W4_PBAL || (W4_S == W4_NPW && W4_QC <= 32 && W4_MG == 1 && W4_MS == 1), "balanced producers: one time sample per producer warp");
+#ifndef CB200_W4_UNSAFE_FREEMETA
+#define CB200_W4_UNSAFE_FREEMETA 0    // timing experiment only: WRONG results
+#endif
+#ifndef CB200_W4_UNSAFE_ABLATE
+#define CB200_W4_UNSAFE_ABLATE 0      // timing experiments only: WRONG results
 #endif
 #ifndef CB200_W4_PREDLOAD
 #define CB200_W4_PREDLOAD 0
@@ -116,6 +167,9 @@ struct Proj4Params {
 #define CB200_W4_TSPLIT 1  // 1: the two consumer warps of a wavenumber group split the slab's time samples, not the octets
 #endif
 constexpr bool W4_TS = CB200_W4_TSPLIT != 0;
+constexpr bool W4_OS = CB200_W4_OSPLIT != 0;      // octet parity split on top of the time split
+constexpr bool W4_OSPL = W4_OS || !W4_TS;         // a consumer lane holds every second octet
+static_assert(!W4_OS || W4_TS, "the octet-parity split is defined on top of the time split");
 #ifndef CB200_W4_UNROLL
 #define CB200_W4_UNROLL 1
 #endif
@@ -195,10 +249,13 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   // (k -> 2 k + lh).  K2 = octets that need the lensing-potential accumulator: for a scalar run every multipole above
   // 400 takes the Limber value in the epilogue (cmbmain.f90:1546-1556), so the host passes KLIM < LK when all octets
   // >= KLIM lie above 400 (88-multipole set: KLIM = 6) and their third accumulator is never formed.
-  constexpr int LKH = W4_TS ? LK : (LK + 1) / 2;
-  constexpr int K2 = W4_TS ? KLIM : LKH;
+  // W4_OS: both at once - 4 warps per wavenumber group, each with half of the time samples and the octets of one parity
+  // (more warps with fewer accumulators each: the loop is latency-bound, not bandwidth-bound).
+  constexpr int LKH = W4_OSPL ? (LK + 1) / 2 : LK;
+  constexpr int K2 = !W4_TS ? LKH : (!W4_OS ? KLIM : (KLIM == LK ? LKH : KLIM / 2));
   static_assert(W4_TS || KLIM == LK, "the Limber cut of the accumulators needs the time-split consumers");
-#define W4_OCT(k) (W4_TS ? (k) : 2 * (k) + lh)
+  static_assert(!W4_OS || KLIM == LK || KLIM % 2 == 0, "octet-parity split: the Limber cut must fall on an even octet");
+#define W4_OCT(k) (W4_OSPL ? 2 * (k) + op : (k))
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int R = p.R;
   constexpr int rb = LK * 128;  // ring row stride in bytes
@@ -222,6 +279,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   const bool consumer = warp < NCW;
   const int qr = lane >> 3, li = lane & 7;   // quarter-warp = wavenumber slot ; octet position
   const int wg = warp % NQG, lh = (warp / NQG) & 1;  // consumer: wavenumber group, half (time samples or octets)
+  const int op = W4_OS ? (warp / (2 * NQG)) & 1 : (W4_TS ? 0 : lh);  // octet parity of this warp (when octets are split)
 
   const int nt = v.n_tau[pt], nk = v.n_k[pt];
   const double tau0 = v.thermo[(size_t)pt * 5];
@@ -410,12 +468,14 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     // The two roles only meet the consumers (full / empty barriers), never each other: the metadata runs ahead as far
     // as the NST buffers allow even while the ring warp waits for room.
     const bool ring_warp = (warp == NCW);
-    const int m_tid = tid - 32 * (NCW + 1);          // metadata thread index
-    const int m_grp = ring_warp ? 0 : min(m_tid / (32 * W4_MW), W4_MG);  // == MG: spare warp (exits)
+    // W4_PBAL: producer warp pw owns time sample pw of every slab (lane = wavenumber), the ring warp included: the
+    // metadata instructions are spread over the four SM sub-partitions instead of three
+    const int m_tid = W4_PBAL ? (warp - NCW) * QC + lane : tid - 32 * (NCW + 1);   // metadata thread index
+    const int m_grp = (ring_warp || W4_PBAL) ? 0 : min(m_tid / (32 * W4_MW), W4_MG);  // == MG: spare warp (exits)
     const int m_pair = m_tid - m_grp * 32 * W4_MW;   // pair of the slab owned by this (metadata) thread
-    const bool m_live = !ring_warp && m_pair < QC * W4_PNN;  // spare threads only take part in the barriers
+    const bool m_live = W4_PBAL ? lane < QC : (!ring_warp && m_pair < QC * W4_PNN);  // spare threads only take part in the barriers
     if (!ring_warp && m_grp >= W4_MG) return;
-    const int m_qi = m_live ? m_pair % QC : 0, m_nn = m_pair / QC;
+    const int m_qi = m_live ? m_pair % QC : 0, m_nn = W4_PBAL ? warp - NCW : m_pair / QC;
     const ProjQ3& pc = qc[m_qi];  // read from shared memory where needed: the producer runs on few registers
     const int pw1 = (pc.valid && m_live) ? max(s_q1[m_qi], 1) : 0x7fffffff;  // (ring warp: never valid)
     const int pw2 = pc.valid ? min(s_q2[m_qi], pc.steps) : 0;
@@ -438,7 +498,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         const int du = (u / PPT) * S + (u % PPT) * PNN;   // slab u / PPT of the iteration (compile-time constant)
         const int n = pf_n + du;
         f_valid[u] = (n >= pw1) && (n <= pw2);
-        if (f_valid[u]) {
+        if (f_valid[u] && !CB200_W4_UNSAFE_FREEMETA) {
           f_tau[u] = __ldg(tau + n - 1);
           f_dtau[u] = __ldg(dtau + n - 1);
           const unsigned char* Sp = pf_s + (size_t)du * ts_b;
@@ -482,40 +542,50 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     int rlo = 0x7fffffff;      // lowest resident row (identical in every producer thread by construction)
     int released = -1;         // slabs <= released have been released by every consumer warp
     int jlo[NU], jhi[NU];      // active multipole slots of this thread's pairs (both only ever move down)
-#pragma unroll
-    for (int u = 0; u < NU; u++) { jlo[u] = NJ; jhi[u] = NJ - 1; }
     const unsigned* wrow = s_wtab + m_qi * NJP;
+    // thresholds of the next moves: n2 of slot jhi, n1 of slot jlo - 1 (reloaded only when the slot moves)
+    int w_hi[NU], w_lo[NU];
+#pragma unroll
+    for (int u = 0; u < NU; u++) {
+      jlo[u] = NJ; jhi[u] = NJ - 1;
+      w_hi[u] = (int)(wrow[NJ - 1] >> 16); w_lo[u] = (int)(wrow[NJ - 1] & 0xffffu);
+    }
     const float rinvR = 1.0f / (float)R;
-    if (ring_warp) {
+    // ring duty for slab t (ring warp): wait until the rows of slab t may overwrite their slots, then fetch them
+    auto ring_step = [&](int t, bool wait_own) {
+      const int par = t % W4_NST;
+      // the barrier phase of slab t - NST must be over before anything is signalled on it again
+      if (t >= W4_NST) {
+        if (wait_own) mbar_wait(s_bar + W4_NST + par, ((t - W4_NST) / W4_NST) & 1);
+        released = max(released, t - W4_NST);
+      }
+      CK4(ck_c);
+      const int2 w = s_win[t];
+      // The windows slide towards lower rows (x falls with tau).  Rows [w.x, ...] may overwrite ring slots only
+      // if the highest row still needed by the oldest slab not yet released stays within R rows of w.x.
+      while (released + 1 < t && s_win[released + 1].y - w.x + 1 > R) {
+        const int r = released + 1;
+        mbar_wait(s_bar + W4_NST + (r % W4_NST), (r / W4_NST) & 1);
+        released = r;
+        if (COUNT && p.ring_stats && lane == 0) st_late++;
+      }
+      CK4(ck_c);
+      const int f_hi = (rlo <= w.y) ? rlo - 1 : w.y;  // rows >= rlo are resident (fetched for earlier slabs)
+      if (w.x <= f_hi) fetch_rows(w.x, f_hi, s_bar + par);
+      rlo = min(rlo, w.x);
+      if (COUNT && p.ring_stats && lane == 0) st_slabs++;
+      CK4(ck_b);
+    };
+    if (ring_warp && !W4_PBAL) {
       for (int t = 0; t < nslab; t++) {
-        const int par = t % W4_NST;
-        // the barrier phase of slab t - NST must be over before anything is signalled on it again
-        if (t >= W4_NST) {
-          mbar_wait(s_bar + W4_NST + par, ((t - W4_NST) / W4_NST) & 1);
-          released = max(released, t - W4_NST);
-        }
-        CK4(ck_c);
-        const int2 w = s_win[t];
-        // The windows slide towards lower rows (x falls with tau).  Rows [w.x, ...] may overwrite ring slots only
-        // if the highest row still needed by the oldest slab not yet released stays within R rows of w.x.
-        while (released + 1 < t && s_win[released + 1].y - w.x + 1 > R) {
-          const int r = released + 1;
-          mbar_wait(s_bar + W4_NST + (r % W4_NST), (r / W4_NST) & 1);
-          released = r;
-          if (COUNT && p.ring_stats && lane == 0) st_late++;
-        }
-        CK4(ck_c);
-        const int f_hi = (rlo <= w.y) ? rlo - 1 : w.y;  // rows >= rlo are resident (fetched for earlier slabs)
-        if (w.x <= f_hi) fetch_rows(w.x, f_hi, s_bar + par);
-        rlo = min(rlo, w.x);
-        if (COUNT && p.ring_stats && lane == 0) st_slabs++;
-        CK4(ck_b);
-        mbar_arrive(s_bar + par);
+        ring_step(t, true);
+        mbar_arrive(s_bar + (t % W4_NST));
       }
     }
-    if (!ring_warp && m_grp * MS < nslab) prefetch();
+    const bool m_role = W4_PBAL || !ring_warp;   // this warp computes metadata
+    if (m_role && m_grp * MS < nslab) prefetch();
     CK4(ck_a);
-    for (int t = m_grp * MS; !ring_warp && t < nslab; t += W4_MG * MS) {
+    for (int t = m_grp * MS; m_role && t < nslab; t += W4_MG * MS) {
       // metadata buffers are free once the consumers have released the slabs that used them NST slabs ago
 #pragma unroll
       for (int us = 0; us < MS; us++) {
@@ -523,6 +593,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         if (tu < nslab && tu >= W4_NST) mbar_wait(s_bar + W4_NST + (tu % W4_NST), ((tu - W4_NST) / W4_NST) & 1);
       }
       CK4(ck_c);
+      if (W4_PBAL && ring_warp) ring_step(t, false);
       // ---- metadata of this thread's pairs ----
 #pragma unroll
       for (int u = 0; u < NU; u++) {
@@ -537,12 +608,30 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         int moff = 0, jr = 127;
         double ma = 0, mfac = 0, ms0 = 0, ms1 = 0, ms2 = 0;
         // slots still inside their window at time sample n: n2 >= n from above, n1 <= n from below
+#if CB200_W4_LEANMETA
+        while (jhi[u] >= 0 && w_hi[u] < n) { jhi[u]--; w_hi[u] = (int)(wrow[max(jhi[u], 0)] >> 16); }
+        while (jlo[u] > 0 && w_lo[u] <= n) { jlo[u]--; w_lo[u] = (int)(wrow[max(jlo[u] - 1, 0)] & 0xffffu); }
+#else
         while (jhi[u] >= 0 && (int)(wrow[jhi[u]] >> 16) < n) jhi[u]--;
         while (jlo[u] > 0 && (int)(wrow[jlo[u] - 1] & 0xffffu) <= n) jlo[u]--;
+#endif
+#if CB200_W4_UNSAFE_FREEMETA
+        if (f_valid[u]) {  // timing experiment only (WRONG results): the consumers' floor with metadata that costs nothing
+          ma = 0.5; mfac = 0.01; ms0 = ms1 = ms2 = 1.0;
+          moff = ((n * 7 + m_qi * 3) % R) * rb;
+          if (jlo[u] <= jhi[u]) jr = jlo[u] | ((jhi[u] + 1) << 8);
+        }
+        if (false) {
+#else
         if (f_valid[u]) {
+#endif
           const double x = fabs(__dmul_rn(pc.q, __dsub_rn(tau0, f_tau[u])));
           double x0, x1, inv_h;
+#if CB200_W4_LEANMETA
+          int bi = w4_locate(p, x, x0, x1, inv_h);
+#else
           int bi = lin_locate_desc(p.bseg, x, x0, x1, inv_h);
+#endif
           if (bi > p.num_xx - 1) { bi = p.num_xx - 1; x0 = p.bx[bi - 1]; x1 = p.bx[bi]; inv_h = 1.0 / (x1 - x0); }
           // interpolation weights (values, not indices): reciprocal multiplies instead of the reference's divisions
           const double fac = x1 - x0;
@@ -595,9 +684,9 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   for (int k = 0; k < LKH; k++) acc[k][0] = acc[k][1] = 0.0;
 #pragma unroll
   for (int k = 0; k < K2; k++) acc2[k] = 0.0;
-  const unsigned ring_lane = smem_u32(ring) + li * 16 + (W4_TS ? 0 : lh * 128);  // shared-space address
-  const int lc = li + (W4_TS ? 0 : 8 * lh);
-  constexpr int OSH = W4_TS ? 3 : 4, ORND = W4_TS ? 7 : 15, OSTR = W4_TS ? 128 : 256;  // l-slot stride 8 or 16 per k
+  const unsigned ring_lane = smem_u32(ring) + li * 16 + (W4_OSPL ? op * 128 : 0);  // shared-space address
+  const int lc = li + (W4_OSPL ? 8 * op : 0);
+  constexpr int OSH = W4_OSPL ? 4 : 3, ORND = W4_OSPL ? 15 : 7, OSTR = W4_OSPL ? 256 : 128;  // l-slot stride 16 or 8 per k
   CK4(ck_a);
   for (int t = 0; t < nslab; t++) {
     const int par = t % W4_NST;
@@ -649,18 +738,21 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
       {
         unsigned rp = ring_lane + rec.off;
         const unsigned U = __reduce_or_sync(0xffffffffu, m);  // octets with an active lane anywhere in the warp
-#pragma unroll
-        for (int k0 = 0; k0 < LKH; k0 += KB) {
-          if (!(U & (((1u << KB) - 1u) << k0))) continue;  // warp-uniform: no loads, no FP64 issue
+        // octets [kf, kf + cnt) of a batch: loads first (in flight together), then the arithmetic
+        auto octets = [&](const int kf, const int cnt) {
           double2 N0[KB], N1[KB];
 #pragma unroll
           for (int kk = 0; kk < KB; kk++) {
-            const int k = k0 + kk;
-            if (k < LKH) {
+            const int k = kf + kk;
+            if (kk < cnt && k < LKH) {
               const bool act = (m >> k) & 1u;
 #if CB200_W4_PREDLOAD
               N0[kk] = lds128_if(rp + k * OSTR, act);
               N1[kk] = lds128_if(rp + k * OSTR + rb, act);
+#elif CB200_W4_UNSAFE_ABLATE == 1   // timing experiment only (WRONG results): no table loads
+              (void)act;
+              N0[kk] = make_double2(a2, g0);
+              N1[kk] = make_double2(b2, g1);
 #else
               (void)act;
               N0[kk] = lds128(rp + k * OSTR);
@@ -670,16 +762,39 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
           }
 #pragma unroll
           for (int kk = 0; kk < KB; kk++) {
-            const int k = k0 + kk;
-            if (k < LKH) {
+            const int k = kf + kk;
+            if (kk < cnt && k < LKH) {
               const bool act = (m >> k) & 1u;
+#if CB200_W4_UNSAFE_ABLATE == 2     // timing experiment only (WRONG results): loads kept, one FP64 add per load instead of 7 FMAs
+              (void)act;
+              acc[k][0] += N0[kk].x + N1[kk].y;
+              acc[k][1] += N0[kk].y + N1[kk].x;
+#else
               double Jv = fma(g1, N1[kk].y, fma(g0, N0[kk].y, fma(b2, N1[kk].x, a2 * N0[kk].x)));
               Jv = act ? Jv : 0.0;
               acc[k][0] = fma(s01.x, Jv, acc[k][0]);
               acc[k][1] = fma(s01.y, Jv, acc[k][1]);
-              if (k < K2) acc2[k] = fma(rec.s2, Jv, acc2[k]);
+              if (k < K2) acc2[k < K2 ? k : 0] = fma(rec.s2, Jv, acc2[k < K2 ? k : 0]);
+#endif
             }
           }
+        };
+#pragma unroll
+        for (int k0 = 0; k0 < LKH; k0 += KB) {
+          const unsigned ub = (U >> k0) & ((1u << KB) - 1u);
+          if (!ub) continue;  // warp-uniform: no loads, no FP64 issue
+#if CB200_W4_OCTSKIP
+          if (KB == 2 && k0 + 1 < LKH) {
+            // a run of active multipoles ends inside half of the batches it touches: the idle octet loads nothing
+            if (ub == 3u) octets(k0, 2);
+            else if (ub == 1u) octets(k0, 1);
+            else octets(k0 + 1, 1);
+          } else {
+            octets(k0, KB);
+          }
+#else
+          octets(k0, KB);
+#endif
         }
       }
     }
@@ -713,6 +828,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   const int tid = (int)e_tid, lane = tid & 31, warp = tid >> 5;
   const int lp = (int)e_by, pt = p.p0 + lp, qb = (int)e_bx, q0 = qb * QC;
   const int qr = lane >> 3, li = lane & 7, wg = warp % NQG, lh = (warp / NQG) & 1;
+  const int op = W4_OS ? (warp / (2 * NQG)) & 1 : (W4_TS ? 0 : lh);
   const double tau0 = v.thermo[(size_t)pt * 5];
   const double* tau = v.tau + (size_t)pt * v.NT;
   const LinSegs& tseg = v.tseg[pt];
@@ -729,8 +845,9 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     // the two time halves of a wavenumber group meet: each hands the sums of the octets the OTHER half finishes over
     // through the (now free) ring, so the epilogue (Limber values, partial k-contraction) is shared between them
     constexpr int NE = 3 * LKH;
-    static_assert((size_t)NQG * 6 * PROJ_LP * 8 <= 32 * 1024 && 32 * 1024 + (size_t)NQG * NE * 32 * 8 <= 128 * 1024, "epilogue scratch inside the ring");
-    double* xs = reinterpret_cast<double*>(smem_raw + 32 * 1024) + (size_t)wg * NE * 32 + lane;  // [wg][entry][lane]
+    constexpr int NGX = NQG * (W4_OS ? 2 : 1);  // warp pairs that exchange sums
+    static_assert((size_t)NQG * 6 * PROJ_LP * 8 <= 32 * 1024 && 32 * 1024 + (size_t)NGX * NE * 32 * 8 <= 128 * 1024, "epilogue scratch inside the ring");
+    double* xs = reinterpret_cast<double*>(smem_raw + 32 * 1024) + (size_t)(W4_OS ? 2 * wg + op : wg) * NE * 32 + lane;  // [pair][entry][lane]
 #pragma unroll
     for (int k = 0; k < LKH; k++) {
       if ((k < KS) == (lh == 1)) {   // not mine to finish

@@ -20,12 +20,20 @@
     implicit none
     private
 
-    !-- mirror of cb200_config (include/cosmob200.h)
+    !-- mirror of cb200_config (include/cosmob200.h:25-48).  The C layout this type must reproduce is stated here and
+    !   checked WITHOUT a Fortran compiler by tests/test_abi_layout.py (gcc _Static_assert on the header against these
+    !   numbers, and a field-by-field comparison of this declaration with the header):
+    !   ABI-LAYOUT sizeof=96 struct_size=0 device=4 lmax_computed_cl=8 cmb_lensing=12 use_lensing_potential=16
+    !   ABI-LAYOUT use_nonlinear_lensing=20 compute_tensors=24 lmax_tensor=28 accurate_bb=32 k_eta_max_scalar=40
+    !   ABI-LAYOUT accuracy_level=48 lmax_out=56 highl_norm_first_call=60 max_points=64 chunk_points=68 n_tau_max=72
+    !   ABI-LAYOUT n_k_max=76 n_q_max=80 n_tau_max_tensor=84 n_k_max_tensor=88 n_q_max_tensor=92
+    !   cb200_default_config writes struct_size = 96; cb200_create returns -3 for any other value.
     type, bind(C) :: cb200_config
-        integer(c_int) :: device, lmax_computed_cl, cmb_lensing, use_lensing_potential, use_nonlinear_lensing
+        integer(c_int) :: struct_size, device, lmax_computed_cl, cmb_lensing, use_lensing_potential, use_nonlinear_lensing
         integer(c_int) :: compute_tensors, lmax_tensor, accurate_bb
         real(c_double) :: k_eta_max_scalar, accuracy_level
         integer(c_int) :: lmax_out, highl_norm_first_call, max_points, chunk_points, n_tau_max, n_k_max, n_q_max
+        integer(c_int) :: n_tau_max_tensor, n_k_max_tensor, n_q_max_tensor
     end type cb200_config
 
     interface

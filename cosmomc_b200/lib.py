@@ -13,6 +13,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CB200_LIB", os.path.join(_HERE, "libcosmob200.so"))  # CB200_LIB: dev override for kernel-tuning builds
+# the same sources plus the superseded projection kernels 1 and 2 (cross-checks of the parity tests; never the product)
+TEST_LIB_PATH = os.path.join(_HERE, "libcosmob200_test.so")
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
@@ -24,14 +26,15 @@ EXPORTS = [
     "cb200_make_source_k", "cb200_grid_build", "cb200_get_bessel_table", "cb200_upload_sources", "cb200_powers",
     "cb200_debug_fetch", "cb200_keep_transfers", "cb200_like_add_pliklite", "cb200_like_add_cmblikes",
     "cb200_loglike_batch", "cb200_loglike_cls", "cb200_get_timing", "cb200_sync", "cb200_set_option",
-    "cb200_timer_start", "cb200_timer_stop", "cb200_measure_fp64_peaks",
+    "cb200_timer_start", "cb200_timer_stop", "cb200_measure_fp64_peaks", "cb200_config_size", "cb200_abi_version",
+    "cb200_upload_sources_packed",
     "cb200_powers_shared", "cb200_like_set_bk_foregrounds", "cb200_background", "cb200_set_background", "cb200_like_add_bao", "cb200_like_add_hst", "cb200_like_add_sn",
     "cb200_eval_batch", "cb200_test_like_batch",
 ]
 
 
 class Config(C.Structure):
-    _fields_ = [("device", C.c_int), ("lmax_computed_cl", C.c_int), ("cmb_lensing", C.c_int),
+    _fields_ = [("struct_size", C.c_int), ("device", C.c_int), ("lmax_computed_cl", C.c_int), ("cmb_lensing", C.c_int),
                 ("use_lensing_potential", C.c_int), ("use_nonlinear_lensing", C.c_int), ("compute_tensors", C.c_int),
                 ("lmax_tensor", C.c_int), ("accurate_bb", C.c_int), ("k_eta_max_scalar", C.c_double),
                 ("accuracy_level", C.c_double), ("lmax_out", C.c_int), ("highl_norm_first_call", C.c_int),
@@ -73,15 +76,19 @@ class Timing(C.Structure):
 _lib = None
 
 
-def load():
+_libs = {}
+
+
+def load(path=None):
     """Load the shared library; raises with a clear message if it has not been built."""
     global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
         raise RuntimeError("cosmomc_b200: %s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
-                           "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+                           "(nvcc, sm_100a). There is no CPU fallback." % path)
+    L = C.CDLL(path)
     L.cb200_last_error.restype = C.c_char_p
     L.cb200_last_error.argtypes = [C.c_void_p]
     L.cb200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
@@ -99,6 +106,7 @@ def load():
     L.cb200_grid_build.argtypes = [C.c_int, c_dp, C.c_int, c_dp, c_dp, c_ip, C.c_int, c_dp, c_ip]
     L.cb200_get_bessel_table.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_dp]
     L.cb200_upload_sources.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_dp, C.c_void_p, C.c_int]
+    L.cb200_upload_sources_packed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_ip, c_dp, C.c_void_p]
     L.cb200_powers.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip]
     L.cb200_powers_shared.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip]
     L.cb200_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_ip]
@@ -127,7 +135,9 @@ def load():
                                     c_ip]
     L.cb200_eval_batch.argtypes = [C.c_void_p, C.POINTER(ParamLayout), C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_ip]
     L.cb200_test_like_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp]
-    _lib = L
+    _libs[path] = L
+    if path == LIB_PATH:
+        _lib = L
     return L
 
 
@@ -169,9 +179,12 @@ def grid_build(ops, query=None, max_n=200000):
 class Handle:
     """Owns one cb200_handle (device tables, resident sources, likelihood data)."""
 
-    def __init__(self, **kw):
-        L = load()
+    def __init__(self, lib_path=None, **kw):
+        L = load(lib_path)
         self.L = L
+        if L.cb200_config_size() != C.sizeof(Config):
+            raise CB200Error("ctypes mirror of cb200_config (%d bytes) is out of step with the library (%d bytes)"
+                             % (C.sizeof(Config), L.cb200_config_size()))
         cfg = Config()
         L.cb200_default_config(C.byref(cfg))
         for k, v in kw.items():
@@ -268,6 +281,22 @@ class Handle:
         self._check(self.L.cb200_upload_sources(self.h, kind, first, npts, _pd(thermo), _pi(n_k), _pd(k), ptr, isdev),
                     "upload_sources")
 
+    def upload_sources_packed(self, thermo, n_tau, n_k, k, src_packed=None, first=0, kind=0, src_host_ptr=None):
+        """cb200_upload_sources_packed: point i's sources are [n_tau[i]][3][n_k[i]], back to back, no padding.
+        `src_packed`: 1-D float64 array, or `src_host_ptr`: address of a caller-owned (pinned) buffer."""
+        thermo = _d(thermo).reshape(-1, 5)
+        npts = len(thermo)
+        n_tau, n_k, k = _i(n_tau), _i(n_k), _d(k)
+        if src_host_ptr is not None:
+            ptr = C.c_void_p(src_host_ptr)
+        else:
+            src_packed = _d(src_packed).reshape(-1)
+            assert src_packed.size == int((n_tau.astype(np.int64) * 3 * n_k).sum()), "packed size"
+            self._keep = src_packed
+            ptr = C.c_void_p(src_packed.ctypes.data)
+        self._check(self.L.cb200_upload_sources_packed(self.h, kind, first, npts, _pd(thermo), _pi(n_tau), _pi(n_k),
+                                                       _pd(k), ptr), "upload_sources_packed")
+
     def powers(self, initpower, alens=None, aphiphi=None, first=0, want_cls=True, want_derived=True):
         ip = _d(initpower).reshape(-1, 10)
         npts = len(ip)
@@ -300,6 +329,16 @@ class Handle:
         al = _d(alens) if alens is not None else None
         ap = _d(aphiphi) if aphiphi is not None else None
         self._check(self.L.cb200_powers(self.h, first, len(ip), _pd(ip), _pd(al), _pd(ap), None, None, None), "powers")
+
+    def powers_into(self, initpower, alens=None, aphiphi=None, first=0, cls_ptr=None, derived_ptr=None, status_ptr=None):
+        """cb200_powers with caller-owned (e.g. pinned) host output buffers given as raw addresses."""
+        ip = _d(initpower).reshape(-1, 10)
+        al = _d(alens) if alens is not None else None
+        ap = _d(aphiphi) if aphiphi is not None else None
+        self._check(self.L.cb200_powers(self.h, first, len(ip), _pd(ip), _pd(al), _pd(ap),
+                                        C.cast(C.c_void_p(cls_ptr), c_dp) if cls_ptr else None,
+                                        C.cast(C.c_void_p(derived_ptr), c_dp) if derived_ptr else None,
+                                        C.cast(C.c_void_p(status_ptr), c_ip) if status_ptr else None), "powers")
 
     def keep_transfers(self, on=True):
         self.L.cb200_keep_transfers(self.h, int(on))

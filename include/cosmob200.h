@@ -16,13 +16,16 @@
 extern "C" {
 #endif
 
-#define CB200_VERSION 1
+#define CB200_VERSION 2
 #define CB200_LOGZERO 1e30 /* source/settings.f90:114 */
 
 typedef struct cb200_handle cb200_handle;
 
 /* Mirrors what CAMBCalc_InitCAMBParams derives from CosmoSettings (source/Calculator_CAMB.f90:729-836). */
 typedef struct cb200_config {
+  int struct_size;           /* sizeof(cb200_config) as the CALLER's binding lays it out; set by cb200_default_config.
+                                cb200_create refuses a value other than its own sizeof (a Fortran / ctypes mirror that
+                                fell out of step with this header fails loudly instead of reading garbage) */
   int device;                /* CUDA device ordinal */
   int lmax_computed_cl;      /* CosmoSettings%lmax_computed_cl (batch3: 2500) */
   int cmb_lensing;           /* CosmoSettings%CMB_Lensing */
@@ -56,6 +59,9 @@ typedef struct cb200_info {
 } cb200_info;
 
 void cb200_default_config(cb200_config* cfg);
+/* sizeof(cb200_config) / CB200_VERSION of the loaded library, for bindings that want to check before anything else */
+int cb200_config_size(void);
+int cb200_abi_version(void);
 int cb200_create(const cb200_config* cfg, cb200_handle** out);
 void cb200_destroy(cb200_handle* h);
 const char* cb200_last_error(const cb200_handle* h);
@@ -94,6 +100,13 @@ int cb200_get_bessel_table(const cb200_handle* h, int kind, double* x, double* a
  * src_is_device != 0: `src` is a device pointer (used by the HBM-resident benchmark leg). */
 int cb200_upload_sources(cb200_handle* h, int kind, int first, int npts, const double* thermo, const int* n_k,
                          const double* k, const double* src, int src_is_device);
+/* Same hand-off with the sources PACKED at their exact sizes, the way CAMB holds them: point i contributes
+ * Src(1:n_k[i], 1:3, 1:n_tau[i]) (= C [n_tau][3][n_k]) back to back in src_packed, no padding (7 % fewer bytes over
+ * PCIe than the padded form at the batch3 sizes, and no padding copy on the Fortran side).  n_tau[i] must equal the
+ * number of time steps the library derives from thermo[i] (checked; camb/modules.f90:2994-3027).  A device kernel
+ * scatters the block into the resident padded layout. */
+int cb200_upload_sources_packed(cb200_handle* h, int kind, int first, int npts, const double* thermo, const int* n_tau,
+                                const int* n_k, const double* k, const double* src_packed);
 
 /* ---- calculator: semi-slow step -------------------------------------------------------------------------
  * Replaces CAMBCalc_GetNewPowerData (source/Calculator_CAMB.f90:220-275): k-contraction, l-interpolation,

@@ -234,6 +234,7 @@ int orc_lens_cls(int nl, const int* ls, int Max_l, const double* cl_scalar, cons
 }  // extern "C"
 
 #include "orc_like_api.inc"
+#include "orc_batch.inc"
 
 extern "C" {
 // ---- background (orc_bg.hpp): bg[16] layout documented there.  DA, H [nz]; extras[3] = tau0, age/Gyr, CosmomcTheta

@@ -24,19 +24,50 @@ def build(force=False):
     return so
 
 
+def _declare(L):
+    L.orc_bessel_create.restype = C.c_void_p
+    L.orc_bessel_destroy.argtypes = [C.c_void_p]
+    L.orc_bessel_numxx.argtypes = [C.c_void_p]
+    L.orc_bessel_get.argtypes = [C.c_void_p, c_dp, c_dp, c_dp]
+    L.orc_project.restype = C.c_longlong
+    L.orc_quadform.restype = C.c_double
+    L.orc_pliklite.restype = C.c_double
+    L.orc_cmblikes_chisq.restype = C.c_double
+    return L
+
+
+_FAST = None
+
+
+def fast_lib():
+    """Timing build of the same sources (-O3 -march=native -fopenmp) for bench.py's CPU baseline.
+    Rebuilt whenever the host CPU differs from the one it was built on (-march=native is host-specific)."""
+    global _FAST
+    if _FAST is None:
+        so = os.path.join(_HERE, "liborc_fast.so")
+        tag = os.path.join(_HERE, "liborc_fast.cpu")
+        try:
+            with open("/proc/cpuinfo") as f:
+                cpu = "".join(l for l in f if l.startswith(("model name", "flags")))[:8192]
+            import hashlib
+            cpu = hashlib.sha1(cpu.encode()).hexdigest()
+        except OSError:
+            cpu = "unknown"
+        have = open(tag).read().strip() if os.path.exists(tag) else ""
+        srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp", ".inc"))]
+        if (have != cpu or not os.path.exists(so)
+                or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs)):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "fast"])
+            with open(tag, "w") as f:
+                f.write(cpu)
+        _FAST = _declare(C.CDLL(so))
+    return _FAST
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = C.CDLL(build())
-        L = _LIB
-        L.orc_bessel_create.restype = C.c_void_p
-        L.orc_bessel_destroy.argtypes = [C.c_void_p]
-        L.orc_bessel_numxx.argtypes = [C.c_void_p]
-        L.orc_bessel_get.argtypes = [C.c_void_p, c_dp, c_dp, c_dp]
-        L.orc_project.restype = C.c_longlong
-        L.orc_quadform.restype = C.c_double
-        L.orc_pliklite.restype = C.c_double
-        L.orc_cmblikes_chisq.restype = C.c_double
+        _LIB = _declare(C.CDLL(build()))
     return _LIB
 
 
@@ -171,6 +202,48 @@ def project(bessel, tau0, taurst, taurend, reion_start, reion_complete, maximum_
     if n < 0:
         raise RuntimeError("orc_project failed")
     return q[:n].copy(), dq[:n].copy(), Delta[:n].copy(), trip.value
+
+
+class BatchChain:
+    """Whole per-point chain (projection ... plik-lite-shaped chi^2) for a batch of points in ONE C call
+    (orc_eval_pliklite_batch); the CPU baseline of bench.py.  `fast` selects the -O3 -march=native timing build.
+    mode 0: points one after the other, OpenMP inside the point; mode 1: one point per thread."""
+
+    def __init__(self, ls, max_eta_k, Max_l, lmax_computed_cl, lmax_out, tmpl_unl, highl, data, fast=True,
+                 threads=None):
+        self.L = fast_lib() if fast else lib()
+        if threads:
+            self.L.orc_set_num_threads(int(threads))
+        self.threads = int(self.L.orc_num_threads())
+        self.ls = _i(ls)
+        self.args = (float(max_eta_k), int(Max_l), int(lmax_computed_cl), int(lmax_out))
+        self.tm, self.hl = _d(tmpl_unl), _d(highl)
+        self.data = {k: (_d(v) if k in ("weights", "invcov", "x_data") else _i(v)) for k, v in data.items()
+                     if k in ("nb", "blmin", "blmax", "weights", "invcov", "x_data")}
+        self.h = self.L.orc_bessel_create(len(self.ls), _p(self.ls), C.c_double(max_eta_k))
+        if not self.h:
+            raise RuntimeError("orc_bessel_create failed")
+
+    def run(self, batch, mode):
+        L, d = self.L, self.data
+        src = _d(batch["src"])
+        npts, NT, _, NK = src.shape
+        out = np.zeros(npts)
+        mek, Max_l, lcc, lmo = self.args
+        rc = L.orc_eval_pliklite_batch(
+            C.c_void_p(self.h), len(self.ls), _p(self.ls), Max_l, C.c_double(mek), lcc, lmo,
+            int(npts), int(NT), int(NK), _p(_d(batch["thermo"])), _p(_i(batch["n_tau"])), _p(_i(batch["n_k"])),
+            _p(_d(batch["k"])), _p(src), _p(_d(batch["initpower"])), _p(_d(batch["alens"])), _p(_d(batch["cal"])),
+            _p(self.tm), _p(self.hl), self.hl.shape[1], _p(d["nb"]), _p(d["blmin"]), _p(d["blmax"]),
+            _p(d["weights"]), _p(d["invcov"]), _p(d["x_data"]), int(mode), _p(out))
+        if rc != 0:
+            raise RuntimeError("orc_eval_pliklite_batch failed")
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.orc_bessel_destroy(C.c_void_p(self.h))
+            self.h = None
 
 
 def initpower_vec(As=2.1e-9, ns=0.96, nrun=0.0, nrunrun=0.0, r=0.0, nt=0.0, ntrun=0.0, pivot_k=0.05,

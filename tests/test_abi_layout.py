@@ -1,0 +1,97 @@
+"""The C ABI as its three bindings see it (no GPU, no Fortran compiler needed).
+
+* include/cosmob200.h is compiled with gcc and `_Static_assert`ed against the layout numbers that
+  cosmomc_b200/fortran/Calculator_B200.f90 states for its `bind(C)` mirror of cb200_config;
+* the field list of the Fortran `type, bind(C) :: cb200_config` is parsed and compared, name by name and kind by kind,
+  with the header's struct (a bind(C) derived type with the same component order and interoperable kinds has the C
+  layout: Fortran 2008 15.3.4);
+* the ctypes mirror (cosmomc_b200/lib.py) must have the same size and offsets;
+* every entry point the header declares is exported by libcosmob200.so, and cb200_create refuses a stale mirror.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import helpers as H
+
+HDR = os.path.join(H.ROOT, "include", "cosmob200.h")
+F90 = os.path.join(H.ROOT, "cosmomc_b200", "fortran", "Calculator_B200.f90")
+
+
+def header_fields():
+    src = open(HDR).read()
+    body = re.search(r"typedef struct cb200_config \{(.*?)\} cb200_config;", src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        kind, names = decl.split(None, 1)
+        out += [(n.strip(), kind) for n in names.split(",")]
+    return out
+
+
+def fortran_layout():
+    txt = open(F90).read()
+    nums = {}
+    for line in txt.splitlines():
+        if "ABI-LAYOUT" in line:
+            for k, v in re.findall(r"(\w+)=(\d+)", line.split("ABI-LAYOUT", 1)[1]):
+                nums[k] = int(v)
+    body = re.search(r"type, bind\(C\) :: cb200_config\n(.*?)end type cb200_config", txt, re.S).group(1)
+    fields = []
+    for line in body.splitlines():
+        m = re.match(r"\s*(integer\(c_int\)|real\(c_double\)) :: (.*)", line)
+        if m:
+            kind = "int" if "c_int" in m.group(1) else "double"
+            fields += [(n.strip(), kind) for n in m.group(2).split(",")]
+    return nums, fields
+
+
+def test_fortran_mirror_matches_header_fields():
+    nums, ffields = fortran_layout()
+    assert ffields == header_fields()
+
+
+def test_header_layout_static_asserts():
+    nums, _ = fortran_layout()
+    lines = ['#include <stddef.h>', '#include "cosmob200.h"',
+             '_Static_assert(sizeof(cb200_config) == %d, "sizeof");' % nums.pop("sizeof")]
+    assert {n for n, _ in header_fields()} == set(nums), "the Fortran comment must state every field's offset"
+    for name, off in nums.items():
+        lines.append('_Static_assert(offsetof(cb200_config, %s) == %d, "%s");' % (name, off, name))
+    lines.append("int main(void) { return 0; }")
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "abi.c")
+        open(c, "w").write("\n".join(lines) + "\n")
+        r = subprocess.run(["gcc", "-std=c11", "-I", os.path.dirname(HDR), "-c", c, "-o", os.path.join(d, "abi.o")],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_ctypes_mirror_and_exports():
+    from cosmomc_b200 import lib
+    nums, _ = fortran_layout()
+    assert C.sizeof(lib.Config) == nums["sizeof"]
+    for name, _ in header_fields():
+        assert getattr(lib.Config, name).offset == nums[name], name
+    L = lib.load()
+    assert L.cb200_config_size() == nums["sizeof"]
+    declared = set(re.findall(r"\b(cb200_\w+)\s*\(", re.sub(r"/\*.*?\*/", "", open(HDR).read(), flags=re.S)))
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(lib.EXPORTS) <= declared
+
+
+def test_create_refuses_a_stale_mirror():
+    from cosmomc_b200 import lib
+    L = lib.load()
+    cfg = lib.Config()
+    L.cb200_default_config(C.byref(cfg))
+    assert cfg.struct_size == C.sizeof(lib.Config)
+    cfg.struct_size -= 8  # what an out-of-date binding would pass
+    h = C.c_void_p()
+    assert L.cb200_create(C.byref(cfg), C.byref(h)) == -3 and not h

@@ -138,13 +138,15 @@ def test_triple_count_matches_oracle(setup):
     """The instrumented unit-of-work count is an integer artefact: identical in both kernels."""
     h, orc = setup["h"], setup["orc"]
     want = sum(o["triples"] for o in orc)
+    ht = test_kernel_handle(setup)
     for pk in (1, 2, 3, 4):
-        h.set_option("proj_kernel", pk)
-        h.set_option("count_triples", 1)
-        h.timing(reset=True)
-        h.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
-        t = h.timing()
-        h.set_option("count_triples", 0)
+        hh = h if pk >= 3 else ht   # kernels 1 and 2 only exist in the test library
+        hh.set_option("proj_kernel", pk)
+        hh.set_option("count_triples", 1)
+        hh.timing(reset=True)
+        hh.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
+        t = hh.timing()
+        hh.set_option("count_triples", 0)
         assert t["proj_triples"] == want, (pk, t["proj_triples"], want)
     # kernel 4 ships the active multipoles of a (q, tau) pair as ONE run of l-slots; with "ring_stats" on it
     # re-derives every lane's mask from the exact integration windows and counts the differences
@@ -157,12 +159,39 @@ def test_triple_count_matches_oracle(setup):
     assert t["ring_slabs"] > 0 and t["proj_mask_mismatch"] == 0, t
 
 
+def test_kernel_handle(setup):
+    """A handle of libcosmob200_test.so (product sources + the superseded projection kernels 1 and 2) holding the same
+    batch; built once per module."""
+    if "h_test" not in setup:
+        from cosmomc_b200 import lib
+        b, T = setup["batch"], setup["T"]
+        ht = lib.Handle(lib_path=lib.TEST_LIB_PATH, max_points=8, chunk_points=2, lmax_out=H.LMAX_OUT)
+        ht.set_templates(T["highl_unlensed"], T["highl_lensed"])
+        ht.upload_sources(b["thermo"], b["n_k"], b["k"], b["src"])
+        setup["h_test"] = ht
+    return setup["h_test"]
+
+
+test_kernel_handle.__test__ = False
+
+
+def test_product_library_has_no_test_kernels(setup):
+    """Kernels 1 and 2 are cross-checks, not product: libcosmob200.so refuses them."""
+    from cosmomc_b200 import lib
+    h = setup["h"]
+    h.set_option("proj_kernel", 1)
+    with pytest.raises(lib.CB200Error):
+        h.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
+    h.set_option("proj_kernel", 4)
+
+
 @pytest.mark.parametrize("pk", [1, 2, 3])
 def test_earlier_projection_kernels_agree(setup, pk):
-    """The earlier projection kernels (1: direct L2 gathers, 2: windowed warp-per-pair, 3: quarter-warp pairs per
-    32-multipole chunk - also the fallback pass of the default) stay as cross-checks of the default (4: all multipoles
-    per quarter-warp, producer/consumer warps, TMA-filled ring on mbarriers)."""
-    h, orc = setup["h"], setup["orc"]
+    """The earlier projection kernels (1: direct L2 gathers, 2: windowed warp-per-pair - both only built into
+    libcosmob200_test.so -, 3: quarter-warp pairs per 32-multipole chunk - the fallback pass of the default) stay as
+    cross-checks of the default (4: all multipoles per quarter-warp, producer/consumer warps, TMA-filled ring on
+    mbarriers)."""
+    h, orc = (setup["h"] if pk >= 3 else test_kernel_handle(setup)), setup["orc"]
     h.set_option("proj_kernel", pk)
     cls, derived, status = h.powers(setup["batch"]["initpower"], setup["batch"]["alens"])
     h.set_option("proj_kernel", 4)
@@ -174,12 +203,13 @@ def test_earlier_projection_kernels_agree(setup, pk):
 
 
 def test_pliklite_loglike(setup):
-    """plik-lite-shaped chi^2 (synthetic data set): |Delta lnL| < 1e-7 (north_star: 0.01)."""
+    """plik-lite-shaped chi^2 (synthetic data set).  The data vector is the binned MEAN C_l of the
+    batch's own points (oracle) plus covariance noise, so -lnL is O(10^2..10^4) as in a real chain, and the check is the
+    north_star's ABSOLUTE one: |Delta lnL| < 0.01 - demanded here at 1e-5 absolute."""
     import pyoracle as o
     from cosmomc_b200 import lib, synthetic as syn
     T = setup["T"]
-    fid = np.zeros((5, H.LMAX_OUT + 1))
-    fid[0], fid[1], fid[2] = T["theory_cl"][:, 0], T["theory_cl"][:, 1], T["theory_cl"][:, 2]
+    fid = np.mean([setup["orc"][i]["cls_out"] for i in range(NPTS)], axis=0)
     data = syn.synthetic_pliklite(H.LMAX_OUT, fiducial_cls=fid)
     h = setup["h"]
     if h.n_like == 0:
@@ -190,14 +220,15 @@ def test_pliklite_loglike(setup):
         c = setup["orc"][i]["cls_out"]
         ref = o.pliklite(np.stack([c[0], c[1], c[2]]), data["nb"], data["blmin"], data["blmax"], data["weights"],
                          data["invcov"], data["x_data"], cal[i])
-        assert abs(ll[i, 0] - ref) < 1e-7 * max(1.0, abs(ref)), (ll[i, 0], ref)
+        assert 10 < ref < 1e5, ref          # a chain-like -lnL, not the 1e7 of a data vector unrelated to the batch
+        assert abs(ll[i, 0] - ref) < 1e-5, (ll[i, 0], ref)   # absolute; north_star: 0.01
     # golden C_l through the host-Cls entry point: same answer as the oracle at the Planck best fit
     gold = np.zeros((1, 5, H.LMAX_OUT + 1))
     gold[0] = T["theory_cl"].T
     ll2, _, _ = h.loglike_cls(gold, np.array([[1.00061]]))
     ref = o.pliklite(np.stack([gold[0, 0], gold[0, 1], gold[0, 2]]), data["nb"], data["blmin"], data["blmax"],
                      data["weights"], data["invcov"], data["x_data"], 1.00061)
-    assert abs(ll2[0, 0] - ref) < 1e-7 * max(1.0, abs(ref))
+    assert abs(ll2[0, 0] - ref) < 1e-9 * abs(ref)   # a data vector unrelated to these C_l: -lnL ~ 1e7, relative check
 
 
 def test_lensing2018_real_data_golden_chi2(setup):
@@ -377,3 +408,61 @@ def test_default_kernel_matches_chunked_kernel_on_many_points(seed):
         nz = out[3][:, X] != 0
         assert np.array_equal(nz, out[4][:, X] != 0)
         assert np.abs(out[4][:, X][nz] / out[3][:, X][nz] - 1).max() < 1e-9, X
+
+
+def test_highl_norm_first_call_semantics(setup):
+    """highl_norm_first_call = 1 keeps the reference's SAVEd highL_norm (`real(mcp) :: highL_norm = 0`,
+    source/Calculator_CAMB.f90:358,398-399): the lensed-only TT(lmax_computed_cl) of the FIRST point ever evaluated
+    fixes the tail l > lmax_computed_cl of every later point and call (device scalar, no host round trip).  With the
+    default 0 every point normalises its own tail.  Checked against the oracle's SetPowersFromCAMB run the same way."""
+    import pyoracle as o
+    from cosmomc_b200 import lib
+    b, T, orc = setup["batch"], setup["T"], setup["orc"]
+    h1 = lib.Handle(max_points=4, chunk_points=2, lmax_out=H.LMAX_OUT, highl_norm_first_call=1)
+    h1.set_templates(T["highl_unlensed"], T["highl_lensed"])
+    h1.upload_sources(b["thermo"], b["n_k"], b["k"], b["src"])
+    # all outputs left on the device first (the path on which a host-side read of the norm used to race the kernels)
+    h1.powers_resident(b["initpower"][:2], b["alens"][:2])
+    cls, _, _ = h1.powers(b["initpower"], b["alens"])          # second call: the norm of call 1 / point 0 persists
+    lmx = H.LMAX_COMPUTED
+    hl = T["highl_lensed"]
+    norm0 = orc[0]["cls_out"][0][lmx] / hl[0][lmx]
+    for i in range(NPTS):
+        lens_pad = orc[i]["lensed"]
+        want, _, _ = o.set_powers(lens_pad, orc[i]["cl"][3], lmx, [H.LMAX_OUT] * 5, hl, lmax_out=H.LMAX_OUT,
+                                  highL_norm=norm0)
+        for X in (0, 1, 2, 3):
+            tail = slice(lmx + 1, H.LMAX_OUT + 1)
+            assert np.allclose(cls[i, X][tail], want[X][tail], rtol=1e-9, atol=0), (i, X)
+            assert np.allclose(cls[i, X][tail], norm0 * hl[[0, 3, 1, 2][X]][tail], rtol=1e-9)
+    # default mode: every point its own norm
+    own = setup["cls"]
+    for i in range(1, NPTS):
+        n_i = orc[i]["cls_out"][0][lmx] / hl[0][lmx]
+        assert np.allclose(own[i, 0][lmx + 1:], n_i * hl[0][lmx + 1:H.LMAX_OUT + 1], rtol=1e-9)
+        assert abs(n_i / norm0 - 1) > 1e-6   # the two modes really differ on this batch
+
+
+def test_packed_upload_and_async_results_match(setup):
+    """cb200_upload_sources_packed (sources at their exact sizes, device-side scatter into the padded layout) and option
+    "async_results" (C_l copied back on a third stream, closed by cb200_sync): identical to the padded, blocking path."""
+    import torch
+    from cosmomc_b200 import lib
+    b, T = setup["batch"], setup["T"]
+    h2 = lib.Handle(max_points=4, chunk_points=2, lmax_out=H.LMAX_OUT)
+    h2.set_templates(T["highl_unlensed"], T["highl_lensed"])
+    packed = np.concatenate([b["src"][i, :b["n_tau"][i], :, :b["n_k"][i]].ravel() for i in range(NPTS)])
+    pin = torch.from_numpy(packed).pin_memory()
+    out = torch.zeros((NPTS, 5, H.LMAX_OUT + 1), dtype=torch.float64).pin_memory()
+    h2.set_option("async_upload", 1)
+    h2.set_option("async_results", 1)
+    h2.upload_sources_packed(b["thermo"], b["n_tau"], b["n_k"], b["k"], first=0, src_host_ptr=pin.data_ptr())
+    h2.powers_into(b["initpower"], b["alens"], first=0, cls_ptr=out.data_ptr())
+    h2.sync()
+    assert np.array_equal(out.numpy(), setup["cls"])
+    # the padded resident copy is what the padded upload would have left there (zeros in the padding)
+    from cosmomc_b200.lib import CB200Error
+    bad = b["n_tau"].copy()
+    bad[0] -= 1
+    with pytest.raises(CB200Error):
+        h2.upload_sources_packed(b["thermo"], bad, b["n_k"], b["k"], packed)
