@@ -14,7 +14,7 @@
     use, intrinsic :: iso_c_binding
     use CosmologyTypes
     use CosmoTheory
-    use CAMB, only : CAMB_GetTransfers, CAMBParams, CAMB_SetDefParams
+    use CAMB, only : CAMB_GetResults, CAMBParams, CAMB_SetDefParams
     use Calculator_CAMB
     use settings
     implicit none
@@ -64,6 +64,15 @@
     real(c_double), intent(in) :: thermo(*), k(*), src(*)
     integer(c_int), intent(in) :: n_k(*)
     end function
+    integer(c_int) function cb200_upload_sources_packed(h, kind, first, npts, thermo, n_tau, n_k, k, src_packed) &
+        bind(C, name='cb200_upload_sources_packed')
+    !sources at their exact sizes: CAMB's Src(1:n_k, 1:3, 1:n_tau) IS the packed layout (no padding copy on this side)
+    import :: c_ptr, c_int, c_double
+    type(c_ptr), value :: h
+    integer(c_int), value :: kind, first, npts
+    real(c_double), intent(in) :: thermo(*), k(*), src_packed(*)
+    integer(c_int), intent(in) :: n_tau(*), n_k(*)
+    end function
     integer(c_int) function cb200_powers(h, first, npts, initpower, alens, aphiphi, cls_out, derived_out, status) &
         bind(C, name='cb200_powers')
     import :: c_ptr, c_int, c_double
@@ -92,9 +101,17 @@
     end function
     end interface
 
+    !the likelihood plug-ins (Likelihood_B200.f90) register with, and evaluate on, the calculator's handle
+    type(c_ptr), save :: shared_handle = c_null_ptr
+    abstract interface
+    subroutine no_arg_sub()
+    end subroutine
+    end interface
+    procedure(no_arg_sub), pointer, save :: invalidate_like_cache => null()
+
     Type, extends(CAMB_Calculator) :: B200_Calculator
         type(c_ptr) :: handle = c_null_ptr
-        integer :: n_tau_max = 768, n_k_max = 256
+        integer :: n_tau_max = 768, n_k_max = 256, n_tau_max_tensor = 2304, n_k_max_tensor = 128
     contains
     procedure :: InitForLikelihoods => B200_InitForLikelihoods
     procedure :: GetNewTransferData => B200_GetNewTransferData
@@ -102,8 +119,14 @@
     procedure :: VersionTraceOutput => B200_VersionTraceOutput
     end type B200_Calculator
 
-    public B200_Calculator
+    public B200_Calculator, b200_shared_handle, invalidate_like_cache
     contains
+
+    function b200_shared_handle() result(h)
+    type(c_ptr) :: h
+    if (.not. c_associated(shared_handle)) call MpiStop('B200: likelihood registered before the calculator was initialised')
+    h = shared_handle
+    end function
 
     subroutine B200_InitForLikelihoods(this)
     !Called once after the likelihoods fixed CosmoSettings (source/Calculator_CAMB.f90:926-946)
@@ -128,7 +151,11 @@
     cfg%max_points = 1
     cfg%n_tau_max = this%n_tau_max
     cfg%n_k_max = this%n_k_max
-    if (cb200_create(cfg, this%handle) /= 0) call MpiStop('B200: cb200_create failed (no CUDA device?)')
+    cfg%n_tau_max_tensor = this%n_tau_max_tensor
+    cfg%n_k_max_tensor = this%n_k_max_tensor
+    !cfg%struct_size was set by cb200_default_config; cb200_create returns -3 if this mirror is out of step with the header
+    if (cb200_create(cfg, this%handle) /= 0) call MpiStop('B200: cb200_create failed (no CUDA device, or stale cb200_config mirror)')
+    shared_handle = this%handle
     !templates: camb/modules.f90:1162-1185 (highL_CL_template) and source/Calculator_CAMB.f90:966-990
     allocate(unl(0:8000,4), lens(0:CosmoSettings%lmax,4))
     unl = 0; lens = 0
@@ -146,39 +173,61 @@
 
     subroutine B200_GetNewTransferData(this, CMB, Info, Theory, error)
     !Slow step (source/Calculator_CAMB.f90:179-218): CAMB evolves the sources, then the library takes over.
-    !Requires the small CAMB patch of INTEGRATION.md section 3 (`cmbmain_sources_only`), which stops cmbmain after the
-    !DoSourcek loop (camb/cmbmain.f90:198-202) and exposes Src, Evolve_q, taurst, taurend, ReionHist.
-    use CAMBmain, only : Src, Evolve_q, SourceNum
-    use ThermoData, only : taurst, taurend
-    use ModelParams, only : CP
+    !Requires cosmomc_b200/fortran/camb_sources_only.patch (INTEGRATION.md section 3): with cmbmain_sources_only = .true.
+    !cmbmain returns after the DoSourcek loop, TransferOut and MakeNonlinearSources (camb/cmbmain.f90:198-233), i.e. with
+    !the non-linear lensing rescale already applied to Src, and leaves Src, Evolve_q allocated.  CAMB_GetResults runs one
+    !cmbmain pass per perturbation type (camb/camb.f90:124-180); the hook returns before FreeSourceMem, so the passes are
+    !driven one at a time here and the sources of each are handed over before the next pass allocates its own.
+    use CAMBmain, only : Src, Evolve_q, SourceNum, cmbmain_sources_only, FreeSourceMem
+    use ModelParams, only : CP, taurst, taurend        !camb/modules.f90:27-36,179 (module ModelParams is public)
     class(B200_Calculator) :: this
     class(CMBParams) CMB
     class(TTheoryIntermediateCache), pointer :: Info
     class(TCosmoTheoryPredictions) :: Theory
     integer error
-    type(CAMBParams) P
-    real(c_double) :: thermo(5)
-    real(c_double), allocatable :: k(:), srcbuf(:,:,:)
-    integer(c_int) :: nk(1)
-    integer nt
+    type(CAMBParams) P, P1
+    integer pass
 
     select type (Info)
     class is (CAMBTransferCache)
         call this%CMBToCAMB(CMB, P)
         P%OnlyTransfers = .true.
-        call CAMB_GetTransfers(P, Info%Transfers, error)   !with cmbmain_sources_only = .true.
-        if (error /= 0) return
-        thermo = [CP%tau0, taurst, taurend, &
-            merge(CP%ReionHist%tau_start, -1._dl, CP%Reion%Reionization), CP%ReionHist%tau_complete]
-        nt = size(Src, 3)
-        allocate(k(this%n_k_max), srcbuf(this%n_k_max, 3, this%n_tau_max))
-        k = 0; srcbuf = 0
-        nk(1) = Evolve_q%npoints
-        k(1:nk(1)) = Evolve_q%points(1:nk(1))
-        srcbuf(1:nk(1), 1:SourceNum, 1:nt) = Src(1:nk(1), 1:SourceNum, 1:nt)   !Src(k,s,tau) == C [tau][s][k]
-        if (cb200_upload_sources(this%handle, 0_c_int, 0_c_int, 1_c_int, thermo, nk, k, srcbuf, 0_c_int) /= 0) error = 1
+        cmbmain_sources_only = .true.
+        do pass = 0, merge(1, 0, CosmoSettings%compute_tensors)
+            P1 = P
+            if (pass == 0) then
+                P1%WantTensors = .false.                       !scalar pass: also the matter transfer functions (sigma8)
+            else
+                P1%WantScalars = .false.; P1%WantTransfer = .false.
+            end if
+            call CAMB_GetResults(P1, error)
+            if (error == 0) call upload_pass(int(pass, c_int))
+            call FreeSourceMem
+            if (error /= 0) exit
+        end do
+        cmbmain_sources_only = .false.
         if (error == 0) call this%SetDerived(Theory)
     end select
+
+    contains
+
+    subroutine upload_pass(kind)
+    integer(c_int), intent(in) :: kind
+    real(c_double) :: thermo(5)
+    real(c_double), allocatable :: k(:)
+    integer(c_int) :: nk(1), nt(1)
+    thermo = [CP%tau0, taurst, taurend, &
+        merge(CP%ReionHist%tau_start, -1._dl, CP%Reion%Reionization), CP%ReionHist%tau_complete]
+    nk(1) = Evolve_q%npoints
+    nt(1) = size(Src, 3)
+    if (SourceNum /= 3) call MpiStop('B200: expects three sources per perturbation type (T, E, lensing potential / B)')
+    allocate(k(merge(this%n_k_max_tensor, this%n_k_max, kind == 1)))   !k is padded to n_k_max; Src is not
+    k = Evolve_q%points(nk(1))
+    k(1:nk(1)) = Evolve_q%points(1:nk(1))
+    !Src(k,s,tau), contiguous and exactly (n_k, 3, n_tau): C [n_tau][3][n_k], the packed layout of the header
+    if (cb200_upload_sources_packed(this%handle, kind, 0_c_int, 1_c_int, thermo, nt, nk, k, Src) /= 0) error = 1
+    end subroutine upload_pass
+
     end subroutine B200_GetNewTransferData
 
     subroutine B200_GetNewPowerData(this, CMB, Info, Theory, error)
@@ -206,6 +255,7 @@
         return
     end if
     error = st(1)
+    call B200_InvalidateLikeCache_hook()          !new C_l are resident: Likelihood_B200's cached -lnL are stale
     if (error /= 0) return
     !order of cls columns: TT, TE, EE, BB, PP  ->  Theory%Cls(i,j)%CL   (source/CosmoTheory.f90:23-52)
     if (allocated(Theory%Cls(1,1)%CL)) Theory%Cls(1,1)%CL(2:) = cls(2:ubound(Theory%Cls(1,1)%CL,1), 1)
@@ -216,6 +266,12 @@
         Theory%Cls(CL_Phi,CL_Phi)%CL(2:) = cls(2:ubound(Theory%Cls(CL_Phi,CL_Phi)%CL,1), 5)
     Theory%Lensing_rms_deflect = derived(1)
     end subroutine B200_GetNewPowerData
+
+    subroutine B200_InvalidateLikeCache_hook()
+    !Likelihood_B200 uses this module, so the dependency cannot point the other way: it sets this procedure pointer when
+    !its first likelihood registers
+    if (associated(invalidate_like_cache)) call invalidate_like_cache()
+    end subroutine
 
     subroutine B200_VersionTraceOutput(this, ReadValues)
     use IniObjects

@@ -95,3 +95,49 @@ def test_create_refuses_a_stale_mirror():
     cfg.struct_size -= 8  # what an out-of-date binding would pass
     h = C.c_void_p()
     assert L.cb200_create(C.byref(cfg), C.byref(h)) == -3 and not h
+
+
+def _header_protos():
+    src = re.sub(r"/\*.*?\*/", "", open(HDR).read(), flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|void|const char\*)\s+(cb200_\w+)\s*\(([^;{]*?)\)\s*;", src, re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+def test_fortran_bindings_name_exported_symbols_with_matching_arity():
+    """Every `bind(C, name='cb200_...')` interface of the Fortran glue names an entry point the header declares, with
+    the same number of arguments (the Fortran side cannot be compiled here; this catches a binding that drifted)."""
+    protos = _header_protos()
+    fdir = os.path.join(H.ROOT, "cosmomc_b200", "fortran")
+    seen = set()
+    for fn in sorted(os.listdir(fdir)):
+        if not fn.endswith(".f90"):
+            continue
+        txt = open(os.path.join(fdir, fn)).read().replace("&\n", " ")
+        for m in re.finditer(r"(?:function|subroutine)\s+(\w+)\s*\(([^)]*)\)\s*bind\(C,\s*name='(cb200_\w+)'\)", txt):
+            fname, args, cname = m.group(1), m.group(2), m.group(3)
+            nargs = len([a for a in args.split(",") if a.strip()])
+            assert cname in protos, (fn, cname)
+            assert nargs == protos[cname], (fn, cname, nargs, protos[cname])
+            seen.add(cname)
+    assert {"cb200_create", "cb200_upload_sources_packed", "cb200_powers", "cb200_like_add_cmblikes",
+            "cb200_like_add_pliklite", "cb200_loglike_batch"} <= seen
+
+
+def test_camb_patch_is_a_well_formed_unified_diff():
+    """cosmomc_b200/fortran/camb_sources_only.patch: the CAMB-side hook shipped as a diff (applies with `patch -p1` in the
+    reference root; checked against the reference checkout when it is present, i.e. in the build container)."""
+    p = os.path.join(H.ROOT, "cosmomc_b200", "fortran", "camb_sources_only.patch")
+    txt = open(p).read()
+    assert txt.startswith("--- a/camb/cmbmain.f90") and "+++ b/camb/cmbmain.f90" in txt
+    assert "cmbmain_sources_only" in txt and txt.count("\n@@ ") == 2
+    ref = "/root/reference"
+    if os.path.isdir(os.path.join(ref, "camb")):
+        import shutil
+        with tempfile.TemporaryDirectory() as d:
+            os.makedirs(os.path.join(d, "camb"))
+            shutil.copy(os.path.join(ref, "camb", "cmbmain.f90"), os.path.join(d, "camb", "cmbmain.f90"))
+            r = subprocess.run(["patch", "-p1", "--dry-run", "-i", p], cwd=d, capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout + r.stderr

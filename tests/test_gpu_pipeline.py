@@ -460,9 +460,8 @@ def test_packed_upload_and_async_results_match(setup):
     h2.powers_into(b["initpower"], b["alens"], first=0, cls_ptr=out.data_ptr())
     h2.sync()
     assert np.array_equal(out.numpy(), setup["cls"])
-    # the padded resident copy is what the padded upload would have left there (zeros in the padding)
     from cosmomc_b200.lib import CB200Error
     bad = b["n_tau"].copy()
     bad[0] -= 1
-    with pytest.raises(CB200Error):
-        h2.upload_sources_packed(b["thermo"], bad, b["n_k"], b["k"], packed)
+    with pytest.raises(CB200Error):   # the library re-derives the time-step grid and refuses a block of another shape
+        h2.upload_sources_packed(b["thermo"], bad, b["n_k"], b["k"], first=0, src_host_ptr=pin.data_ptr())
