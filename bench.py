@@ -19,7 +19,8 @@ Launch: python bench.py --gpus N --steps K --warmup W   (N > 1: under torchrun, 
   --impl reference : the CPU restatement of the reference (oracle/, -O3 -march=native -fopenmp build; the Fortran
                      reference cannot be built: no Fortran compiler in this image or on the GPU box, see
                      profiles/r02_probe_gpu_host_no_fortran.log) on ALL host cores, rank 0 only.
-  --config 2|3     : BASELINE configs[1] (background-only, JLA + BAO + HST) / configs[2] (BK15, shared transfers).
+  --config 2|3|5   : BASELINE configs[1] (background-only, JLA + BAO + HST) / configs[2] (BK15, shared transfers) /
+                     configs[4] (64-chain adaptive MCMC, NCCL covariance learning; run it under torchrun for N > 1).
 """
 import argparse
 import json
@@ -47,7 +48,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4],
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5],
                     help="SURVEY 8d config: 4 = BASELINE configs[3] (the metric's workload, default); 2, 3 = configs[1], [2]")
     ap.add_argument("--points", type=int, default=int(os.environ.get("CB200_BENCH_POINTS", 16384)),
                     help="parameter points per step: in total (strong scaling) or per GPU (weak)")

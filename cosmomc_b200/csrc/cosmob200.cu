@@ -118,6 +118,11 @@ struct cb200_handle {
     unsigned char* pin = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr; bool used = false;
   } stage[2];
   int stage_next = 0;
+  // change mask of cb200_eval_batch: what each resident slot's spectra were computed from
+  std::vector<double> ev_key;         // [max_points][12] initpower[10], alens, aphiphi
+  std::vector<unsigned> ev_epoch;     // [max_points] source-upload epoch + 1 the spectra belong to (0 = none)
+  std::vector<unsigned> src_epoch;    // [max_points] bumped by every upload into the slot
+  long long ev_powers = 0, ev_reused = 0;
   DevBuf<double> w_packed;            // device landing buffer of a packed source block (cb200_upload_sources_packed)
   DevBuf<long long> w_packed_off;     // [npts] offset of each point's block in it (doubles)
   struct BusyRange { int kind, first, npts; cudaEvent_t done; };
@@ -734,6 +739,8 @@ int upload_impl(cb200_handle* h, int kind, int first, int npts, const double* th
     CB_CUDA(cudaMemcpyAsync(S.n_k.p + f, p_nk, sizeof(int) * nb, cudaMemcpyHostToDevice, s));
     CB_CUDA(cudaMemcpyAsync(S.tseg.p + f, p_tseg, sizeof(LinSegs) * nb, cudaMemcpyHostToDevice, s));
     for (int i = 0; i < nb; i++) { S.h_nq[f + i] = p_nq[i]; S.h_ntau[f + i] = p_ntau[i]; }
+    if (h->src_epoch.size() < (size_t)h->cfg.max_points) h->src_epoch.assign(h->cfg.max_points, 0);
+    for (int i = 0; i < nb; i++) h->src_epoch[f + i]++;
     if (src_mode == 0 || src_mode == 1) {
       CB_CUDA(cudaMemcpyAsync(S.src.p + f * per, src + (size_t)b0 * per, sizeof(double) * per * nb,
                               src_mode == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
@@ -1067,6 +1074,7 @@ int cb200_powers(cb200_handle* h, int first, int npts, const double* initpower, 
   CB_API_BEGIN
   if (!h->kind[0].active) return fail(h, "powers: background-only handle");
   if (!h->have_templates) return fail(h, "powers: call cb200_set_templates first");
+  for (int i = std::max(first, 0); i < first + npts && i < (int)h->ev_epoch.size(); i++) h->ev_epoch[i] = 0;
   PointStore& S = h->store[0];
   if (!S.cap || first < 0 || npts <= 0 || first + npts > S.cap) return fail(h, "powers: point range not resident");
   const bool tens = h->cfg.compute_tensors != 0;
@@ -1122,6 +1130,7 @@ int cb200_powers_shared(cb200_handle* h, int src_point, int first, int npts, con
   if (!h) return -1;
   CB_API_BEGIN
   if (!h->kind[0].active) return fail(h, "powers_shared: background-only handle");
+  for (int i = std::max(first, 0); i < first + npts && i < (int)h->ev_epoch.size(); i++) h->ev_epoch[i] = 0;
   if (!h->have_templates) return fail(h, "powers_shared: call cb200_set_templates first");
   PointStore& S = h->store[0];
   if (!S.cap || src_point < 0 || src_point >= S.cap) return fail(h, "powers_shared: source point not resident");
@@ -1773,11 +1782,40 @@ int cb200_eval_batch(cb200_handle* h, const cb200_param_layout* L, int first, in
     for (int j = 0; j < L->n_nuis; j++) nuis[(size_t)i * L->n_nuis + j] = P[L->i_nuis_first + j];
   }
   int rc = 0;
-  if (h->n_cmb_likes > 0 || h->kind[0].active) {
-    if (h->kind[0].active) {
-      rc = cb200_powers(h, first, npts, ip.data(), al.data(), ap.data(), nullptr, nullptr, stp.data());
-      if (rc) return rc;
+  if (h->kind[0].active) {
+    // change mask (CalcLike_Cosmology.f90:59-94): recompute the spectra of a point only after a slow (new sources) or
+    // semi-slow (initial power, ALens, Aphiphi) change; runs of such points go to cb200_powers together
+    const int MP = h->cfg.max_points;
+    if ((int)h->ev_epoch.size() < MP) { h->ev_epoch.assign(MP, 0); h->ev_key.assign((size_t)MP * 12, 0.0); }
+    if ((int)h->src_epoch.size() < MP) h->src_epoch.assign(MP, 0);
+    if (first < 0 || first + npts > MP) return fail(h, "eval_batch: point range exceeds max_points");
+    std::vector<char> need(npts, 0);
+    for (int i = 0; i < npts; i++) {
+      if (st[i] == 1) continue;                               // out of bounds: the reference returns before any theory
+      const int slot = first + i;
+      double key[12];
+      std::copy(&ip[(size_t)i * 10], &ip[(size_t)i * 10] + 10, key);
+      key[10] = al[i]; key[11] = ap[i];
+      const bool same = h->ev_epoch[slot] != 0 && h->ev_epoch[slot] == h->src_epoch[slot] + 1 &&
+                        std::equal(key, key + 12, &h->ev_key[(size_t)slot * 12]);
+      need[i] = !same;
     }
+    for (int a = 0; a < npts;) {
+      if (!need[a]) { a++; continue; }
+      int b = a;
+      while (b < npts && need[b]) b++;
+      rc = cb200_powers(h, first + a, b - a, &ip[(size_t)a * 10], &al[a], &ap[a], nullptr, nullptr, &stp[a]);
+      if (rc) return rc;
+      for (int i = a; i < b; i++) {                           // (cb200_powers cleared these entries)
+        const int slot = first + i;
+        std::copy(&ip[(size_t)i * 10], &ip[(size_t)i * 10] + 10, &h->ev_key[(size_t)slot * 12]);
+        h->ev_key[(size_t)slot * 12 + 10] = al[i]; h->ev_key[(size_t)slot * 12 + 11] = ap[i];
+        h->ev_epoch[slot] = (stp[i] == 0) ? h->src_epoch[slot] + 1 : 0;   // a rejected point is never reused
+      }
+      h->ev_powers += b - a;
+      a = b;
+    }
+    for (int i = 0; i < npts; i++) if (!need[i] && st[i] != 1) h->ev_reused++;
   }
   std::vector<double> ll((size_t)npts * n_like), tot(npts);
   rc = cb200_loglike_batch(h, first, npts, L->n_nuis ? nuis.data() : nullptr, L->n_nuis, ll.data(), tot.data(), stl.data());
@@ -1860,6 +1898,8 @@ int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset) {
   t->ring_slabs = (long long)rs[0]; t->ring_direct = (long long)rs[1]; t->ring_rows = (long long)rs[2];
   t->ring_pairs = (long long)rs[3];
   t->proj_mask_mismatch = (h->proj_kernel == 4) ? (long long)rs[1] : 0;
+  t->eval_points_powers = h->ev_powers;
+  t->eval_points_reused = h->ev_reused;
   if (getenv("CB200_DEBUG_WAIT")) fprintf(stderr, "[cb200] consumer warp0 wait cycles: all %llu, before last metadata arrive %llu, before ring-warp arrive %llu\n", rs[10], rs[11], rs[12]);
   if (reset) {
     for (int p = 0; p < PH_COUNT; p++) {
@@ -1867,6 +1907,7 @@ int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset) {
       h->ev[p].clear();
     }
     h->n_launches = 0;
+    h->ev_powers = h->ev_reused = 0;
     if (h->d_triples.p) h->d_triples.zero(h->stream);
     if (h->d_ring_stats.p) h->d_ring_stats.zero(h->stream);
   }

@@ -70,7 +70,8 @@ class Timing(C.Structure):
                 ("n_launches", C.c_longlong), ("proj_triples", C.c_longlong), ("ring_slabs", C.c_longlong),
                 ("ring_direct", C.c_longlong), ("ring_rows", C.c_longlong), ("ring_pairs", C.c_longlong),
                 ("phase_cycles", C.c_longlong * 6), ("ms_background", C.c_float),
-                ("proj_mask_mismatch", C.c_longlong)]
+                ("proj_mask_mismatch", C.c_longlong), ("eval_points_powers", C.c_longlong),
+                ("eval_points_reused", C.c_longlong)]
 
 
 _lib = None

@@ -61,8 +61,14 @@ class RandDirectionProposer:
 
 class BatchedMetropolis:
     def __init__(self, loglike_fn, start, propose_cov, pmin=None, pmax=None, propose_scale=2.4, seed=0, rank=0,
-                 update_every=None, converge_test=0.01, learn_propose=True, chain_root=None, names=None):
-        """start [K][n]: starting points of this rank's K chains (all n parameters vary)."""
+                 update_every=None, converge_test=0.01, learn_propose=True, chain_root=None, names=None,
+                 chain_offset=None, max_R_propose_update=2.0, R_stop_propose_update=0.0, max_stored=500000):
+        """start [K][n]: starting points of this rank's K chains (all n parameters vary).
+        chain_offset: global index of this rank's first chain (default rank * K).  The random stream of a chain depends
+        on (seed, global chain index) only, so K x world chains evolve identically however they are spread over ranks.
+        max_R_propose_update / R_stop_propose_update: MPI_Max_R_ProposeUpdate / MPI_R_StopProposeUpdate
+        (source/SampleCollector.f90:306-313): the proposal is re-learned only while R_stop < R-1 < max_R (or while the
+        current proposal matrix is diagonal, or with a single chain)."""
         self.f = loglike_fn
         self.P = np.array(start, dtype=np.float64)
         self.K, self.n = self.P.shape
@@ -70,7 +76,8 @@ class BatchedMetropolis:
         self.pmax = None if pmax is None else np.asarray(pmax, dtype=np.float64)
         self.scale = propose_scale
         self.set_covariance(propose_cov)
-        self.rngs = [np.random.default_rng([seed, rank, k]) for k in range(self.K)]
+        self.chain_offset = rank * self.K if chain_offset is None else int(chain_offset)
+        self.rngs = [np.random.default_rng([seed, self.chain_offset + k]) for k in range(self.K)]
         self.prop = [RandDirectionProposer(self.n, r) for r in self.rngs]
         self.like = self._eval(self.P)
         if np.any(self.like >= LOG_ZERO):
@@ -81,13 +88,20 @@ class BatchedMetropolis:
         self.converge_test = converge_test
         self.learn = learn_propose
         self.R_history = []
+        self.max_R_propose_update = max_R_propose_update
+        self.R_stop_propose_update = R_stop_propose_update
+        self.cov_is_diagonal = bool(np.count_nonzero(self.cov - np.diag(np.diag(self.cov))) == 0)
+        self.flukecheck = False          # TMpiChainCollector%flukecheck: R-1 has to pass twice in a row
+        self.converged = False
+        self.thin_fac = 1
+        self.max_stored = max_stored
         self.n_steps = 0
         self.n_accept = np.zeros(self.K, dtype=np.int64)
         self.rank = rank
         self.files = None
         if chain_root is not None:
             os.makedirs(os.path.dirname(os.path.abspath(chain_root)), exist_ok=True)
-            self.files = [open("%s_%d.txt" % (chain_root, rank * self.K + k + 1), "w") for k in range(self.K)]
+            self.files = [open("%s_%d.txt" % (chain_root, self.chain_offset + k + 1), "w") for k in range(self.K)]
             if rank == 0 and names is not None:
                 write_paramnames(chain_root + ".paramnames", names)
                 write_ranges(chain_root + ".ranges", names, self.pmin, self.pmax)
@@ -118,27 +132,39 @@ class BatchedMetropolis:
                 self.n_accept[k] += 1
             else:
                 self.mult[k] += 1.0
-            self.samples[k].append(self.P[k].copy())
+            if self.n_steps % self.thin_fac == 0:
+                self.samples[k].append(self.P[k].copy())
         self.n_steps += 1
 
     def update(self):
-        """SampleCollector.f90:212-322 on this rank's chains + all-gather.  Returns the pooled statistics dict."""
+        """TMpiChainCollector_UpdateCovAndCheckConverge (source/SampleCollector.f90:212-322) on this rank's chains + the
+        all-gather.  Returns the pooled statistics dict; sets self.converged after two consecutive passes of R-1."""
         st = _chains.update_cov_and_check_converge([np.asarray(s) for s in self.samples], self.n)
-        if st.get("ready"):
-            if st.get("R") is not None:
-                self.R_history.append(st["R"])
-            if self.learn:
-                self.set_covariance(st["cov"])
+        if not st.get("ready"):
+            return st
+        R = st.get("R")
+        single = R is None                      # MPIChains == 1
+        if not single:
+            self.R_history.append(R)
+            if R < self.converge_test and self.flukecheck:
+                self.converged = True
+            self.flukecheck = R < self.converge_test
+            if max(len(x) for x in self.samples) > self.max_stored:   # Samples%Thin(2), MPI_thin_fac *= 2
+                self.samples = [x[::2] for x in self.samples]
+                self.thin_fac *= 2
+        if self.learn and (single or ((self.cov_is_diagonal or R < self.max_R_propose_update)
+                                      and R > self.R_stop_propose_update)):
+            self.set_covariance(st["cov"])
+            self.cov_is_diagonal = False
         return st
 
     def run(self, max_steps, min_steps=0):
-        """Step until R-1 < converge_test (checked every update_every steps) or max_steps.  Returns True if converged."""
+        """Step until R-1 < converge_test at two consecutive checks (every update_every steps) or max_steps."""
         while self.n_steps < max_steps:
             self.step()
             if self.n_steps % self.update_every == 0:
-                st = self.update()
-                if (st.get("ready") and st.get("R") is not None and st["R"] < self.converge_test
-                        and self.n_steps >= min_steps):
+                self.update()
+                if self.converged and self.n_steps >= min_steps:
                     self.close()
                     return True
         self.close()

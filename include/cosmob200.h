@@ -246,7 +246,12 @@ typedef struct cb200_param_layout {
   int inflation_consistency;
   int i_nuis_first, n_nuis;     /* nuisance parameters of the likelihoods = params[:, i_nuis_first : +n_nuis] */
 } cb200_param_layout;
-/* params [npts][num_params]; loglike [npts] (-ln L incl. priors, 1e30 = rejected); likelihoods [npts][n_like] (may be
+/* Change mask (Cosmo_CalculateRequiredTheoryChanges, source/CalcLike_Cosmology.f90:59-94), per point: the spectra are
+ * recomputed only if the point's sources were re-uploaded since its last evaluation (slow change) or its initial-power /
+ * ALens / Aphiphi values differ from the ones its resident spectra were computed with (semi-slow change); a point whose
+ * nuisance parameters alone moved (fast change) goes straight to the likelihoods, and an out-of-bounds point is never
+ * evaluated.  A direct cb200_powers / cb200_powers_shared call on a slot invalidates its entry.
+ * params [npts][num_params]; loglike [npts] (-ln L incl. priors, 1e30 = rejected); likelihoods [npts][n_like] (may be
  * NULL); prior [npts] (may be NULL; the un-tempered prior term); status [npts] 0 ok / 1 out of bounds / >1 soft error */
 int cb200_eval_batch(cb200_handle* h, const cb200_param_layout* layout, int first, int npts, const double* params,
                      double* loglike, double* likelihoods, double* prior, int* status);
@@ -264,6 +269,8 @@ typedef struct cb200_timing {
   long long phase_cycles[6]; /* per-warp clock64 sums: prologue, prefetch, barrier wait, ring fill, accumulate, metadata */
   float ms_background;       /* K5 distance kernels */
   long long proj_mask_mismatch; /* proj_kernel 4 with "ring_stats": (pair, lane) activity masks that differ from the exact windows; must be 0 */
+  long long eval_points_powers; /* cb200_eval_batch: points whose spectra were recomputed (slow or semi-slow change) ... */
+  long long eval_points_reused; /* ... and points whose resident spectra were reused (only nuisance parameters moved) */
 } cb200_timing;
 int cb200_get_timing(cb200_handle* h, cb200_timing* t, int reset);
 int cb200_sync(cb200_handle* h);

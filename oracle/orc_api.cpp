@@ -231,6 +231,25 @@ int orc_lens_cls(int nl, const int* ls, int Max_l, const double* cl_scalar, cons
   ORC_CATCH
 }
 
+// same with the accuracy knobs of the reference exposed (AccuracyBoost, accurate_BB: camb/lensing.f90:163-189), to
+// check that the restatement CONVERGES to the reference's independent implementation (pycamb correlations.py)
+int orc_lens_cls_opts(int nl, const int* ls, int Max_l, const double* cl_scalar, const double* tmpl, double* out,
+                      int out_stride, double AccuracyBoost, int AccurateBB) {
+  ORC_TRY
+  std::vector<int> lsv(ls, ls + nl);
+  HighLTemplate T;
+  for (int X = 0; X < 4; X++) T.cl[X].assign(tmpl + (size_t)X * (lmax_extrap_highl + 1),
+                                             tmpl + (size_t)(X + 1) * (lmax_extrap_highl + 1));
+  const double* in[4];
+  double* o[4];
+  for (int X = 0; X < 4; X++) { in[X] = cl_scalar + (size_t)X * (Max_l + 1); o[X] = out + (size_t)X * out_stride; }
+  LensOpts lo;
+  lo.AccuracyBoost = AccuracyBoost;
+  lo.AccurateBB = AccurateBB != 0;
+  return CorrFuncFullSky(lsv, Max_l, in, T, o, lo);
+  ORC_CATCH
+}
+
 }  // extern "C"
 
 #include "orc_like_api.inc"

@@ -303,13 +303,18 @@ def interp_cl(ls, iCl, max_ind=None, template_index=0, tmpl=None):
     return out
 
 
-def lens_cls(ls, Max_l, cl_scalar, tmpl):
-    """cl_scalar: [4][Max_l+1] TT,EE,TE,PP(l^4 C_phi) dimensionless; returns ([4][lmax_lensed+1] TT,EE,BB,TE)."""
+def lens_cls(ls, Max_l, cl_scalar, tmpl, accuracy_boost=None, accurate_bb=False):
+    """cl_scalar: [4][Max_l+1] TT,EE,TE,PP(l^4 C_phi) dimensionless; returns ([4][lmax_lensed+1] TT,EE,BB,TE).
+    accuracy_boost / accurate_bb: the reference's AccuracyBoost and accurate_BB knobs (default: the production settings)."""
     ls = _i(ls)
     cl_scalar = _d(cl_scalar)
     assert cl_scalar.shape == (4, Max_l + 1)
     out = np.zeros((4, Max_l + 1))
-    lml = lib().orc_lens_cls(len(ls), _p(ls), int(Max_l), _p(cl_scalar), _p(_d(tmpl)), _p(out), Max_l + 1)
+    if accuracy_boost is not None or accurate_bb:
+        lml = lib().orc_lens_cls_opts(len(ls), _p(ls), int(Max_l), _p(cl_scalar), _p(_d(tmpl)), _p(out), Max_l + 1,
+                                      C.c_double(accuracy_boost or 1.0), int(accurate_bb))
+    else:
+        lml = lib().orc_lens_cls(len(ls), _p(ls), int(Max_l), _p(cl_scalar), _p(_d(tmpl)), _p(out), Max_l + 1)
     if lml < 0:
         raise RuntimeError("orc_lens_cls failed")
     return out[:, : lml + 1].copy()

@@ -101,10 +101,3 @@ def test_config2_likelihoods():
         assert abs(tot[i] - sum(want)) < 1e-7 * abs(sum(want))
     t = h.timing()
     assert t["n_launches"] > 0 and t["ms_background"] > 0
-
-
-def test_sn_vs_reference_port_fixture():
-    """-lnL of the GPU path against the reference's python port (tests/golden/sn_py.npz) with SN.py's fit(z) distances:
-    D_A is injected by choosing bg such that ... not possible -> instead compare through loglike with a distance table:
-    the C ABI takes distances from its own K5, so this check goes oracle -> port (CPU test) and GPU -> oracle (above)."""
-    assert os.path.exists(os.path.join(H.ROOT, "tests", "golden", "sn_py.npz"))

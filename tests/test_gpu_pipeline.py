@@ -465,3 +465,48 @@ def test_packed_upload_and_async_results_match(setup):
     bad[0] -= 1
     with pytest.raises(CB200Error):   # the library re-derives the time-step grid and refuses a block of another shape
         h2.upload_sources_packed(b["thermo"], bad, b["n_k"], b["k"], first=0, src_host_ptr=pin.data_ptr())
+
+
+def test_eval_batch_change_mask(setup):
+    """Per-point change mask of cb200_eval_batch (Cosmo_CalculateRequiredTheoryChanges, CalcLike_Cosmology.f90:59-94):
+    nuisance-only moves reuse the resident spectra, an initial-power move or a re-upload of the sources recomputes that
+    point only, out-of-bounds points are never evaluated; results equal the always-recompute answer bit for bit."""
+    from cosmomc_b200 import lib, synthetic as syn
+    b, T = setup["batch"], setup["T"]
+    h2 = lib.Handle(max_points=4, chunk_points=2, lmax_out=H.LMAX_OUT)
+    h2.set_templates(T["highl_unlensed"], T["highl_lensed"])
+    h2.upload_sources(b["thermo"], b["n_k"], b["k"], b["src"])
+    fid = np.mean([setup["orc"][i]["cls_out"] for i in range(NPTS)], axis=0)
+    d = syn.synthetic_pliklite(H.LMAX_OUT, fiducial_cls=fid)
+    h2.add_pliklite(d["nb"], d["blmin"], d["blmax"], d["weights"], d["invcov"], d["x_data"], 0)
+    ip = b["initpower"]
+    P = np.stack([np.log(1e10 * ip[:, 0]), ip[:, 1], b["cal"]], axis=1)
+    pmin, pmax = [1.0, 0.8, 0.9], [5.0, 1.2, 1.1]
+    kw = dict(columns=dict(logA=0, ns=1), nuis_first=2, n_nuis=1, pivot_scalar=ip[0, 7], pivot_tensor=ip[0, 8],
+              inflation_consistency=bool(ip[0, 9]), defaults=dict(nrun=ip[0, 2], nrunrun=ip[0, 3], r=ip[0, 4], nt=ip[0, 5], ntrun=ip[0, 6]))
+
+    def run(P):
+        h2.timing(reset=True)
+        ll, likes, pr, st = h2.eval_batch(P, pmin, pmax, kw["columns"], **{k: v for k, v in kw.items() if k != "columns"})
+        t = h2.timing(reset=True)
+        return ll, (t["eval_points_powers"], t["eval_points_reused"])
+
+    ll0, c0 = run(P)
+    assert c0 == (NPTS, 0)                                   # first evaluation: everything is new
+    P1 = P.copy(); P1[:, 2] *= 1.001                         # fast change only (calPlanck)
+    ll1, c1 = run(P1)
+    assert c1 == (0, NPTS) and np.all(ll1 != ll0)
+    P2 = P1.copy(); P2[1, 1] += 0.01                         # semi-slow change of point 1 (n_s)
+    ll2, c2 = run(P2)
+    assert c2 == (1, NPTS - 1) and ll2[0] == ll1[0] and ll2[2] == ll1[2] and ll2[1] != ll1[1]
+    h2.upload_sources(b["thermo"][2:3], b["n_k"][2:3], b["k"][2:3], b["src"][2:3], first=2)   # slow change of point 2
+    P3 = P2.copy(); P3[0, 0] = 9.0                           # point 0 leaves the prior box: never evaluated
+    ll3, c3 = run(P3)
+    assert c3 == (1, 1) and ll3[0] == 1e30 and ll3[2] == ll2[2]
+    # the always-recompute answer (fresh handle state through cb200_powers) is identical
+    ip2 = ip.copy(); ip2[:, 1] = P2[:, 1]
+    h2.powers_resident(ip2, b["alens"])
+    _, tot, _ = h2.loglike_batch(NPTS, P2[:, 2:3])
+    assert np.array_equal(tot, ll2)
+    ll4, c4 = run(P2)                                        # the direct cb200_powers call invalidated every entry
+    assert c4 == (NPTS, 0) and np.array_equal(ll4, ll2)

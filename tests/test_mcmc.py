@@ -94,6 +94,46 @@ def test_gloo_two_ranks_share_the_learned_covariance(tmp_path):
     assert bool(a["conv"]) and np.abs(a["cov"] - C).max() < 0.3
 
 
+TRAJ_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch.distributed as dist
+from cosmomc_b200 import mcmc
+world = int(os.environ["WORLD"])
+if world > 1:
+    dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=world,
+                            init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"])
+rank = int(os.environ["RANK"])
+n, Ktot = 3, 8
+K = Ktot // world
+C = np.array([[1.0, 0.3, 0.0], [0.3, 2.0, -0.4], [0.0, -0.4, 0.5]]); Ci = np.linalg.inv(C)
+f = lambda P: 0.5 * np.einsum("ki,ij,kj->k", P, Ci, P)
+start = np.random.default_rng(7).normal(size=(Ktot, n))[rank * K:(rank + 1) * K]
+m = mcmc.BatchedMetropolis(f, start, np.eye(n), seed=11, rank=rank, update_every=200, converge_test=1e-9)
+m.run(max_steps=2400)
+np.savez(os.environ["OUT"] + "w%%d_r%%d.npz" %% (world, rank), cov=m.cov, R=np.array(m.R_history), P=m.P)
+if world > 1:
+    dist.destroy_process_group()
+"""
+
+
+def test_R_trajectory_is_independent_of_the_rank_layout(tmp_path):
+    """SURVEY 8d config 5's acceptance test on CPU (gloo): 8 chains on 2 ranks x 4 and in one process give the SAME R-1
+    trajectory, learned covariance and chain positions, bit for bit - a chain's random stream depends on its global index
+    only, and the all-gathered per-chain records are pooled in global chain order."""
+    script = tmp_path / "w.py"
+    script.write_text(TRAJ_WORKER % H.ROOT)
+    env = dict(os.environ, PORT="29743", OUT=str(tmp_path) + os.sep)
+    one = subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK="0", WORLD="1"))
+    two = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), WORLD="2")) for r in range(2)]
+    assert one.wait(timeout=240) == 0 and all(p.wait(timeout=240) == 0 for p in two)
+    a = np.load(str(tmp_path / "w1_r0.npz"))
+    b0, b1 = np.load(str(tmp_path / "w2_r0.npz")), np.load(str(tmp_path / "w2_r1.npz"))
+    assert len(a["R"]) == 12 and np.array_equal(a["R"], b0["R"]) and np.array_equal(a["R"], b1["R"])
+    assert np.array_equal(a["cov"], b0["cov"])
+    assert np.array_equal(a["P"], np.concatenate([b0["P"], b1["P"]]))
+
+
 def test_eval_batch_control_flow_restatement():
     """numpy restatement of GetLogLike (calclike.f90:97-151) used as the checker of cb200_eval_batch in the GPU tests."""
     sys.path.insert(0, os.path.join(H.ROOT, "oracle"))
