@@ -150,6 +150,7 @@ struct cb200_handle {
   int spline_kernel = 2;  // 1: one thread per row straight from global memory, 2: tiled through shared memory
   DevBuf<unsigned long long> d_ring_stats;
   DevBuf<unsigned char> w_fallback;  // [chunk][NQB] blocks left to the chunked kernel by project4_kernel
+  DevBuf<CUtensorMap> d_tmaps[2];    // per perturbation type: TMA descriptors of {sources, second derivatives}
   // resident outputs
   DevBuf<double> r_cl_lensed, r_cls_out, r_derived, r_icl, r_cl;
   DevBuf<int> r_status;
@@ -803,6 +804,32 @@ namespace {
 
 struct ProjLaunch { int q_per_block, nqb_total; };
 
+// 2-D TMA descriptor of a [rows][NK] array of doubles with a box of (W4_S * 3 rows) x (W4_KSP wavenumbers): the raw
+// source rows of one slab of the projection kernel.  cuTensorMapEncodeTiled is taken from the driver at run time.
+CUtensorMap make_source_tensor_map(const double* base, size_t rows, int NK) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled not available in this driver");
+    enc = reinterpret_cast<encode_fn>(fn);
+  }
+  CUtensorMap tm;
+  const cuuint64_t dims[2] = {(cuuint64_t)NK, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)NK * sizeof(double)};   // bytes between rows (a multiple of 16: NK is even)
+  const cuuint32_t box[2] = {(cuuint32_t)W4_KSP, (cuuint32_t)(W4_S * 3)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return tm;
+}
+
 // K0 + K1 + K2 for one chunk of points of one perturbation type: resident sources -> sampled C_l in w_icl
 // (source spline, line-of-sight projection fused with the partial k-contraction, fixed-order reduction + l-norms)
 void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, double* d_delta) {
@@ -860,6 +887,7 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       pp.rb = LK * 128;
       pp.R = std::min(w4_ring_rows(LK, S.NT), 4096);
       pp.max_eta_k = K.max_eta_k; pp.ddsrc = h->w_ddsrc.p; pp.bx = K.d_bx.p; pp.bes = K.d_bes4.p;
+      if (S.NK % 2) throw std::runtime_error("n_k_max must be even");
       pp.initpower = h->w_initpower.p; pp.part = h->w_part.p;
       pp.delta = d_delta;
       pp.triples = h->count_triples ? h->d_triples.p : nullptr;
@@ -867,6 +895,14 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       pp.fallback = h->w_fallback.p;
       pp.bseg = K.bseg;
       w4_set_last_stretch(pp);
+      if (!h->d_tmaps[kind].p) {  // descriptors of this perturbation type's source arrays (fixed buffers: built once)
+        CUtensorMap tm[2] = {make_source_tensor_map(S.src.p, (size_t)S.cap * S.NT * 3, S.NK),
+                             make_source_tensor_map(h->w_ddsrc.p, (size_t)h->chunk * S.NT * 3, S.NK)};
+        h->d_tmaps[kind].alloc(2);
+        CB_CUDA(cudaMemcpyAsync(h->d_tmaps[kind].p, tm, sizeof(tm), cudaMemcpyHostToDevice, s));
+        CB_CUDA(cudaStreamSynchronize(s));   // tm lives on this stack frame
+      }
+      pp.tmaps = h->d_tmaps[kind].p;
       for (int i = 0; i < PROJ_LP; i++) pp.ls[i] = i < nl ? K.ls[i] : 0;
       dim3 grid((nq_max + W4_QC - 1) / W4_QC, np);
       const bool cnt = h->count_triples || h->ring_stats;

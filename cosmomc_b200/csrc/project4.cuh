@@ -5,15 +5,19 @@
 // saturated — 2.86e7 shared-memory wavefronts and 1.28e8 warp instructions per point, 25 % occupancy, two
 // barriers per slab, metadata and ring filled three times because a CTA only covers 32 of the 88 multipoles):
 //   * one CTA = (point, 32 wavenumbers) and ALL sampled multipoles: a quarter-warp still owns one (q, tau)
-//     pair per step, but each lane now carries LK = ceil(n_l / 8) multipoles (l-slots li + 8k), so the 48 B of
+//     pair per step, but each lane now carries LK = ceil(n_l / 8) multipoles (l-slots li + 8k), so the 40 B of
 //     per-pair metadata are read once per 88 multipoles instead of once per 32, the pair metadata is computed
 //     once (not once per multipole chunk) and the ring is filled once per wavenumber block;
 //   * warp specialisation: 12 CONSUMER warps (6 wavenumber groups x 2 time halves: the two warps of a group take
 //     alternate time samples of a slab, every lane all octets; CB200_W4_TSPLIT=0: even / odd octets instead) do nothing
 //     but the accumulation (shared-memory loads + FP64 FMAs).  4 PRODUCER warps: warp 0 keeps the ring filled with
 //     TMA bulk copies (cp.async.bulk, one per run of table rows, byte count on the slab's `full` mbarrier); warps 1-3 compute
-//     the (q, tau)-pair metadata of the coming slabs (table row, spline weights, k-interpolated d-tau-weighted
-//     sources; global loads software-pipelined one more slab ahead).  The two producer roles run in separate loops
+//     the (q, tau)-pair metadata of the coming slabs (table row, spline weight, k-interpolated d-tau-weighted
+//     sources).  The source rows a slab needs (S time samples x 3 sources x {Src, ddSrc}, cut to the 8 source
+//     wavenumbers that bracket the block's wavenumbers) are staged in shared memory by two 2-D TMA tensor copies of
+//     the ring warp, so the metadata threads read them with LDS instead of 12 global loads per pair through running
+//     64-bit pointers (122.2 -> 118.2 us/point; a separate pre-pass kernel that wrote S(q,tau) dtau for every pair
+//     made this kernel 110.4 us/point but cost 8.6 us/point of HBM writes itself).  The two producer roles run in separate loops
 //     and meet only the consumers (full / empty mbarriers per metadata buffer): the metadata runs up to NST slabs
 //     ahead even while the ring warp waits for room, and there is no CTA-wide barrier inside the time loop.
 //     setmaxnreg moves registers from the producer warps to the consumers;
@@ -25,6 +29,7 @@
 //   * wavenumber blocks whose table window exceeds the ring are flagged and left to project3_kernel (host launches
 //     it right after, on the flagged blocks only).
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include "common.cuh"
 #include "project.cuh"
 #include "project3.cuh"
@@ -82,18 +87,22 @@ static_assert(W4_MS == 1 || W4_PPT == 1, "several slabs per metadata iteration n
 #define CB200_STR(x) CB200_STR2(x)
 constexpr int W4_SMEM_TOTAL = 227 * 1024;
 
-struct __align__(16) Proj4Rec {  // third metadata word of a pair
-  double s2;  // lensing-potential source x dtau
-  int off;    // byte offset of node row i0 in the ring
+struct __align__(16) Proj4Rec {  // what the metadata threads compute for a (q, tau) pair
+  double a;   // spline weight of node row i0: (x1 - x) / (x1 - x0)
+  int off;    // byte offset of node row i0 in the ring (a multiple of 128) | stretch of the abscissa grid (low 3 bits)
   int jr;     // active multipole slots [jlo, jhi]: jlo | (jhi + 1) << 8 ; none: 127
 };
 
 struct Proj4Params {
+  // 2-D TMA descriptors of the resident sources [point][tau][source][k] and of the chunk's second derivatives, both
+  // seen as [rows = (point, tau, source)][k]: a slab's S x 3 consecutive rows x W4_KSP wavenumbers are ONE box
+  const CUtensorMap* tmaps;   // device memory: [0] sources, [1] second derivatives (written by the host before the launch)
   PointView v;
   int p0, nl, num_xx, NQB, tensors;
   int R, rb;                // ring capacity in rows (+1 mirror row), row stride in bytes (= 128 * octets)
   double max_eta_k;
   const double* ddsrc;
+  double h2o6[8];           // (x1 - x0)^2 / 6 of every stretch of the Bessel abscissa grid
   const double* bx;
   const double2* bes;       // [num_xx][rb / 16]: rows packed at the ring's row stride
   const double* initpower;
@@ -115,6 +124,11 @@ inline void w4_set_last_stretch(Proj4Params& p) {
   const int r = g.n - 1;
   p.bl_lo = g.seg[r][0]; p.bl_hi = g.seg[r][1]; p.bl_step = g.seg[r][2]; p.bl_inv = g.inv_step[r];
   p.bl_first = (int)g.seg[r][3]; p.bl_nseg = g.npoints - p.bl_first;
+  for (int i = 0; i < 8; i++) {
+    // spacing of the stretch as the table holds it: lo + step * 1 - lo, rounded like the abscissae themselves
+    const double h = i < g.n ? (g.seg[i][0] + g.seg[i][2] * 1.0) - g.seg[i][0] : 0.0;
+    p.h2o6[i] = h * h / 6;
+  }
 }
 
 #ifndef CB200_W4_LEANMETA
@@ -128,7 +142,7 @@ inline void w4_set_last_stretch(Proj4Params& p) {
 // true IEEE quotient (x - lo) / step (camb/utils.F90:81-111).  t = (x - lo) * (1/step) differs from that quotient by a few
 // ulp (< 1e-11 for t < 2e4), so the two truncations agree unless t lies within 1e-7 of an integer - only then is the
 // division carried out.  Everything else (x0, x1 rebuilt without FMA) is lin_locate_desc's arithmetic.
-__device__ __forceinline__ int w4_locate(const Proj4Params& p, double v, double& x0, double& x1, double& inv_h) {
+__device__ __forceinline__ int w4_locate(const Proj4Params& p, double v, double& x0, double& x1, double& inv_h, int& rs) {
   if (v < p.bl_hi && v >= p.bl_lo) {
     const double d = __dsub_rn(v, p.bl_lo);
     const double t = __dmul_rn(d, p.bl_inv);
@@ -138,9 +152,30 @@ __device__ __forceinline__ int w4_locate(const Proj4Params& p, double v, double&
     x0 = __dadd_rn(p.bl_lo, __dmul_rn(p.bl_step, (double)j));
     x1 = (j + 1 < p.bl_nseg) ? __dadd_rn(p.bl_lo, __dmul_rn(p.bl_step, (double)(j + 1))) : p.bl_hi;
     inv_h = p.bl_inv;
+    rs = p.bseg.n - 1;
     return p.bl_first + j;
   }
-  return lin_locate_desc(p.bseg, v, x0, x1, inv_h);
+  // the finer stretches (x < 150): lin_locate_desc's arithmetic, also reporting the stretch
+  const LinSegs& g = p.bseg;
+#pragma unroll 1
+  for (int r = g.n - 1; r >= 0; r--) {
+    const double lo = g.seg[r][0], hi = g.seg[r][1];
+    if (v < hi && v >= lo) {
+      const double step = g.seg[r][2];
+      const int first = (int)g.seg[r][3];
+      const int j = (int)(__ddiv_rn(__dsub_rn(v, lo), step));
+      const int nseg = ((r + 1 < g.n) ? (int)g.seg[r + 1][3] : g.npoints) - first;
+      x0 = __dadd_rn(lo, __dmul_rn(step, (double)j));
+      x1 = (j + 1 < nseg) ? __dadd_rn(lo, __dmul_rn(step, (double)(j + 1))) : hi;
+      inv_h = g.inv_step[r];
+      rs = r;
+      return first + j;
+    }
+  }
+  x0 = x1 = g.highest;
+  inv_h = 0;
+  rs = g.n - 1;
+  return g.npoints;
 }
 
 #ifndef CB200_W4_KB
@@ -153,6 +188,7 @@ __device__ __forceinline__ int w4_locate(const Proj4Params& p, double v, double&
 #define CB200_W4_PBAL 0   // 1: every producer warp (the ring warp too) computes the metadata of ONE time sample of the slab
 #endif
 constexpr bool W4_PBAL = CB200_W4_PBAL != 0;
+static_assert(!W4_PBAL, "balanced producers were dropped with the in-kernel source staging");
 static_assert(!W4_PBAL || (W4_S == W4_NPW && W4_QC <= 32 && W4_MG == 1 && W4_MS == 1), "balanced producers: one time sample per producer warp");
 #ifndef CB200_W4_UNSAFE_FREEMETA
 #define CB200_W4_UNSAFE_FREEMETA 0    // timing experiment only: WRONG results
@@ -178,7 +214,19 @@ constexpr int W4_UNROLL = CB200_W4_UNROLL;
 #define CB200_W4_NST 4
 #endif
 constexpr int W4_NST = CB200_W4_NST;  // metadata buffers = slabs the producer may run ahead of the consumers
-constexpr size_t W4_META_BYTES = (size_t)W4_NST * W4_NPAIR * 48;
+constexpr int W4_MB = W4_NPAIR * 40;   // one metadata buffer: {a, off, jr} 16 B + {S_T, S_E} dtau 16 B + S_phi dtau 8 B per (q, tau) pair
+// staging of the raw source rows of a slab (ring warp): S time samples x 3 sources x {Src, ddSrc} rows of W4_KSP
+// consecutive source wavenumbers (the few that bracket the block's integration wavenumbers)
+constexpr int W4_KSP = 8;   // doubles per staged row
+#ifndef CB200_W4_SPD
+#define CB200_W4_SPD 2
+#endif
+// the copies of slab t + SPD are issued when slab t's metadata buffer is free (the consumers have released slab t - NST,
+// so the metadata threads are done with every stage up to that slab's): NST + SPD stages keep a refill off live rows
+constexpr int W4_SPD = CB200_W4_SPD, W4_NSR = W4_NST + W4_SPD;
+constexpr int W4_SRAW_STAGE = W4_S * 3 * 2 * W4_KSP * 8;   // bytes: [Src | ddSrc][S x 3 rows][KSP]
+static_assert((W4_S * 3 * W4_KSP * 8) % 128 == 0, "TMA box destinations are 128-byte aligned");
+constexpr size_t W4_META_BYTES = (size_t)W4_NST * W4_MB + (size_t)W4_NSR * W4_SRAW_STAGE;
 constexpr size_t W4_QC_BYTES = sizeof(ProjQ3) * W4_QC;
 constexpr size_t W4_MISC_BYTES = 768;
 // octets per ring row for a multipole set of noct octets (the kernel's template instances)
@@ -219,6 +267,13 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned b
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+// TMA tensor copy of a 2-D box global -> shared (coordinates in elements, innermost first; out-of-range elements read 0)
+__device__ __forceinline__ void tma_box_g2s(void* dst, const CUtensorMap* tm, int c0, int c1, unsigned long long* b) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(b))
                : "memory");
 }
 // predicated 16-byte shared load: the destination keeps its (undefined) previous contents when !pred
@@ -344,6 +399,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
       mbar_init(s_bar + i, 32 * (1 + W4_MW)); // full: ring warp + one metadata group arrive (+ the bytes of the bulk copies)
       mbar_init(s_bar + W4_NST + i, NCW);    // empty: one lane per consumer warp
     }
+    for (int i = 0; i < W4_NSR; i++) mbar_init(s_bar + 32 + i, 1);  // raw source rows of a slab landed
   }
   __syncthreads();
 
@@ -479,19 +535,13 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     const ProjQ3& pc = qc[m_qi];  // read from shared memory where needed: the producer runs on few registers
     const int pw1 = (pc.valid && m_live) ? max(s_q1[m_qi], 1) : 0x7fffffff;  // (ring warp: never valid)
     const int pw2 = pc.valid ? min(s_q2[m_qi], pc.steps) : 0;
-    const double* Sp0 = src + (pc.klo - 1);
-    const double* Dp0 = dds + (pc.klo - 1);
     constexpr int PPT = W4_PPT, PNN = W4_PNN, MS = W4_MS, NU = PPT * MS;
-    double f_tau[NU], f_dtau[NU], f_s[NU][3][4];
+    double f_tau[NU], f_dtau[NU];
     bool f_valid[NU];
-    // Source loads of the coming slab(s).  The addresses advance by a fixed stride from one call to the next, so the
-    // thread keeps running byte pointers instead of rebuilding 64-bit addresses from the sample index for each load.
-    const size_t ts_b = tau_stride * sizeof(double);                 // one time sample
-    const unsigned o1 = (unsigned)(row_stride * sizeof(double));     // one source row
+    // Conformal times of the coming slab(s), loaded one iteration ahead.  (The sources themselves no longer pass through
+    // these threads: source_q_kernel has interpolated them to the integration wavenumbers, the ring warp copies a
+    // slab's values straight into the metadata buffer.)
     int pf_n = n_lo + m_grp * MS * S + m_nn;                         // time sample of pair u = 0 at the next call
-    const unsigned char* pf_s = reinterpret_cast<const unsigned char*>(Sp0) + (ptrdiff_t)(pf_n - 1) * (ptrdiff_t)ts_b;
-    const unsigned char* pf_d = reinterpret_cast<const unsigned char*>(Dp0) + (ptrdiff_t)(pf_n - 1) * (ptrdiff_t)ts_b;
-    const size_t pf_step = (size_t)(W4_MG * MS * S) * ts_b;
     auto prefetch = [&]() {
 #pragma unroll
       for (int u = 0; u < NU; u++) {
@@ -500,24 +550,39 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         f_valid[u] = (n >= pw1) && (n <= pw2);
         if (f_valid[u] && !CB200_W4_UNSAFE_FREEMETA) {
           f_tau[u] = __ldg(tau + n - 1);
-          f_dtau[u] = __ldg(dtau + n - 1);
-          const unsigned char* Sp = pf_s + (size_t)du * ts_b;
-          const unsigned char* Dp = pf_d + (size_t)du * ts_b;
-#pragma unroll
-          for (int sI = 0; sI < 3; sI++) {
-            const double* sa = reinterpret_cast<const double*>(Sp + sI * o1);
-            const double* da = reinterpret_cast<const double*>(Dp + sI * o1);
-            f_s[u][sI][0] = __ldg(sa);
-            f_s[u][sI][1] = __ldg(sa + 1);
-            f_s[u][sI][2] = __ldg(da);
-            f_s[u][sI][3] = __ldg(da + 1);
-          }
+          f_dtau[u] = (n >= 2) ? __ldg(dtau + n - 1) : 0.0;  // Source_q(1,:) is forced to zero (IntegrationVars_Init, cmbmain.f90:1380)
         }
       }
       pf_n += W4_MG * MS * S;
-      pf_s += pf_step;
-      pf_d += pf_step;
     };
+    // ---- InterpolateSources (cmbmain.f90:1295-1374) for the slab's (q, tau) pairs.  The metadata threads used to fetch
+    // their 12 source values with global loads (one slab ahead, 24 registers, running 64-bit pointers): with the table
+    // lookup that made ~320 instructions per pair and the three metadata warps paced the kernel.  Now the S x 3
+    // consecutive source rows of a slab, cut down to the W4_KSP source wavenumbers that bracket the block's integration
+    // wavenumbers, are staged by TWO TMA tensor copies of the ring warp (one box of Src, one of ddSrc) as soon as the
+    // slab's metadata buffer is free, and the metadata threads evaluate the spline out of shared memory.  Blocks whose
+    // wavenumbers span more source intervals than a staged row holds (two log-spaced blocks per point) keep the loads
+    // from global memory.
+    const int r_nvalid = min(QC, nq - q0);
+    const int r_k0 = (qc[0].klo - 1) & ~1;   // even: TMA wants the box to start on a 16-byte boundary (odd: illegal instruction)
+    const bool r_wide = qc[r_nvalid - 1].klo - r_k0 + 1 > W4_KSP;
+    unsigned char* sraw = meta_base + (size_t)W4_NST * W4_MB;   // [NSR][Src | ddSrc][S * 3][KSP] doubles
+    unsigned long long* s_sbar = s_bar + 32;                     // [NSR] "raw rows landed"
+    auto stage_sources = [&](int t) {  // issue the copies of slab t (ring warp)
+      if (r_wide || t >= nslab) return;
+      if (lane == 0) {
+        const int st = t % W4_NSR;
+        asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(s_sbar + st)),
+                     "r"((unsigned)W4_SRAW_STAGE) : "memory");
+        const int n0 = n_lo + t * S - 1;   // first time sample of the slab (0-based); rows past the grid are never used
+        unsigned char* d = sraw + (size_t)st * W4_SRAW_STAGE;
+        tma_box_g2s(d, p.tmaps, r_k0, (pt * v.NT + n0) * 3, s_sbar + st);
+        tma_box_g2s(d + W4_SRAW_STAGE / 2, p.tmaps + 1, r_k0, (lp * v.NT + n0) * 3, s_sbar + st);
+      }
+    };
+    // this metadata thread's wavenumber: spline weights of InterpolateSources (cmbmain.f90:1317-1320), ho^2/6 folded in
+    const double i_a0 = pc.a0, i_b0 = pc.b0, i_a3 = pc.a03h * pc.ho2o6, i_b3 = pc.b03h * pc.ho2o6;
+    const int i_ko = pc.klo - 1 - r_k0;      // column of source wavenumber klo - 1 in a staged row
     // rows [a, b] of the table -> ring.  The table is packed at the ring's row stride and slot = row mod R, so a run of
     // rows is ONE TMA bulk copy (two when it wraps around the end of the ring).  Slot 0 is mirrored behind slot R-1
     // (a pair reads rows i0 and i0 + 1 at a fixed offset): a run that continues through slot 0 simply copies one row
@@ -560,6 +625,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         released = max(released, t - W4_NST);
       }
       CK4(ck_c);
+      stage_sources(t + W4_SPD);
       const int2 w = s_win[t];
       // The windows slide towards lower rows (x falls with tau).  Rows [w.x, ...] may overwrite ring slots only
       // if the highest row still needed by the oldest slab not yet released stays within R rows of w.x.
@@ -577,6 +643,8 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
       CK4(ck_b);
     };
     if (ring_warp && !W4_PBAL) {
+#pragma unroll 1
+      for (int t = 0; t < W4_SPD; t++) stage_sources(t);
       for (int t = 0; t < nslab; t++) {
         ring_step(t, true);
         mbar_arrive(s_bar + (t % W4_NST));
@@ -601,23 +669,15 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         const int n = n_lo + tu * S + m_nn + (u % PPT) * PNN;
         const int pidx = m_pair + (u % PPT) * QC * PNN;
         const int par = tu % W4_NST;
-        unsigned char* mb = meta_base + (size_t)par * NPAIR * 48;
-        double2* m_af = reinterpret_cast<double2*>(mb);
-        double2* m_s01 = reinterpret_cast<double2*>(mb + NPAIR * 16);
-        Proj4Rec* m_rec = reinterpret_cast<Proj4Rec*>(mb + NPAIR * 32);
+        Proj4Rec* m_rec = reinterpret_cast<Proj4Rec*>(meta_base + (size_t)par * W4_MB);
         int moff = 0, jr = 127;
-        double ma = 0, mfac = 0, ms0 = 0, ms1 = 0, ms2 = 0;
+        double ma = 0;
         // slots still inside their window at time sample n: n2 >= n from above, n1 <= n from below
-#if CB200_W4_LEANMETA
         while (jhi[u] >= 0 && w_hi[u] < n) { jhi[u]--; w_hi[u] = (int)(wrow[max(jhi[u], 0)] >> 16); }
         while (jlo[u] > 0 && w_lo[u] <= n) { jlo[u]--; w_lo[u] = (int)(wrow[max(jlo[u] - 1, 0)] & 0xffffu); }
-#else
-        while (jhi[u] >= 0 && (int)(wrow[jhi[u]] >> 16) < n) jhi[u]--;
-        while (jlo[u] > 0 && (int)(wrow[jlo[u] - 1] & 0xffffu) <= n) jlo[u]--;
-#endif
 #if CB200_W4_UNSAFE_FREEMETA
         if (f_valid[u]) {  // timing experiment only (WRONG results): the consumers' floor with metadata that costs nothing
-          ma = 0.5; mfac = 0.01; ms0 = ms1 = ms2 = 1.0;
+          ma = 0.5;
           moff = ((n * 7 + m_qi * 3) % R) * rb;
           if (jlo[u] <= jhi[u]) jr = jlo[u] | ((jhi[u] + 1) << 8);
         }
@@ -627,33 +687,49 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
 #endif
           const double x = fabs(__dmul_rn(pc.q, __dsub_rn(tau0, f_tau[u])));
           double x0, x1, inv_h;
-#if CB200_W4_LEANMETA
-          int bi = w4_locate(p, x, x0, x1, inv_h);
-#else
-          int bi = lin_locate_desc(p.bseg, x, x0, x1, inv_h);
-#endif
-          if (bi > p.num_xx - 1) { bi = p.num_xx - 1; x0 = p.bx[bi - 1]; x1 = p.bx[bi]; inv_h = 1.0 / (x1 - x0); }
-          // interpolation weights (values, not indices): reciprocal multiplies instead of the reference's divisions
-          const double fac = x1 - x0;
+          int rs;
+          int bi = w4_locate(p, x, x0, x1, inv_h, rs);
+          if (bi > p.num_xx - 1) { bi = p.num_xx - 1; x0 = p.bx[bi - 1]; x1 = p.bx[bi]; inv_h = 1.0 / (x1 - x0); rs = p.bseg.n - 1; }
+          // interpolation weight (a value, not an index): reciprocal multiply instead of the reference's division.  The
+          // cubic term's (x1 - x0)^2 / 6 is a constant of the stretch: the consumers take it from p.h2o6[rs]
           ma = (x1 - x) * inv_h;
-          mfac = fac * fac * ma * (1.0 / 6.0);
-          if (n >= 2) {  // Source_q(1,:) is forced to zero (IntegrationVars_Init, cmbmain.f90:1380)
-            ms0 = (pc.a0 * f_s[u][0][0] + pc.b0 * f_s[u][0][1] + (pc.a03h * f_s[u][0][2] + pc.b03h * f_s[u][0][3]) * pc.ho2o6) * f_dtau[u];
-            ms1 = (pc.a0 * f_s[u][1][0] + pc.b0 * f_s[u][1][1] + (pc.a03h * f_s[u][1][2] + pc.b03h * f_s[u][1][3]) * pc.ho2o6) * f_dtau[u];
-            ms2 = (pc.a0 * f_s[u][2][0] + pc.b0 * f_s[u][2][1] + (pc.a03h * f_s[u][2][2] + pc.b03h * f_s[u][2][3]) * pc.ho2o6) * f_dtau[u];
-          }
           // ring slot of row bi - 1 without an integer division: float estimate of the quotient, corrected by one
           int sl = (bi - 1) - R * (int)((float)(bi - 1) * rinvR);
           sl += (sl < 0) ? R : 0;
           sl -= (sl >= R) ? R : 0;
-          moff = sl * rb;
+          moff = sl * rb + rs;   // rb is a multiple of 128: the stretch rides in the low bits
           if (jlo[u] <= jhi[u]) jr = jlo[u] | ((jhi[u] + 1) << 8);
         }
         if (m_live && tu < nslab) {
-          m_af[pidx] = make_double2(ma, mfac);
-          m_s01[pidx] = make_double2(ms0, ms1);
-          Proj4Rec rec; rec.s2 = ms2; rec.off = moff; rec.jr = jr;
+          Proj4Rec rec; rec.a = ma; rec.off = moff; rec.jr = jr;
           m_rec[pidx] = rec;
+          // the three sources at this wavenumber and time sample, weighted by dtau
+          double o[3] = {0.0, 0.0, 0.0};
+          const int stg_i = tu % W4_NSR;
+          if (!r_wide) mbar_wait(s_sbar + stg_i, (tu / W4_NSR) & 1);
+          if (f_valid[u] && !CB200_W4_UNSAFE_FREEMETA) {
+            if (!r_wide) {
+              const double* stg = reinterpret_cast<const double*>(sraw + (size_t)stg_i * W4_SRAW_STAGE) + ((m_nn + (u % PPT) * PNN) * 3) * W4_KSP + i_ko;
+#pragma unroll
+              for (int sI = 0; sI < 3; sI++) {
+                const double* Sp = stg + sI * W4_KSP;
+                const double* Dp = Sp + S * 3 * W4_KSP;
+                o[sI] = (i_a0 * Sp[0] + i_b0 * Sp[1] + (i_a3 * Dp[0] + i_b3 * Dp[1])) * f_dtau[u];
+              }
+            } else {
+#pragma unroll
+              for (int sI = 0; sI < 3; sI++) {
+                const double* Sp = src + ((size_t)(n - 1) * v.NSRC + sI) * v.NK + (pc.klo - 1);
+                const double* Dp = dds + ((size_t)(n - 1) * v.NSRC + sI) * v.NK + (pc.klo - 1);
+                o[sI] = (i_a0 * __ldg(Sp) + i_b0 * __ldg(Sp + 1) + (i_a3 * __ldg(Dp) + i_b3 * __ldg(Dp + 1))) * f_dtau[u];
+              }
+            }
+          }
+#if CB200_W4_UNSAFE_FREEMETA
+          o[0] = o[1] = o[2] = 1.0;
+#endif
+          reinterpret_cast<double2*>(meta_base + (size_t)par * W4_MB + NPAIR * 16)[pidx] = make_double2(o[0], o[1]);
+          reinterpret_cast<double*>(meta_base + (size_t)par * W4_MB + NPAIR * 32)[pidx] = o[2];
         }
       }
       // publish first, then issue the global loads of the next slab (their issue would only delay the consumers)
@@ -702,18 +778,18 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
       s_bar[16 + par] = 0;
     }
     CK4(ck_b);
-    const unsigned char* mb = meta_base + (size_t)par * NPAIR * 48;
-    const double2* m_af = reinterpret_cast<const double2*>(mb);
+    const unsigned char* mb = meta_base + (size_t)par * W4_MB;
+    const Proj4Rec* m_rec = reinterpret_cast<const Proj4Rec*>(mb);
     const double2* m_s01 = reinterpret_cast<const double2*>(mb + NPAIR * 16);
-    const Proj4Rec* m_rec = reinterpret_cast<const Proj4Rec*>(mb + NPAIR * 32);
+    const double* m_s2 = reinterpret_cast<const double*>(mb + NPAIR * 32);
     // quarter-warp r works on pair (q_r, n); every lane covers LK multipoles
 #pragma unroll W4_UNROLL
     for (int nn = W4_TS ? lh : 0; nn < S; nn += W4_TS ? 2 : 1) {
       const int n = n_base + nn;
       const int pr = nn * QC + myqi;
       const Proj4Rec rec = m_rec[pr];
-      const double2 af = m_af[pr];
       const double2 s01 = m_s01[pr];
+      const double s2v = m_s2[pr];
       // this lane's octets k with jlo <= lc + 16 k <= jhi (lc = li + 8 lh: the lane's first l-slot)
       const int klo = max((int)((rec.jr & 0xff) + ORND - lc) >> OSH, 0);
       const int khi1 = ((rec.jr >> 8) + ORND - lc) >> OSH;  // khi + 1 >= 0
@@ -729,14 +805,14 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
       }
       // cubic-spline value of j_l between the two nodes (cmbmain.f90:1515-1516), weights expanded:
       //   J = a j0 + b j1 + g0 p0 + g1 p1,  b = 1-a, g0 = -b fac (a+1), g1 = -b fac (2-a)
-      const double a2 = af.x, b2 = 1 - a2, t2 = -(b2 * af.y);
+      const double a2 = rec.a, b2 = 1 - a2, t2 = -(b2 * (a2 * p.h2o6[rec.off & 7]));
       const double g0 = t2 * (a2 + 1), g1 = t2 * (2 - a2);
       if (COUNT && p.triples) my_triples += __popc(m);
       // octets in batches of KB: the loads of a batch are in flight together, and a batch with no active lane
       // anywhere in the warp is skipped altogether (no loads, no FP64 issue)
       constexpr int KB = CB200_W4_KB;
       {
-        unsigned rp = ring_lane + rec.off;
+        unsigned rp = ring_lane + (rec.off & ~127);
         const unsigned U = __reduce_or_sync(0xffffffffu, m);  // octets with an active lane anywhere in the warp
         // octets [kf, kf + cnt) of a batch: loads first (in flight together), then the arithmetic
         auto octets = [&](const int kf, const int cnt) {
@@ -774,7 +850,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
               Jv = act ? Jv : 0.0;
               acc[k][0] = fma(s01.x, Jv, acc[k][0]);
               acc[k][1] = fma(s01.y, Jv, acc[k][1]);
-              if (k < K2) acc2[k < K2 ? k : 0] = fma(rec.s2, Jv, acc2[k < K2 ? k : 0]);
+              if (k < K2) acc2[k < K2 ? k : 0] = fma(s2v, Jv, acc2[k < K2 ? k : 0]);
 #endif
             }
           }

@@ -17,11 +17,11 @@ tau, dtau, n_tau, k, n_k = syn.build_grids(h, th)
 src = syn.make_sources(th, tau, k, pert).numpy()
 h.upload_sources(th, n_k, k, src)
 h.powers_resident(ip, al); h.timing(reset=True)
-best = 1e9
+best = 1e9; bs = 1e9
 for rep in range(3):
     h.powers_resident(ip, al)
     t = h.timing(reset=True)
-    best = min(best, 1e3 * t["ms_project"] / n)
+    best = min(best, 1e3 * t["ms_project"] / n); bs = min(bs, 1e3 * t["ms_spline"] / n)
 cls, der, st = h.powers(ip, al)
 ref = "/tmp/variants_base.npy"
 if name == "base":
@@ -29,7 +29,7 @@ if name == "base":
 else:
     b = np.load(ref); nz = b != 0
     err = float(np.abs(cls[nz] / b[nz] - 1).max())
-print("%%-10s %%8.1f us/point   max rel C_l diff vs base %%.2e" %% (name, best, err), flush=True)
+print("%%-10s %%8.1f us/point (+ spline / source-q %%5.1f)   max rel C_l diff vs base %%.2e" %% (name, best, bs, err), flush=True)
 ''' % (ROOT, ROOT)
 libs = [("base", os.path.join(ROOT, "cosmomc_b200", "libcosmob200.so"))]
 libs += [(os.path.basename(p)[4:-3], p) for p in sorted(glob.glob(os.path.join(ROOT, "variants", "lib_*.so")))]
