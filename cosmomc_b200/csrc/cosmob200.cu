@@ -18,6 +18,7 @@
 #include "background.cuh"
 #include "sn.cuh"
 #include "bk.cuh"
+#include "thermo.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -150,7 +151,9 @@ struct cb200_handle {
   int spline_kernel = 2;  // 1: one thread per row straight from global memory, 2: tiled through shared memory
   DevBuf<unsigned long long> d_ring_stats;
   DevBuf<unsigned char> w_fallback;  // [chunk][NQB] blocks left to the chunked kernel by project4_kernel
-  DevBuf<CUtensorMap> d_tmaps[2];    // per perturbation type: TMA descriptors of {sources, second derivatives}
+  DevBuf<CUtensorMap> d_tmaps[2];
+  DevBuf<double> w_th_work, w_th_in, w_th_out;   // thermal history: work tables [sample][point], input / result rows
+  DevBuf<int> w_th_status;    // per perturbation type: TMA descriptors of {sources, second derivatives}
   // resident outputs
   DevBuf<double> r_cl_lensed, r_cls_out, r_derived, r_icl, r_cl;
   DevBuf<int> r_status;
@@ -1460,6 +1463,64 @@ int cb200_background(cb200_handle* h, int npts, const double* bg, int nz, const 
     h->n_launches += 1;
     CB_CUDA(cudaMemcpyAsync(scalars, h->w_quad.p, sizeof(double) * npts * 3, cudaMemcpyDeviceToHost, s));
   }
+  CB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+  CB_API_END(h)
+}
+
+
+// ---- thermal history (thermo.cuh) ----
+int cb200_thermo(cb200_handle* h, int npts, const double* bg, const double* thermo_in, double* thermo_out, int* status) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (npts <= 0 || !bg || !thermo_in || !thermo_out) return fail(h, "thermo: bad arguments");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->stream;
+  cb200_handle::Scope sc(h, PH_BG);
+  const int C = std::min(npts, 16384);   // points per pass: 720 KB of work tables per point (11.8 GB at 16 384)
+  h->w_th_work.alloc((size_t)C * (3 * TH_NZ + 3 * TH_NTHERMO));
+  h->w_bg_in.alloc((size_t)C * NBG);
+  h->w_th_in.alloc((size_t)C * TH_NIN);
+  h->w_th_out.alloc((size_t)C * TH_NOUT);
+  h->w_th_status.alloc(C);
+  std::vector<int> st(C);
+  for (int c0 = 0; c0 < npts; c0 += C) {
+    const int np = std::min(C, npts - c0);
+    ThermoScratch W;
+    W.P = np;
+    W.xrec = h->w_th_work.p; W.dxrec = W.xrec + (size_t)np * TH_NZ; W.work = W.dxrec + (size_t)np * TH_NZ;
+    W.dotmu = W.work + (size_t)np * TH_NZ; W.sdotmu = W.dotmu + (size_t)np * TH_NTHERMO; W.sfac = W.sdotmu + (size_t)np * TH_NTHERMO;
+    CB_CUDA(cudaMemcpyAsync(h->w_bg_in.p, bg + (size_t)c0 * NBG, sizeof(double) * np * NBG, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(h->w_th_in.p, thermo_in + (size_t)c0 * TH_NIN, sizeof(double) * np * TH_NIN, cudaMemcpyHostToDevice, s));
+    thermo_recfast_kernel<<<(np + 63) / 64, 64, 0, s>>>(np, h->w_bg_in.p, h->w_th_in.p, h->bg_tables(), W, h->w_th_status.p);
+    CB_LAUNCH_CHECK();
+    thermo_init_kernel<<<(np + 63) / 64, 64, 0, s>>>(np, h->w_bg_in.p, h->w_th_in.p, h->bg_tables(), W, h->w_th_status.p, h->w_th_out.p);
+    CB_LAUNCH_CHECK();
+    h->n_launches += 2;
+    CB_CUDA(cudaMemcpyAsync(thermo_out + (size_t)c0 * TH_NOUT, h->w_th_out.p, sizeof(double) * np * TH_NOUT, cudaMemcpyDeviceToHost, s));
+    if (status) CB_CUDA(cudaMemcpyAsync(status + c0, h->w_th_status.p, sizeof(int) * np, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+  }
+  return 0;
+  CB_API_END(h)
+}
+
+int cb200_theta_to_background(cb200_handle* h, int npts, const double* cosmo, const double* nu, double tcmb, double* bg) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (npts <= 0 || !cosmo || !nu || !bg) return fail(h, "theta_to_background: bad arguments");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->stream;
+  cb200_handle::Scope sc(h, PH_BG);
+  h->w_bg_in.alloc((size_t)npts * NBG);
+  h->w_th_in.alloc((size_t)npts * 16);
+  CB_CUDA(cudaMemcpyAsync(h->w_bg_in.p, bg, sizeof(double) * npts * NBG, cudaMemcpyHostToDevice, s));   // keeps rdrag (bg[15])
+  CB_CUDA(cudaMemcpyAsync(h->w_th_in.p, cosmo, sizeof(double) * npts * 8, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(h->w_th_in.p + (size_t)npts * 8, nu, sizeof(double) * npts * 8, cudaMemcpyHostToDevice, s));
+  thermo_theta_kernel<<<(npts + 63) / 64, 64, 0, s>>>(npts, h->w_th_in.p, h->w_th_in.p + (size_t)npts * 8, tcmb, h->bg_tables(), h->w_bg_in.p);
+  CB_LAUNCH_CHECK();
+  h->n_launches += 1;
+  CB_CUDA(cudaMemcpyAsync(bg, h->w_bg_in.p, sizeof(double) * npts * NBG, cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
   return 0;
   CB_API_END(h)

@@ -29,7 +29,7 @@ EXPORTS = [
     "cb200_timer_start", "cb200_timer_stop", "cb200_measure_fp64_peaks", "cb200_config_size", "cb200_abi_version",
     "cb200_upload_sources_packed",
     "cb200_powers_shared", "cb200_like_set_bk_foregrounds", "cb200_background", "cb200_set_background", "cb200_like_add_bao", "cb200_like_add_hst", "cb200_like_add_sn",
-    "cb200_eval_batch", "cb200_test_like_batch",
+    "cb200_eval_batch", "cb200_test_like_batch", "cb200_thermo", "cb200_theta_to_background",
 ]
 
 
@@ -91,6 +91,8 @@ def load(path=None):
                            "(nvcc, sm_100a). There is no CPU fallback." % path)
     L = C.CDLL(path)
     L.cb200_last_error.restype = C.c_char_p
+    L.cb200_thermo.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_ip]
+    L.cb200_theta_to_background.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, C.c_double, c_dp]
     L.cb200_last_error.argtypes = [C.c_void_p]
     L.cb200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
     L.cb200_destroy.argtypes = [C.c_void_p]
@@ -410,6 +412,40 @@ class Handle:
         self._check(self.L.cb200_background(self.h, npts, _pd(bg), len(z), _pd(z), _pd(DA), _pd(H), _pd(sc)),
                     "background")
         return (DA, H, sc) if want_scalars else (DA, H)
+
+    THERMO_DERIVED = ["age", "zstar", "rstar", "thetastar", "DAstar", "zdrag", "rdrag", "kd", "thetad", "zeq", "keq",
+                      "thetaeq", "thetarseq"]
+
+    def thermo(self, bg, yhe, zre=0.0, optical_depth=0.0, max_eta_k=14000.0, want_tensors=False, transfer_kmax_h=5.0,
+               accuracy_boost=1.0):
+        """Thermal history of every bg row (RECFAST, reionisation, inithermo): returns (out [npts][32], status [npts]);
+        out[:, :12] = tau0, taurst, taurend, tau_start, tau_complete, dtaurec, tau_maxvis, zre, z_star, z_drag,
+        actual_opt_depth, status; out[:, 12:25] = ThermoDerivedParams in the order of THERMO_DERIVED."""
+        bg = _d(bg).reshape(-1, 16)
+        npts = len(bg)
+        tin = np.zeros((npts, 8))
+        tin[:, 0], tin[:, 1], tin[:, 2] = yhe, zre, optical_depth
+        tin[:, 3], tin[:, 4], tin[:, 5], tin[:, 6] = max_eta_k, 1.0 if want_tensors else 0.0, transfer_kmax_h, accuracy_boost
+        out = np.zeros((npts, 32))
+        st = np.zeros(npts, dtype=np.int32)
+        self._check(self.L.cb200_thermo(self.h, npts, _pd(bg), _pd(tin), _pd(out), _pi(st)), "thermo")
+        return out, st
+
+    def theta_to_background(self, ombh2, omch2, theta100, omnuh2, nu_split, omk=0.0, w=-1.0, H0_min=20.0, H0_max=100.0,
+                            tcmb=2.7255, rdrag=None):
+        """theta_MC -> H0 by the reference's bisection; returns bg [npts][16] (H0 = 0 rows: theta out of range).
+        nu_split [npts][8] or [8] = bg[7:15] (massless degeneracy, eigenstates, degeneracies, mass fractions)."""
+        ombh2 = _d(np.atleast_1d(ombh2))
+        npts = len(ombh2)
+        cs = np.zeros((npts, 8))
+        cs[:, 0], cs[:, 1], cs[:, 2], cs[:, 3], cs[:, 4], cs[:, 5] = ombh2, omch2, omnuh2, omk, w, theta100
+        cs[:, 6], cs[:, 7] = H0_min, H0_max
+        nu = np.ascontiguousarray(np.broadcast_to(_d(nu_split).reshape(-1, 8), (npts, 8)))
+        bg = np.zeros((npts, 16))
+        if rdrag is not None:
+            bg[:, 15] = rdrag
+        self._check(self.L.cb200_theta_to_background(self.h, npts, _pd(cs), _pd(nu), float(tcmb), _pd(bg)), "theta_to_background")
+        return bg
 
     def set_background(self, bg, first=0):
         bg = _d(bg).reshape(-1, 16)

@@ -188,6 +188,29 @@ int cb200_like_set_bk_foregrounds(cb200_handle* h, int like_id, int nmaps, const
  *   DA, H [npts][nz] (Mpc, Mpc^-1; NULL to skip), scalars [npts][3] = tau0, age/Gyr, CosmomcTheta (NULL to skip). */
 int cb200_background(cb200_handle* h, int npts, const double* bg, int nz, const double* z, double* DA, double* H,
                      double* scalars);
+/* ---- thermal history ---------------------------------------------------------------------
+ * cb200_thermo replaces, for a batch, what CAMB does between CAMBParams_Set and the source ODEs
+ * (camb/modules.f90:376-400 Nnow / akthom / adotrad, camb/reionization.f90:139-199 Reionization_Init incl. the
+ * z_re-from-optical-depth bisection that CAMB_GetZreFromTau drives (source/Calculator_CAMB.f90 GetZreFromTau),
+ * camb/recfast.f90:460-722 Recombination_init, camb/modules.f90:2682-2992 inithermo) and returns what the rest of the
+ * path consumes: the time-grid scalars of cb200_upload_sources' `thermo` rows and ThermoDerivedParams
+ * (Theory%derived_parameters: r_drag for source/bao.f90:237-248, z_star, theta_star, ... of the chain's derived block).
+ *   bg         [npts][16]  as for cb200_background
+ *   thermo_in  [npts][8]   Y_He, z_re (used when optical depth = 0), optical depth tau (> 0: z_re by bisection),
+ *                          Max_eta_k, WantTensors, Transfer kmax in h/Mpc (0: WantTransfer = F; CosmoMC with
+ *                          use_nonlinear_lensing: 5), AccuracyBoost (0 = 1), reserved
+ *   thermo_out [npts][32]  tau0, taurst, taurend, reionisation tau_start, tau_complete, dtaurec, tau_maxvis, z_re, z_star,
+ *                          z_drag, actual_opt_depth, status, then ThermoDerivedParams(1:13) = age/Gyr, zstar, rstar,
+ *                          100 thetastar, DAstar/Gpc, zdrag, rdrag, kD, 100 thetaD, zEQ, kEQ, 100 thetaEQ, 100 theta_rs_EQ
+ *   status     [npts]      0, 1 = error_reionization, 2 = error_recombination (camb/constants.f90 Errors); may be NULL */
+int cb200_thermo(cb200_handle* h, int npts, const double* bg, const double* thermo_in, double* thermo_out, int* status);
+/* theta -> H0: the bisection of ThetaParameterization%ParamArrayToTheoryParams on CMBToTheta
+ * (source/CosmologyParameterizations.f90:134-176, camb/modules.f90:729-751 CosmomcTheta).
+ *   cosmo [npts][8] = ombh2, omch2, omnuh2, omk, w, 100 theta_MC, H0_min, H0_max ; nu [npts][8] = bg[7..15) (the neutrino
+ *   split, independent of H0) ; bg [npts][16] in: only bg[15] (rdrag) is kept, out: the solved rows (all zero but bg[15]
+ *   when theta is out of range: H0 = 0, the point is rejected as in the reference). */
+int cb200_theta_to_background(cb200_handle* h, int npts, const double* cosmo, const double* nu, double tcmb, double* bg);
+
 /* make bg resident for points [first, first+npts): input of the background likelihoods in cb200_loglike_batch
  * (replaces Calculator%SetParamsForBackground / GetNewBackgroundData, source/Calculator_CAMB.f90:151-177) */
 int cb200_set_background(cb200_handle* h, int first, int npts, const double* bg);

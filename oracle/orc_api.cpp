@@ -5,6 +5,7 @@
 #include "orc_cmb.hpp"
 #include "orc_like.hpp"
 #include "orc_bg.hpp"
+#include "orc_thermo.hpp"
 #include <memory>
 
 using namespace orc;
@@ -273,6 +274,47 @@ int orc_nu_table(double* r1, double* dr1, double* dlnam) {
   g_nu_table.init();
   for (int i = 0; i < NuTable::nrhopn; i++) { r1[i] = g_nu_table.r1[i + 1]; dr1[i] = g_nu_table.dr1[i + 1]; }
   *dlnam = g_nu_table.dlnam;
+  return 0;
+  ORC_CATCH
+}
+}  // extern "C"
+
+extern "C" {
+// ---- thermal history (orc_thermo.hpp).  in[8] = yhe, zre (used when optical_depth = 0), optical_depth (> 0: zre by
+// bisection, Reionization_zreFromOptDepth), max_eta_k, want_tensors, transfer_kmax [h/Mpc; 0: WantTransfer = F],
+// AccuracyBoost, reserved.  out[32] = tau0, taurst, taurend, reion tau_start, tau_complete, dtaurec, tau_maxvis, zre,
+// z_star, z_drag, actual_opt_depth, status, derived[13] from [12], RECFAST derivative evaluations at [25].
+// tables (optional) [4][20000]: xe, dotmu, emmu, cs2 of inithermo.
+int orc_thermo(const double* bg, const double* in, double* out, double* tables) {
+  ORC_TRY
+  g_nu_table.init();
+  Background B;
+  B.set(bg, &g_nu_table);
+  Thermo T;
+  ThermoOut o = T.run(B, in[0], in[1], in[2], in[3], in[4] != 0, in[5], in[6] > 0 ? in[6] : 1.0);
+  for (int i = 0; i < 32; i++) out[i] = 0;
+  out[0] = o.tau0; out[1] = o.taurst; out[2] = o.taurend; out[3] = o.tau_start; out[4] = o.tau_complete; out[5] = o.dtaurec;
+  out[6] = o.tau_maxvis; out[7] = o.zre; out[8] = o.z_star; out[9] = o.z_drag; out[10] = o.actual_opt_depth; out[11] = o.status;
+  for (int i = 0; i < 13; i++) out[12 + i] = o.derived[i];
+  out[25] = (double)T.rec.n_fcn;
+  if (tables && o.status == 0) {
+    for (int i = 0; i < Thermo::nthermo; i++) {
+      tables[i] = T.xe[i + 1]; tables[Thermo::nthermo + i] = T.dotmu[i + 1];
+      tables[2 * Thermo::nthermo + i] = T.emmu[i + 1]; tables[3 * Thermo::nthermo + i] = T.cs2[i + 1];
+    }
+  }
+  return 0;
+  ORC_CATCH
+}
+// xe of RECFAST alone at the given scale factors (Recombination_xe)
+int orc_recfast_xe(const double* bg, double yhe, int n, const double* a, double* xe) {
+  ORC_TRY
+  g_nu_table.init();
+  Background B;
+  B.set(bg, &g_nu_table);
+  Recfast R;
+  R.init(B, yhe);
+  for (int i = 0; i < n; i++) xe[i] = R.xe(a[i]);
   return 0;
   ORC_CATCH
 }

@@ -633,3 +633,66 @@ def bk_loglike(plan, cls, P):
     chi2 = cmblikes_chisq(plan.nmaps, plan.nbins_used, plan.cl_use_index, plan.like_approx, plan.noise, plan.chat,
                           plan.sqrt_fid, plan.invcov, binned)
     return chi2 / 2
+
+
+# ---------------------------------------------------------------- thermal history (orc_thermo.hpp)
+THERMO_DERIVED = ["age", "zstar", "rstar", "thetastar", "DAstar", "zdrag", "rdrag", "kd", "thetad", "zeq", "keq",
+                  "thetaeq", "thetarseq"]
+
+
+def thermo(bg, yhe, zre=0.0, optical_depth=0.0, max_eta_k=14000.0, want_tensors=False, transfer_kmax_h=5.0,
+           accuracy_boost=1.0, tables=False):
+    """CAMBParams_Set tail + cmbmain set-up + inithermo (camb/modules.f90:2682-2992) for one bg[16] row.
+    optical_depth > 0: the reionisation redshift comes from the bisection of Reionization_zreFromOptDepth.
+    Returns a dict (tau0, taurst, taurend, tau_start, tau_complete, dtaurec, tau_maxvis, zre, z_star, z_drag,
+    actual_opt_depth, status, derived{...}, n_fcn[, tables [4][20000] = xe, dotmu, emmu, cs2])."""
+    L = lib()
+    L.orc_thermo.restype = C.c_int
+    inp = _d([yhe, zre, optical_depth, max_eta_k, 1.0 if want_tensors else 0.0, transfer_kmax_h, accuracy_boost, 0.0])
+    out = np.zeros(32)
+    tab = np.zeros((4, 20000)) if tables else None
+    if L.orc_thermo(_p(_d(bg)), _p(inp), _p(out), _p(tab) if tables else None) != 0:
+        raise RuntimeError("orc_thermo failed")
+    keys = ["tau0", "taurst", "taurend", "tau_start", "tau_complete", "dtaurec", "tau_maxvis", "zre", "z_star", "z_drag",
+            "actual_opt_depth", "status"]
+    r = {k: out[i] for i, k in enumerate(keys)}
+    r["status"] = int(r["status"])
+    r["derived"] = {k: out[12 + i] for i, k in enumerate(THERMO_DERIVED)}
+    r["n_fcn"] = int(out[25])
+    if tables:
+        r["tables"] = tab
+    return r
+
+
+def recfast_xe(bg, yhe, a):
+    """Recombination_xe (camb/recfast.f90:434-456) after Recombination_init, at scale factors a."""
+    L = lib()
+    L.orc_recfast_xe.restype = C.c_int
+    L.orc_recfast_xe.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    a = _d(np.atleast_1d(a))
+    xe = np.zeros_like(a)
+    if L.orc_recfast_xe(_p(_d(bg)), float(yhe), len(a), _p(a), _p(xe)) != 0:
+        raise RuntimeError("orc_recfast_xe failed")
+    return xe
+
+
+def h0_from_theta(theta100, make_bg, H0_min=20.0, H0_max=100.0):
+    """ThetaParameterization%ParamArrayToTheoryParams (source/CosmologyParameterizations.f90:134-176): bisection on H0
+    until successive CosmomcTheta values differ by < 1e-7.  make_bg(H0) -> bg[16] row.  Returns H0 (0: out of range)."""
+    DA = theta100 / 100
+    theta = lambda H0: background(make_bg(H0), [0.0])[2][2]
+    try_b, try_t = H0_min, H0_max
+    D_b, D_t = theta(try_b), theta(try_t)
+    if DA < D_b or DA > D_t:
+        return 0.0
+    lasttry = -1.0
+    while True:
+        H0 = (try_b + try_t) / 2
+        D_try = theta(H0)
+        if D_try < DA:
+            try_b = (try_b + try_t) / 2
+        else:
+            try_t = (try_b + try_t) / 2
+        if abs(D_try - lasttry) < 1e-7:
+            return H0
+        lasttry = D_try
