@@ -188,7 +188,6 @@ __device__ __forceinline__ int w4_locate(const Proj4Params& p, double v, double&
 #define CB200_W4_PBAL 0   // 1: every producer warp (the ring warp too) computes the metadata of ONE time sample of the slab
 #endif
 constexpr bool W4_PBAL = CB200_W4_PBAL != 0;
-static_assert(!W4_PBAL, "balanced producers were dropped with the in-kernel source staging");
 static_assert(!W4_PBAL || (W4_S == W4_NPW && W4_QC <= 32 && W4_MG == 1 && W4_MS == 1), "balanced producers: one time sample per producer warp");
 #ifndef CB200_W4_UNSAFE_FREEMETA
 #define CB200_W4_UNSAFE_FREEMETA 0    // timing experiment only: WRONG results
@@ -649,6 +648,10 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         ring_step(t, true);
         mbar_arrive(s_bar + (t % W4_NST));
       }
+    }
+    if (ring_warp && W4_PBAL) {
+#pragma unroll 1
+      for (int t = 0; t < W4_SPD; t++) stage_sources(t);
     }
     const bool m_role = W4_PBAL || !ring_warp;   // this warp computes metadata
     if (m_role && m_grp * MS < nslab) prefetch();

@@ -204,6 +204,33 @@ class LikeCalculator:
     def set_background(self, bg, first=0):
         self.handle.set_background(bg, first=first)
 
+    def set_background_from_params(self, P, yhe=0.2453985, H0_min=20.0, H0_max=100.0, first=0, **nu_kw):
+        """What ThetaParameterization%ParamArrayToTheoryParams + CAMB's thermal history do for every row of P before a
+        background likelihood is called (source/CosmologyParameterizations.f90:114-187, camb/modules.f90:2682-2992), on
+        the device: theta_MC -> H0 (cb200_theta_to_background), then RECFAST / inithermo (cb200_thermo) for r_drag, then
+        the rows are made resident (cb200_set_background).  Columns used: omegabh2, omegach2, theta, tau[, omegak, mnu,
+        nnu, w].  Y_He is an input (the BBN-consistency table of the golden run, PArthENoPE 880.2, does not ship).
+        Returns (bg [B][16], thermo_out [B][32], ok [B]); rows with ok = False (theta out of range, thermal-history
+        error) must be rejected by the caller as the reference rejects them (H0 = 0 / global_error_flag)."""
+        from . import params as prm
+        P = np.atleast_2d(np.asarray(P, dtype=np.float64))
+        col = lambda n, d=None: P[:, self.names.index(n)] if n in self.names else np.full(len(P), d)
+        mnu, nnu = col("mnu", 0.06), col("nnu", 3.046)
+        if np.ptp(mnu) or np.ptp(nnu):
+            raise NotImplementedError("the neutrino split is built once per batch: mnu and nnu must be common to the rows")
+        ref = prm.cmb_to_background(0.022, 0.12, 70.0, mnu=float(mnu[0]), nnu=float(nnu[0]), **nu_kw)
+        omnuh2 = ref[3] * 0.7 ** 2
+        bg = self.handle.theta_to_background(col("omegabh2"), col("omegach2"), col("theta"), omnuh2, ref[7:15],
+                                             omk=col("omegak", 0.0), w=col("w", -1.0), H0_min=H0_min, H0_max=H0_max)
+        ok = bg[:, 0] > 0
+        safe = np.where(ok[:, None], bg, ref[None, :])
+        th, st = self.handle.thermo(safe, yhe, optical_depth=col("tau", 0.0))
+        ok &= st == 0
+        bg[:, 15] = np.where(ok, th[:, 18], 0.0)
+        safe[:, 15] = np.where(ok, th[:, 18], 147.0)
+        self.handle.set_background(safe, first=first)
+        return bg, th, ok
+
     # ---- the batched GetLogLike
     def full_params(self, varied):
         """[B][n_varying] -> [B][num_params] with the fixed parameters at their `param[...]` values."""

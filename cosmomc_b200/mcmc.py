@@ -259,3 +259,114 @@ def read_theory_cl(path):
     """Inverse of write_theory_cl: returns (L[int], cls[n_spectra][len(L)])."""
     a = np.atleast_2d(np.loadtxt(path))
     return a[:, 0].astype(int), a[:, 1:].T.copy()
+
+
+# ---- derived-parameter block and the .minimum file (SURVEY 8f-3) -------------------------------------------------
+# ThermoDerivedParams order (camb/modules.f90:244-246; cb200_thermo out[12:25])
+THERMO_DERIVED = ["age", "zstar", "rstar", "thetastar", "DAstar", "zdrag", "rdrag", "kd", "thetad", "zeq", "keq",
+                  "thetaeq", "thetarseq"]
+DERIVED_CL = (40, 220, 810, 1420, 2000)
+
+
+def calc_derived_params(cmb, thermo_derived, rms_deflect, cl_TT=None, sigma8=0.0, pivot_k=0.05, bbn_dh=None,
+                        background_outputs=(), lss_outputs=(), tensor=None):
+    """TP_CalcDerivedParams (source/CosmologyParameterizations.f90:189-272) for ONE point, in the reference's column
+    order: H0, omegal, omegam, omegamh2, omeganuh2, omegamh3, sigma8, S8, s8omegamp5, s8omegamp25, s8h5, rdragh,
+    rmsdeflect, zrei, A, clamp, DL40..DL2000, ns02, yheused, YpBBN[, DHBBN], ThermoDerivedParams(1:13), then
+    CAMB's background outputs (H(z), D_M(z) pairs), then (f sigma8, sigma8)(z) pairs, then the six tensor entries.
+    cmb: dict with H0, omv, omdm, omb, omdmh2, ombh2, omnuh2, h, zre, tau, logA, ns, nrun, nrunrun, yhe.
+    sigma8 comes from CAMB's transfer functions (not built: pass the CPU path's value)."""
+    omm = cmb["omdm"] + cmb["omb"]
+    d = [cmb["H0"], cmb["omv"], omm, cmb["omdmh2"] + cmb["ombh2"], cmb["omnuh2"], (cmb["omdmh2"] + cmb["ombh2"]) * cmb["h"],
+         sigma8, sigma8 * (omm / 0.3) ** 0.5, sigma8 * omm ** 0.5, sigma8 * omm ** 0.25, sigma8 / cmb["h"] ** 0.5,
+         thermo_derived[6] * cmb["H0"] / 100, rms_deflect, cmb["zre"]]
+    As9 = 1e-10 * np.exp(cmb["logA"]) * 1e9
+    d += [As9, As9 * np.exp(-2 * cmb["tau"])]
+    d += [float(cl_TT[L]) if cl_TT is not None else 0.0 for L in DERIVED_CL]
+    lograt = np.log(0.002 / pivot_k)
+    d.append(cmb["ns"] + cmb.get("nrun", 0.0) * lograt + cmb.get("nrunrun", 0.0) * lograt ** 2 / 2)
+    m_H, not4 = 1.673575e-27, 3.9715          # GetYpBBN (source/bbn.f90:26-36)
+    m_He = m_H * not4
+    d += [cmb["yhe"], 4 * m_H * cmb["yhe"] / (m_He - cmb["yhe"] * (m_He - 4 * m_H))]
+    if bbn_dh is not None:
+        d.append(bbn_dh)
+    d += [float(x) for x in thermo_derived[:13]]
+    d += [float(x) for x in background_outputs]
+    d += [float(x) for x in lss_outputs]
+    if tensor is not None:
+        d += [float(x) for x in tensor]
+    return np.array(d)
+
+
+def _list_directed_real(v):
+    """List-directed output of a double as the build that wrote the reference's golden files prints it (Intel
+    Fortran: G24.15E3): F editing with 15 significant digits and 5 trailing blanks for 0.1 <= |v| < 1e15, E24.15E3 else."""
+    v = float(v)
+    a = abs(v)
+    if v == 0.0:
+        return "  0.000000000000000E+000"
+    if 0.1 <= a < 1e15:
+        k = int(np.floor(np.log10(a))) + 1 if a >= 1 else 0
+        s = "%.*f" % (15 - k, a)
+        if len(s.split(".")[0]) > max(k, 1):       # rounding carried into a new leading digit
+            k += 1
+            s = "%.*f" % (15 - k, a)
+        return (("-" if v < 0 else "") + s).rjust(19) + " " * 5
+    mant, exp = ("%.14e" % a).split("e")
+    e = int(exp) + 1
+    return (("-" if v < 0 else "") + "0." + mant.replace(".", "") + "E%s%03d" % ("+" if e >= 0 else "-", abs(e))).rjust(24)
+
+
+def write_minimum(path, loglike, values, varying, names, labels, derived=(), derived_names=(), derived_labels=(),
+                  like_contribs=(), weight=None):
+    """`<root>.minimum` (TTheoryLike_WriteParamsHumanText, source/calclike.f90:208-236,436-462; called from
+    source/driver.F90:230): -log(Like) and chi-sq, the varied parameters, the fixed ones, the derived block - each line
+    `(1I5,1E15.7,"   ",1A22)` + label - and one `(2f11.3)   <type>: <tag> = <name> <version>` line per likelihood
+    (WriteLikelihoodContribs, source/GeneralTypes.f90:562-583).  values / varying / names / labels: every base parameter in
+    index order (1-based numbering in the file).  like_contribs: (-lnL, type, tag, name, version) tuples.
+    tests/test_writers.py regenerates the reference's golden .minimum from its own contents byte for byte."""
+    with open(path, "w") as f:
+        if weight is not None:
+            f.write("  weight    = " + _list_directed_real(weight) + "\n")
+        f.write(" -log(Like) = " + _list_directed_real(loglike) + "\n")
+        f.write("  chi-sq    = " + _list_directed_real(loglike * 2) + "\n")
+        f.write(" \n")
+        n = len(values)
+        for used in (True, False):
+            for i in range(n):
+                if bool(varying[i]) == used:
+                    f.write("%5d%s   %-22s%s\n" % (i + 1, _fortran_e(values[i], 15, 7), names[i][:22], labels[i].rstrip()))
+            f.write(" \n")
+        for i in range(len(derived)):
+            f.write("%5d%s   %-22s%s\n" % (n + i + 1, _fortran_e(derived[i], 15, 7), derived_names[i][:22], derived_labels[i].rstrip()))
+        f.write(" \n")
+        f.write(" -log(Like)     chi-sq   data\n")
+        for L in like_contribs:
+            v, typ, tag, name, version = (list(L) + [""] * 5)[:5]
+            tagname = name.strip()
+            if tag and tag != name:
+                tagname = tag + " = " + tagname
+            line = "%11.3f%11.3f" % (v, v * 2) + "   " + typ.strip() + ": " + tagname
+            if version:
+                line += " " + version.strip()
+            f.write(line + "\n")
+
+
+def read_minimum(path):
+    """Parse a .minimum file back into (loglike, rows, like_contribs); rows = [(index, value, name, label, block)] with
+    block 0 = varied, 1 = fixed, 2 = derived."""
+    lines = open(path).read().split("\n")
+    loglike = float(lines[0].split("=")[1])
+    rows, contribs, block, i = [], [], 0, 3
+    while i < len(lines) and not lines[i].startswith(" -log(Like)     chi-sq"):
+        ln = lines[i]
+        if ln.strip() == "":
+            block += 1
+        else:
+            rows.append((int(ln[:5]), float(ln[5:20]), ln[23:45].rstrip(), ln[45:], block))
+        i += 1
+    for ln in lines[i + 1:]:
+        if ln.strip():
+            typ, rest = ln[25:].split(": ", 1)
+            contribs.append((float(ln[:11]), typ, rest))
+    return loglike, rows, contribs

@@ -109,3 +109,39 @@ def test_loglike_matches_get_loglike(tmp_path):
     assert ll[1] == 1e30
     assert np.allclose(likes[[0, 2]], want_likes[[0, 2]], rtol=1e-12)
     assert np.abs(ll[[0, 2]] - want[[0, 2]]).max() < 1e-9 and np.allclose(prior[[0, 2]], wprior[[0, 2]], rtol=1e-13)
+
+
+@pytest.mark.gpu
+def test_background_from_params_feeds_bao_with_device_rdrag(tmp_path):
+    """theta -> H0 -> thermal history -> r_drag -> BAO / H0 likelihoods, all on the device, against the oracle chain
+    (h0_from_theta, orc_thermo, bao_loglike, hst_loglike) - the data flow of a background-only CosmoMC run."""
+    import pyoracle as o
+    from cosmomc_b200 import params as prm
+    body = """
+use_BAO = T
+bao_dataset[DR12BAO] = %s/DR12/sdss_DR12Consensus_bao.dataset
+DEFAULT(%s/batch3/HST_Riess2018.ini)
+DEFAULT(%s/batch3/params_CMB_defaults.ini)
+""" % (DATA, DATA, DATA)
+    c = make_calc(tmp_path, body, handle_kw=dict(max_points=4, lmax_computed_cl=0))
+    assert c.like_names() == ["H073p45", "DR12BAO"]
+    i = c.names.index
+    P = np.tile(c.center, (3, 1))
+    P[:, i("omegabh2")] = [0.02237737, 0.0221, 0.0226]
+    P[:, i("omegach2")] = [0.1201035, 0.1180, 0.1230]
+    P[:, i("theta")] = [1.040920, 1.0405, 3.0]           # the last one has no H0 in [20, 100]
+    P[:, i("tau")] = [0.05430138, 0.06, 0.05]
+    bg, th, ok = c.set_background_from_params(P, yhe=0.2453985)
+    assert ok.tolist() == [True, True, False] and bg[2, 0] == 0
+    ll, tot, st = c.handle.loglike_batch(3, np.zeros((3, max(1, c.n_nuis))))
+    for k in range(2):
+        mk = lambda h: prm.cmb_to_background(P[k, i("omegabh2")], P[k, i("omegach2")], h)
+        H0 = o.h0_from_theta(P[k, i("theta")], mk)
+        assert abs(bg[k, 0] / H0 - 1) < 1e-9
+        r = o.thermo(mk(H0), 0.2453985, optical_depth=P[k, i("tau")])
+        assert abs(bg[k, 15] / r["derived"]["rdrag"] - 1) < 2e-6
+        kinds = {kind: plan for kind, tag, plan, _ in c.likes}
+        bao, hst = kinds["bao"], kinds["hst"]
+        want = (o.hst_loglike(bg[k], hst.H0, hst.H0_err) +
+                o.bao_loglike(bg[k], bg[k, 15], bao.rs_rescale, bao.types, bao.z, bao.obs, bao.invcov))
+        assert abs(tot[k] - want) < 1e-6, (tot[k], want)

@@ -1,0 +1,58 @@
+"""CPU tests: the `.minimum` writer and the derived-parameter block against the reference's golden
+data/base_plikHM_TTTEEE_lowl_lowE.minimum (fixture copy under tests/golden/data)."""
+import os
+
+import numpy as np
+
+import helpers as H
+from cosmomc_b200 import mcmc, params as P
+
+GOLD = os.path.join(H.ROOT, "tests", "golden", "data", "base_plikHM_TTTEEE_lowl_lowE.minimum")
+
+
+def test_minimum_writer_reproduces_the_golden_file_byte_for_byte(tmp_path):
+    loglike, rows, contribs = mcmc.read_minimum(GOLD)
+    base = sorted([r for r in rows if r[4] < 2])
+    derived = [r for r in rows if r[4] == 2]
+    assert [r[0] for r in base] == list(range(1, len(base) + 1)) and derived[0][0] == len(base) + 1
+    out = tmp_path / "x.minimum"
+    likes = []
+    g = {r[2]: r[1] for r in rows}
+    for v, typ, rest in contribs:
+        tag, name = rest.split(" = ", 1)
+        # the printed -lnL carries three decimals; the chi2_<tag> derived column of the same file has seven figures
+        # (both are roundings of the same number: take the seven-figure one, kept inside the printed value's interval)
+        likes.append((v + float(np.clip(g["chi2_" + tag] / 2 - v, -4.9e-4, 4.9e-4)), typ, tag, name, ""))
+    mcmc.write_minimum(out, loglike, [r[1] for r in base], [r[4] == 0 for r in base], [r[2] for r in base],
+                       [r[3] for r in base], [r[1] for r in derived], [r[2] for r in derived], [r[3] for r in derived], likes)
+    got, want = open(out, "rb").read(), open(GOLD, "rb").read()
+    assert got == want
+
+
+def test_list_directed_real_matches_the_golden_header():
+    assert mcmc._list_directed_real(1382.88563166157) == "   1382.88563166157     "
+    assert mcmc._list_directed_real(2765.77126332314) == "   2765.77126332314     "
+    assert mcmc._list_directed_real(0.5).strip() == "0.500000000000000" and len(mcmc._list_directed_real(-12.25)) == 24
+
+
+def test_derived_block_order_and_values_match_the_golden_minimum():
+    import pyoracle as o
+    _, rows, _ = mcmc.read_minimum(GOLD)
+    g = {r[2]: r[1] for r in rows}
+    bg = P.cmb_to_background(g["omegabh2"], g["omegach2"], g["H0"])
+    th = o.thermo(bg, g["yheused"], optical_depth=g["tau"])
+    h = g["H0"] / 100
+    omnuh2 = bg[3] * h * h
+    cmb = dict(H0=g["H0"], h=h, omv=bg[4], omb=bg[1], omdm=bg[2] + bg[3], ombh2=g["omegabh2"], omdmh2=g["omegach2"] + omnuh2,
+               omnuh2=omnuh2, zre=th["zre"], tau=g["tau"], logA=g["logA"], ns=g["ns"], yhe=g["yheused"])
+    cl = np.zeros(2001)
+    for L, k in zip(mcmc.DERIVED_CL, ("DL40", "DL220", "DL810", "DL1420", "DL2000")):
+        cl[L] = g[k]
+    bgout = [g[k] for k in ("Hubble015", "DM015", "Hubble038", "DM038", "Hubble051", "DM051", "Hubble061", "DM061",
+                            "Hubble233", "DM233")]
+    d = mcmc.calc_derived_params(cmb, list(th["derived"].values()), g["rmsdeflect"], cl_TT=cl, sigma8=g["sigma8"],
+                                 bbn_dh=g["DHBBN"], background_outputs=bgout)
+    names = [r[2] for r in rows if r[4] == 2]
+    want = np.array([g[n] for n in names[:len(d)]])
+    assert names[:3] == ["H0", "omegal", "omegam"] and names[len(d) - 1] == "DM233"
+    assert np.abs(d / want - 1).max() < 2e-6, dict(zip(names, d / want - 1))

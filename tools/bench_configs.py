@@ -88,8 +88,32 @@ def config2(args):
              + o.hst_loglike(bg[i], hst.H0, hst.H0_err))
         dl = max(dl, abs(w - tot[i]))
     dt = time.perf_counter() - t0
+    # the same step with r_drag from the batched thermal history on the GPU (RECFAST + inithermo per point)
+    tau_re = np.clip(rng.normal(0.0543, 0.007, npts), 0.02, None)
+    bg_th = bg.copy()
+
+    def step_thermo():
+        th, sth = h.thermo(bg, 0.2453985, optical_depth=tau_re)
+        bg_th[:, 15] = th[:, 18]
+        h.set_background(bg_th)
+        return h.loglike_batch(npts, nuis), sth
+
+    step_thermo()
+    t0 = time.perf_counter()
+    (_, tot_th, _), sth = step_thermo()
+    sec_th = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    n_cpu_th = 4
+    rd_cpu = [o.thermo(bg[i], 0.2453985, optical_depth=tau_re[i])["derived"]["rdrag"] for i in range(n_cpu_th)]
+    sec_cpu_th = (time.perf_counter() - t0) / n_cpu_th
+    thermal = {"value": npts / sec_th, "unit": UNIT, "ms_per_step": 1e3 * sec_th, "status_nonzero": int((sth != 0).sum()),
+               "max_rel_rdrag_vs_oracle": float(np.max(np.abs(bg_th[:n_cpu_th, 15] / np.array(rd_cpu) - 1))),
+               "cpu_oracle_s_per_point_1thread": sec_cpu_th,
+               "note": "cb200_thermo inside the step: one thread per point, ~3.1e4 dependent RECFAST derivative evaluations "
+                       "each: latency-bound, 0.75 s per launch for anything up to ~1.9e4 points (one warp per scheduler)"}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "with_thermal_history": thermal,
            "data": "synthetic parameter points; real JLA light curves, DR12 BAO, HST; synthetic JLA covariance blocks",
            "config": {"workload": "BASELINE configs[1]: base LCDM background-only, JLA + DR12 BAO consensus + HST_Riess2018, "
                                   "%d parameter points per batch; r_drag supplied per point (thermal history is SURVEY 8f-1)" % npts,
