@@ -1477,7 +1477,7 @@ int cb200_thermo(cb200_handle* h, int npts, const double* bg, const double* ther
   CB_CUDA(cudaSetDevice(h->cfg.device));
   cudaStream_t s = h->stream;
   cb200_handle::Scope sc(h, PH_BG);
-  const int C = std::min(npts, 16384);   // points per pass: 720 KB of work tables per point (11.8 GB at 16 384)
+  const int C = std::min(npts, 32768);   // points per pass: 720 KB of work tables per point (23.6 GB at 32 768 = the threads one B200 holds at 218 registers)
   h->w_th_work.alloc((size_t)C * (3 * TH_NZ + 3 * TH_NTHERMO));
   h->w_bg_in.alloc((size_t)C * NBG);
   h->w_th_in.alloc((size_t)C * TH_NIN);

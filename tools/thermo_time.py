@@ -11,7 +11,7 @@ for n in ns:
     ombh2 = 0.02237 * (1 + 0.02 * rng.standard_normal(n)); omch2 = 0.12 * (1 + 0.03 * rng.standard_normal(n))
     H0 = 67.3 * (1 + 0.03 * rng.standard_normal(n)); tau = np.clip(0.055 + 0.01 * rng.standard_normal(n), 0.02, 0.2)
     bg = P.background_batch(ombh2, omch2, H0)
-    h.thermo(bg[:8], 0.245, optical_depth=tau[:8])
+    h.thermo(bg, 0.245, optical_depth=tau)   # first call: allocates the work tables
     t = time.time(); out, st = h.thermo(bg, 0.245, optical_depth=tau); dt = time.time() - t
     print("thermo: %6d points %8.1f ms  -> %7.1f us/point (%d failed); rdrag %.3f +- %.3f" % (n, 1e3 * dt, 1e6 * dt / n, (st != 0).sum(), out[:, 18].mean(), out[:, 18].std()), flush=True)
     omnuh2 = bg[0, 3] * (H0[0] / 100) ** 2
