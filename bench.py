@@ -54,7 +54,7 @@ def parse():
                     help="parameter points per step: in total (strong scaling) or per GPU (weak)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--chunk", type=int, default=1024)
-    ap.add_argument("--block-points", type=int, default=512, help="points per pinned host block / upload (e2e)")
+    ap.add_argument("--block-points", type=int, default=0, help="points per pinned host block / upload (e2e); 0 = P/16 clamped to [128, 512]: at least 16 stages per GPU so that the fill and drain of the upload / evaluate / download pipeline stay small under strong scaling")
     ap.add_argument("--cpu-sample", type=int, default=48, help="points of the same workload timed on the CPU oracle")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -311,7 +311,7 @@ def main():
 
     # ---- synthetic sources: generated on the device, made resident, and (e2e) copied to pinned host blocks - one
     #      block per upload, each holding ITS points' sources.  All outside every timed region.
-    B = min(args.block_points, P)
+    B = min(args.block_points if args.block_points > 0 else max(128, min(512, P // 16)), P)
     blocks = [(a, min(P, a + B)) for a in range(0, P, B)]
     stage = []
     for a, b in blocks:

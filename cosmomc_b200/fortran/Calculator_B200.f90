@@ -99,6 +99,25 @@
     real(c_double), intent(out) :: loglike(*), likelihoods(*), prior(*)
     integer(c_int), intent(out) :: status(*)
     end function
+    integer(c_int) function cb200_thermo(h, npts, bg, thermo_in, thermo_out, status) bind(C, name='cb200_thermo')
+    !thermal history of npts points (RECFAST, reionisation, inithermo: camb/modules.f90:2682-2992); thermo_out(13:25, i) =
+    !ThermoDerivedParams, thermo_out(8, i) = z_re from the optical depth (what GetZreFromTau returns)
+    import :: c_ptr, c_int, c_double
+    type(c_ptr), value :: h
+    integer(c_int), value :: npts
+    real(c_double), intent(in) :: bg(*), thermo_in(*)
+    real(c_double), intent(out) :: thermo_out(*)
+    integer(c_int), intent(out) :: status(*)
+    end function
+    integer(c_int) function cb200_theta_to_background(h, npts, cosmo, nu, tcmb, bg) bind(C, name='cb200_theta_to_background')
+    !the H0 bisection of ThetaParameterization%ParamArrayToTheoryParams (source/CosmologyParameterizations.f90:134-176)
+    import :: c_ptr, c_int, c_double
+    type(c_ptr), value :: h
+    integer(c_int), value :: npts
+    real(c_double), intent(in) :: cosmo(*), nu(*)
+    real(c_double), value :: tcmb
+    real(c_double), intent(inout) :: bg(*)
+    end function
     end interface
 
     !the likelihood plug-ins (Likelihood_B200.f90) register with, and evaluate on, the calculator's handle
@@ -117,10 +136,36 @@
     procedure :: GetNewTransferData => B200_GetNewTransferData
     procedure :: GetNewPowerData => B200_GetNewPowerData
     procedure :: VersionTraceOutput => B200_VersionTraceOutput
+    procedure :: GetZreFromTau => B200_GetZreFromTau
     end type B200_Calculator
 
     public B200_Calculator, b200_shared_handle, invalidate_like_cache
     contains
+
+    function B200_GetZreFromTau(this, CMB, tau) result(zre)
+    !TCosmologyCalculator%GetZreFromTau (source/Calculator_CAMB.f90 CAMBCalc_GetZreFromTau -> CAMB_GetZreFromTau ->
+    !Reionization_zreFromOptDepth, camb/reionization.f90:256-291) through the batched thermal history with npts = 1.
+    !A driver that owns many chains calls cb200_thermo once for all of them instead (INTEGRATION.md section 8).
+    class(B200_Calculator) :: this
+    class(CMBParams) :: CMB
+    real(mcp), intent(in) :: tau
+    real(mcp) :: zre
+    type(CAMBParams) :: P
+    real(c_double) :: bg(16), tin(8), tout(32)
+    integer(c_int) :: st(1), rc
+
+    call this%CMBToCAMB(CMB, P)
+    bg = 0
+    bg(1) = P%H0; bg(2) = P%omegab; bg(3) = P%omegac; bg(4) = P%omegan; bg(5) = P%omegav; bg(6) = -1; bg(7) = P%tcmb
+    bg(8) = P%Num_Nu_massless; bg(9) = P%Nu_mass_eigenstates
+    bg(10:9+P%Nu_mass_eigenstates) = P%Nu_mass_degeneracies(1:P%Nu_mass_eigenstates)
+    bg(13:12+P%Nu_mass_eigenstates) = P%Nu_mass_fractions(1:P%Nu_mass_eigenstates)
+    tin = [P%YHe, 0._c_double, real(tau, c_double), real(P%Max_eta_k, c_double), 0._c_double, &
+        real(P%Transfer%kmax, c_double), 1._c_double, 0._c_double]
+    rc = cb200_thermo(this%handle, 1_c_int, bg, tin, tout, st)
+    if (rc /= 0 .or. st(1) /= 0) call MpiStop('B200: thermal history failed in GetZreFromTau')
+    zre = tout(8)
+    end function B200_GetZreFromTau
 
     function b200_shared_handle() result(h)
     type(c_ptr) :: h
