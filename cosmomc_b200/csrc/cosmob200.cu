@@ -435,8 +435,13 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
       throw std::runtime_error("cosmob200: no CUDA device available (there is no CPU fallback)");
     CB_CUDA(cudaSetDevice(c.device));
     CB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    CB_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    {  // the upload stream's unpack kernel and the download stream's copies must not queue behind the thousands of pending
+       // CTAs of a projection launch on the compute stream: highest priority for both
+      int lo = 0, hi = 0;
+      CB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CB_CUDA(cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi));
+      CB_CUDA(cudaStreamCreateWithPriority(&h->d2h_stream, cudaStreamNonBlocking, hi));
+    }
     CB_CUDA(cudaEventCreateWithFlags(&h->ev_upload, cudaEventDisableTiming));
     if (c.accuracy_level != 1) throw std::runtime_error("only accuracy_level = 1 is supported");
     if (!c.cmb_lensing) throw std::runtime_error("only CMB_lensing = T is supported");

@@ -6,8 +6,10 @@
 //   :1028-1168  JLA_alpha_beta_like        scriptM pre-estimate, A..F marginalisation terms, chi^2
 //   :1170-1228  jla_LnLike                 lumdists = 5 log10((1+zhel)(1+zcmb) D_A(zcmb))
 // The reference factors V (DPOTRF), forms the full inverse (DPOTRI) and multiplies (DSYMV).  Here V = L L^T is
-// factored by a blocked left-looking Cholesky on the FP64 tensor pipe (DMMA m8n8k4), V is assembled on the fly
-// from the constant L2-resident blocks when a panel is first touched, and the right-hand sides [d, A1, A2] ride
+// factored by a blocked left-looking Cholesky on the FP64 tensor pipe (DMMA m8n8k4); V(alpha, beta) is assembled from
+// the six constant L2-resident blocks by sn_assemble_kernel ahead of the factorisation (one coalesced pass; the
+// in-kernel assembly of the first version put six dependent loads per element into the panel's latency chain and is
+// kept only behind CholParams::assemble), and the right-hand sides [d, A1, A2] ride
 // along as extra rows of the panel, so that after the factorisation those rows hold y = L^-1 rhs and
 //   A = y_d.y_d, B = y_d.y_1, C = y_d.y_2, D = y_1.y_2, E = y_1.y_1, F = y_2.y_2
 // (algebraically identical to the V^-1 expressions, without ever forming V^-1).
