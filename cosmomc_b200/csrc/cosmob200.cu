@@ -19,6 +19,7 @@
 #include "sn.cuh"
 #include "bk.cuh"
 #include "thermo.cuh"
+#include "nonlin.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -152,6 +153,8 @@ struct cb200_handle {
   DevBuf<unsigned long long> d_ring_stats;
   DevBuf<unsigned char> w_fallback;  // [chunk][NQB] blocks left to the chunked kernel by project4_kernel
   DevBuf<CUtensorMap> d_tmaps[2];
+  DevBuf<double> w_nl_in, w_nl_work;             // non-linear lensing: inputs / power tables, ratios, sigma_8
+  DevBuf<int> w_nl_status;
   DevBuf<double> w_th_work, w_th_in, w_th_out;   // thermal history: work tables [sample][point], input / result rows
   DevBuf<int> w_th_status;    // per perturbation type: TMA descriptors of {sources, second derivatives}
   // resident outputs
@@ -1317,6 +1320,14 @@ int cb200_debug_fetch(cb200_handle* h, int what, int point, int max_n, double* o
     case 5: fetch(S.dq.p + (size_t)point * S.NQ, S.h_nq[point]); break;
     case 6: fetch(S.tau.p + (size_t)point * S.NT, S.h_ntau[point]); break;
     case 7: fetch(S.dtau.p + (size_t)point * S.NT, S.h_ntau[point]); break;
+    case 10: {  // the resident lensing-potential source of the point, [n_tau][NK] (rows of source 3)
+      const size_t nt = (size_t)S.h_ntau[point];
+      if ((long long)(nt * S.NK) > max_n) return fail(h, "debug_fetch: buffer too small");
+      CB_CUDA(cudaMemcpy2D(out, sizeof(double) * S.NK, S.src.p + ((size_t)point * S.NT * 3 + 2) * S.NK, sizeof(double) * 3 * S.NK,
+                           sizeof(double) * S.NK, nt, cudaMemcpyDeviceToHost));
+      *n = (int)(nt * S.NK);
+      break;
+    }
     default: return fail(h, "debug_fetch: unknown selector");
   }
   return 0;
@@ -1473,6 +1484,65 @@ int cb200_background(cb200_handle* h, int npts, const double* bg, int nz, const 
   CB_API_END(h)
 }
 
+
+// ---- non-linear lensing rescale and sigma_8 (nonlin.cuh) ----
+int cb200_nonlinear_lensing(cb200_handle* h, int first, int npts, const double* initpower, const double* cosmo, int n_kt,
+                            int n_z, const double* kh, const double* z, const double* transfer, const double* tautf,
+                            int rescale_sources, double* sigma8, double* ratio, double* spec, int* status) {
+  if (!h) return -1;
+  CB_API_BEGIN
+  if (npts <= 0 || n_kt < 4 || n_z < 2 || n_z > NL_MAXZ || !initpower || !cosmo || !kh || !z || !transfer)
+    return fail(h, "nonlinear_lensing: bad arguments");
+  if (rescale_sources && (!tautf || first < 0 || first + npts > h->cfg.max_points || h->cfg.lmax_computed_cl <= 0))
+    return fail(h, "nonlinear_lensing: rescaling needs resident sources and the conformal times of the transfer redshifts");
+  CB_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->stream;
+  cb200_handle::Scope sc(h, PH_SPLINE);
+  const size_t N = (size_t)npts, nkz = (size_t)n_z * n_kt;
+  // inputs: initpower [10], cosmo [6], kh [n_kt], transfer [n_z][n_kt], tautf [n_z] per point, then z [n_z]
+  const size_t o_ip = 0, o_cs = o_ip + N * 10, o_kh = o_cs + N * 6, o_tr = o_kh + N * n_kt, o_tf = o_tr + N * nkz,
+               o_z = o_tf + N * n_z, n_in = o_z + n_z;
+  h->w_nl_in.alloc(n_in);
+  double* di = h->w_nl_in.p;
+  CB_CUDA(cudaMemcpyAsync(di + o_ip, initpower, sizeof(double) * N * 10, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(di + o_cs, cosmo, sizeof(double) * N * 6, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(di + o_kh, kh, sizeof(double) * N * n_kt, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(di + o_tr, transfer, sizeof(double) * N * nkz, cudaMemcpyHostToDevice, s));
+  if (tautf) CB_CUDA(cudaMemcpyAsync(di + o_tf, tautf, sizeof(double) * N * n_z, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(di + o_z, z, sizeof(double) * n_z, cudaMemcpyHostToDevice, s));
+  // work: logkh [n_kt], matpower, ddmat, ratio [n_z][n_kt], spec [n_z][3], sigma8 [n_z] per point
+  const size_t w_lk = 0, w_mp = w_lk + N * n_kt, w_dd = w_mp + N * nkz, w_ra = w_dd + N * nkz, w_sp = w_ra + N * nkz,
+               w_s8 = w_sp + N * n_z * 3, n_w = w_s8 + N * n_z;
+  h->w_nl_work.alloc(n_w);
+  h->w_nl_status.alloc(N);
+  CB_CUDA(cudaMemsetAsync(h->w_nl_status.p, 0, sizeof(int) * N, s));
+  double* dw = h->w_nl_work.p;
+  NlParams P;
+  P.np = npts; P.n_kt = n_kt; P.n_z = n_z;
+  P.initpower = di + o_ip; P.cosmo = di + o_cs; P.kh = di + o_kh; P.z = di + o_z; P.transfer = di + o_tr;
+  P.logkh = dw + w_lk; P.matpower = dw + w_mp; P.ddmat = dw + w_dd; P.ratio = dw + w_ra; P.spec = dw + w_sp; P.sigma8 = dw + w_s8;
+  P.status = h->w_nl_status.p;
+  nl_sigma8_kernel<<<(unsigned)((N * n_z + 127) / 128), 128, 0, s>>>(P);
+  CB_LAUNCH_CHECK();
+  nl_halofit_kernel<<<(unsigned)(N * n_z), NL_THREADS, sizeof(double) * 4 * n_kt, s>>>(P);
+  CB_LAUNCH_CHECK();
+  h->n_launches += 2;
+  if (rescale_sources) {
+    PointStore& S = h->store[0];
+    PointView v = S.view();
+    dim3 grid((S.NK + 127) / 128, npts);
+    nl_rescale_kernel<<<grid, 128, 0, s>>>(v, first, npts, n_kt, n_z, P.cosmo, P.ratio, di + o_tf, S.src.p);
+    CB_LAUNCH_CHECK();
+    h->n_launches += 1;
+  }
+  if (sigma8) CB_CUDA(cudaMemcpyAsync(sigma8, P.sigma8, sizeof(double) * N * n_z, cudaMemcpyDeviceToHost, s));
+  if (ratio) CB_CUDA(cudaMemcpyAsync(ratio, P.ratio, sizeof(double) * N * nkz, cudaMemcpyDeviceToHost, s));
+  if (spec) CB_CUDA(cudaMemcpyAsync(spec, P.spec, sizeof(double) * N * n_z * 3, cudaMemcpyDeviceToHost, s));
+  if (status) CB_CUDA(cudaMemcpyAsync(status, h->w_nl_status.p, sizeof(int) * N, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+  CB_API_END(h)
+}
 
 // ---- thermal history (thermo.cuh) ----
 int cb200_thermo(cb200_handle* h, int npts, const double* bg, const double* thermo_in, double* thermo_out, int* status) {

@@ -99,6 +99,16 @@
     real(c_double), intent(out) :: loglike(*), likelihoods(*), prior(*)
     integer(c_int), intent(out) :: status(*)
     end function
+    integer(c_int) function cb200_nonlinear_lensing(h, first, npts, initpower, cosmo, n_kt, n_z, kh, z, transfer, tautf, &
+        rescale_sources, sigma8, ratio, spec, status) bind(C, name='cb200_nonlinear_lensing')
+    !MakeNonlinearSources + halofit ratios + sigma_8 for npts points (camb/cmbmain.f90:1145-1204, halofit_ppf.f90:96-352,
+    !modules.f90:2202-2268); transfer(n_kt, n_z, npts) = MT%TransferData(transfer_power_var, :, :) at the NLL redshifts
+    import :: c_ptr, c_int, c_double
+    type(c_ptr), value :: h
+    integer(c_int), value :: first, npts, n_kt, n_z, rescale_sources
+    real(c_double), intent(in) :: initpower(*), cosmo(*), kh(*), z(*), transfer(*), tautf(*)
+    type(c_ptr), value :: sigma8, ratio, spec, status
+    end function
     integer(c_int) function cb200_thermo(h, npts, bg, thermo_in, thermo_out, status) bind(C, name='cb200_thermo')
     !thermal history of npts points (RECFAST, reionisation, inithermo: camb/modules.f90:2682-2992); thermo_out(13:25, i) =
     !ThermoDerivedParams, thermo_out(8, i) = z_re from the optical depth (what GetZreFromTau returns)

@@ -29,7 +29,7 @@ EXPORTS = [
     "cb200_timer_start", "cb200_timer_stop", "cb200_measure_fp64_peaks", "cb200_config_size", "cb200_abi_version",
     "cb200_upload_sources_packed",
     "cb200_powers_shared", "cb200_like_set_bk_foregrounds", "cb200_background", "cb200_set_background", "cb200_like_add_bao", "cb200_like_add_hst", "cb200_like_add_sn",
-    "cb200_eval_batch", "cb200_test_like_batch", "cb200_thermo", "cb200_theta_to_background",
+    "cb200_eval_batch", "cb200_test_like_batch", "cb200_thermo", "cb200_theta_to_background", "cb200_nonlinear_lensing",
 ]
 
 
@@ -91,6 +91,8 @@ def load(path=None):
                            "(nvcc, sm_100a). There is no CPU fallback." % path)
     L = C.CDLL(path)
     L.cb200_last_error.restype = C.c_char_p
+    L.cb200_nonlinear_lensing.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp,
+                                          C.c_int, c_dp, c_dp, c_dp, c_ip]
     L.cb200_thermo.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_ip]
     L.cb200_theta_to_background.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, C.c_double, c_dp]
     L.cb200_last_error.argtypes = [C.c_void_p]
@@ -412,6 +414,21 @@ class Handle:
         self._check(self.L.cb200_background(self.h, npts, _pd(bg), len(z), _pd(z), _pd(DA), _pd(H), _pd(sc)),
                     "background")
         return (DA, H, sc) if want_scalars else (DA, H)
+
+    def nonlinear_lensing(self, initpower, cosmo, kh, z, transfer, tautf=None, rescale_sources=False, first=0):
+        """sigma_8(z), halofit ratios sqrt(P_NL / P_L)(z, k), (k_NL, n_eff, curvature)(z) of every point, and - with
+        rescale_sources - MakeNonlinearSources on the resident lensing sources of points [first, first + npts).
+        cosmo [npts][6] = h, omm0, omegav, fnu, w, wa; kh [npts][n_kt]; z [n_z]; transfer [npts][n_z][n_kt]; tautf [npts][n_z]."""
+        ip, cs, kh, z, tr = _d(initpower).reshape(-1, 10), _d(cosmo).reshape(-1, 6), _d(kh), _d(z), _d(transfer)
+        npts, n_z, n_kt = tr.shape
+        kh = np.ascontiguousarray(np.broadcast_to(kh.reshape(-1, n_kt), (npts, n_kt)))
+        tf = _d(tautf).reshape(npts, n_z) if tautf is not None else None
+        s8, ratio, spec = np.zeros((npts, n_z)), np.zeros((npts, n_z, n_kt)), np.zeros((npts, n_z, 3))
+        st = np.zeros(npts, dtype=np.int32)
+        self._check(self.L.cb200_nonlinear_lensing(self.h, first, npts, _pd(ip), _pd(cs), n_kt, n_z, _pd(kh), _pd(z), _pd(tr),
+                                                   _pd(tf), int(bool(rescale_sources)), _pd(s8), _pd(ratio), _pd(spec), _pi(st)),
+                    "nonlinear_lensing")
+        return dict(sigma8=s8, ratio=ratio, spec=spec, status=st)
 
     THERMO_DERIVED = ["age", "zstar", "rstar", "thetastar", "DAstar", "zdrag", "rdrag", "kd", "thetad", "zeq", "keq",
                       "thetaeq", "thetarseq"]

@@ -131,7 +131,8 @@ int cb200_powers_shared(cb200_handle* h, int src_point, int first, int npts, con
 /* Intermediate read-backs for parity tests (device -> host copies of the last cb200_powers call):
  *   what: 0 iCl [6][n_lsamp], 1 Cl_scalar [6][max_l+1], 2 Cl_lensed [4][max_l+1] (dimensionless),
  *         3 transfers Delta [n_q][n_lsamp_pad][3] (only if cb200_keep_transfers(h,1)), 4 q, 5 dq, 6 tau, 7 dtau,
- *         8 tensor iCl [4][n_lsamp_tensor], 9 Cl_tensor [4][lmax_tensor+1] TT,EE,BB,TE (dimensionless) */
+ *         8 tensor iCl [4][n_lsamp_tensor], 9 Cl_tensor [4][lmax_tensor+1] TT,EE,BB,TE (dimensionless),
+ *         10 the resident lensing-potential source of the point [n_tau][n_k_max] */
 int cb200_debug_fetch(cb200_handle* h, int what, int point, int max_n, double* out, int* n);
 int cb200_keep_transfers(cb200_handle* h, int on);
 
@@ -188,6 +189,24 @@ int cb200_like_set_bk_foregrounds(cb200_handle* h, int like_id, int nmaps, const
  *   DA, H [npts][nz] (Mpc, Mpc^-1; NULL to skip), scalars [npts][3] = tau0, age/Gyr, CosmomcTheta (NULL to skip). */
 int cb200_background(cb200_handle* h, int npts, const double* bg, int nz, const double* z, double* DA, double* H,
                      double* scalars);
+/* ---- non-linear lensing rescale and sigma_8 ---------------------------------------------------
+ * cb200_nonlinear_lensing replaces, for a batch, CAMB's MakeNonlinearSources (camb/cmbmain.f90:1145-1204) with the
+ * halofit ratios of NonLinear_GetNonLinRatios (camb/halofit_ppf.f90:96-352, Takahashi 2012) on the matter power table of
+ * Transfer_GetMatterPowerData (camb/modules.f90:1882-2074), and Transfer_Get_SigmaR at 8 Mpc/h (:2202-2268), i.e. what
+ * happens to Src(k, 3, tau) between the Boltzmann ODEs and cb200_powers when use_nonlinear_lensing = T, plus the sigma_8
+ * of the chain's derived block.  Call it after cb200_upload_sources and before cb200_powers (it multiplies the resident
+ * lensing source of points [first, first+npts) in place: once per upload).
+ *   initpower [npts][10] as for cb200_powers; cosmo [npts][6] = h, Omega_c + Omega_b + Omega_nu, Omega_Lambda,
+ *   Omega_nu / Omega_m, w, wa; kh [npts][n_kt] the transfer wavenumbers in h/Mpc (the first n_k of them are the source
+ *   wavenumbers of the point, as in CAMB where MT%q_trans starts with Evolve_q); z [n_z] the NLL redshifts, descending;
+ *   transfer [npts][n_z][n_kt] = MT%TransferData(transfer_power_var, k, z); tautf [npts][n_z] their conformal times
+ *   (needed when rescale_sources != 0).  Outputs (NULL to skip): sigma8 [npts][n_z], ratio [npts][n_z][n_kt] =
+ *   sqrt(P_NL / P_L), spec [npts][n_z][3] = k_NL, n_eff, curvature, status [npts] (349 = halofit's "totally crazy
+ *   non-linear" exit, global_error_flag of the reference). */
+int cb200_nonlinear_lensing(cb200_handle* h, int first, int npts, const double* initpower, const double* cosmo, int n_kt,
+                            int n_z, const double* kh, const double* z, const double* transfer, const double* tautf,
+                            int rescale_sources, double* sigma8, double* ratio, double* spec, int* status);
+
 /* ---- thermal history ---------------------------------------------------------------------
  * cb200_thermo replaces, for a batch, what CAMB does between CAMBParams_Set and the source ODEs
  * (camb/modules.f90:376-400 Nnow / akthom / adotrad, camb/reionization.f90:139-199 Reionization_Init incl. the

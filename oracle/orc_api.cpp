@@ -6,6 +6,7 @@
 #include "orc_like.hpp"
 #include "orc_bg.hpp"
 #include "orc_thermo.hpp"
+#include "orc_nonlin.hpp"
 #include <memory>
 
 using namespace orc;
@@ -315,6 +316,45 @@ int orc_recfast_xe(const double* bg, double yhe, int n, const double* a, double*
   Recfast R;
   R.init(B, yhe);
   for (int i = 0; i < n; i++) xe[i] = R.xe(a[i]);
+  return 0;
+  ORC_CATCH
+}
+}  // extern "C"
+
+extern "C" {
+// ---- non-linear lensing rescale and sigma_8 (orc_nonlin.hpp).  par[6] = h, omm0 (= omegac + omegab + omegan), omegav,
+// fnu (= omegan / omm0), w, wa.  transfer [nz][nkt], kh [nkt], z [nz] (descending redshift = ascending time), tautf [nz].
+// Outputs: sigma8 [nz], ratio [nz][nkt], spec [nz][3] = rknl, rneff, rncur; src [n_tau][3][n_k] (optional) is rescaled in place.
+int orc_nonlinear(const double* initpower, const double* par, int nkt, int nz, const double* kh, const double* z,
+                  const double* transfer, double* sigma8, double* ratio, double* spec, int n_k, const double* k, int n_tau,
+                  const double* tau, const double* tautf, double* src) {
+  ORC_TRY
+  InitPower IP = ip_from(initpower);
+  auto ps = [&IP](double kk) { return ScalarPower(IP, kk); };
+  const double h = par[0];
+  if (sigma8) sigma_R(nkt, nz, kh, transfer, h, 8.0, ps, sigma8);
+  MatterPower PK;
+  PK.from_transfer(nkt, nz, kh, transfer, z, h, ps);
+  Halofit HF;
+  HF.omm0 = par[1]; HF.omegav = par[2]; HF.fnu = par[3]; HF.w_lam = par[4]; HF.wa = par[5];
+  const int err = HF.ratios(PK, spec);
+  if (ratio)
+    for (int i = 0; i < nz; i++)
+      for (int j = 0; j < nkt; j++) ratio[(size_t)i * nkt + j] = PK.nonlin_ratio[i][j];
+  if (src) make_nonlinear_sources(PK, n_k, k, h, n_tau, tau, tautf, src);
+  return err;
+  ORC_CATCH
+}
+// MatterPowerData_k at arbitrary k/h (first redshift of the table) - for the known-answer tests
+int orc_matter_power_at(const double* initpower, double h, int nkt, const double* kh, const double* transfer, int n,
+                        const double* kq, double* out) {
+  ORC_TRY
+  InitPower IP = ip_from(initpower);
+  auto ps = [&IP](double kk) { return ScalarPower(IP, kk); };
+  MatterPower PK;
+  const double z0 = 0;
+  PK.from_transfer(nkt, 1, kh, transfer, &z0, h, ps);
+  for (int i = 0; i < n; i++) out[i] = PK.at(kq[i], 0);
   return 0;
   ORC_CATCH
 }

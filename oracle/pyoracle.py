@@ -696,3 +696,38 @@ def h0_from_theta(theta100, make_bg, H0_min=20.0, H0_max=100.0):
         if abs(D_try - lasttry) < 1e-7:
             return H0
         lasttry = D_try
+
+
+# ---------------------------------------------------------------- non-linear lensing rescale + sigma_8 (orc_nonlin.hpp)
+def nonlinear(initpower, h, omm0, omegav, fnu, kh, z, transfer, w=-1.0, wa=0.0, k=None, tau=None, tautf=None, src=None):
+    """Transfer_Get_SigmaR(8) + NonLinear_GetNonLinRatios (halofit, Takahashi) [+ MakeNonlinearSources on src in place].
+    transfer [nz][nkt]; returns dict(sigma8 [nz], ratio [nz][nkt], spec [nz][3] = (rknl, rneff, rncur), err)."""
+    L = lib()
+    L.orc_nonlinear.restype = C.c_int
+    kh, z, tr = _d(kh), _d(z), _d(transfer)
+    nz, nkt = tr.shape
+    par = _d([h, omm0, omegav, fnu, w, wa])
+    s8, ratio, spec = np.zeros(nz), np.zeros((nz, nkt)), np.zeros((nz, 3))
+    if src is not None:
+        k, tau, tautf = _d(k), _d(tau), _d(tautf)
+        assert src.flags["C_CONTIGUOUS"] and src.shape == (len(tau), 3, len(k))
+        err = L.orc_nonlinear(_p(_d(initpower)), _p(par), nkt, nz, _p(kh), _p(z), _p(tr), _p(s8), _p(ratio), _p(spec),
+                              len(k), _p(k), len(tau), _p(tau), _p(tautf), _p(src))
+    else:
+        err = L.orc_nonlinear(_p(_d(initpower)), _p(par), nkt, nz, _p(kh), _p(z), _p(tr), _p(s8), _p(ratio), _p(spec),
+                              0, None, 0, None, None, None)
+    if err < 0:
+        raise RuntimeError("orc_nonlinear failed")
+    return dict(sigma8=s8, ratio=ratio, spec=spec, err=err)
+
+
+def matter_power_at(initpower, h, kh, transfer, kq):
+    """MatterPowerData_k (log-log spline of P(k/h) built by Transfer_GetMatterPowerData) at k/h = kq, one redshift."""
+    L = lib()
+    L.orc_matter_power_at.restype = C.c_int
+    L.orc_matter_power_at.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    kh, tr, kq = _d(kh), _d(transfer), _d(np.atleast_1d(kq))
+    out = np.zeros_like(kq)
+    if L.orc_matter_power_at(_p(_d(initpower)), float(h), len(kh), _p(kh), _p(tr), len(kq), _p(kq), _p(out)) != 0:
+        raise RuntimeError("orc_matter_power_at failed")
+    return out
