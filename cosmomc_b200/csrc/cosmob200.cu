@@ -149,6 +149,7 @@ struct cb200_handle {
   bool count_triples = false, ring_stats = false;
   int proj_kernel = 4;
   int sn_preassemble = 1;  // V(alpha, beta) assembled by its own coalesced kernel ahead of the Cholesky
+  int sn_chol_kernel_gen = 2;  // 2: sn_chol2_kernel (A fragments from global, column panel double-buffered), 1: sn_chol_kernel
   int spline_kernel = 2;  // 1: one thread per row straight from global memory, 2: tiled through shared memory
   DevBuf<unsigned long long> d_ring_stats;
   DevBuf<unsigned char> w_fallback;  // [chunk][NQB] blocks left to the chunked kernel by project4_kernel
@@ -463,6 +464,7 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
       h->d_nu_dr1.upload(dr1, h->stream);
       CB_CUDA(cudaStreamSynchronize(h->stream));
       CB_CUDA(cudaFuncSetAttribute(sn_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM));
+      CB_CUDA(cudaFuncSetAttribute(sn_chol2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2_SMEM));
     }
     h->chunk = c.chunk_points > 0 ? c.chunk_points : std::min(c.max_points, 1024);
     h->chunk = std::min(h->chunk, c.max_points);
@@ -1844,7 +1846,8 @@ static int loglike_device(cb200_handle* h, int bg_first, int npts, const double*
             cp.n = n; cp.nr = nr; cp.ld = ld; cp.np = m; cp.assemble = pre ? 0 : 1; cp.S = L.sn;
             cp.nuis = h->w_nuis.p + (size_t)a * n_nuis; cp.n_nuis = n_nuis; cp.ia = L.sn_ia; cp.ib = L.sn_ib;
             cp.W = h->w_snW.p; cp.pt_stride = pst; cp.status = h->w_snbad.p;
-            sn_chol_kernel<<<m, 256, CH_SMEM, s>>>(cp);
+            if (pre && h->sn_chol_kernel_gen == 2) sn_chol2_kernel<<<m, 256, C2_SMEM, s>>>(cp);
+            else sn_chol_kernel<<<m, 256, CH_SMEM, s>>>(cp);
             CB_LAUNCH_CHECK();
             sn_final_kernel<<<m, 256, 0, s>>>(m, n, L.sn.twoscriptm, h->w_snW.p + (size_t)n * ld, pst, ld, h->w_snbad.p,
                                               h->w_ll.p + (size_t)a * nlike + li, nlike);
@@ -2153,6 +2156,7 @@ int cb200_set_option(cb200_handle* h, const char* name, double value) {
   else if (n == "async_upload") h->async_upload = value != 0;
   else if (n == "async_results") h->async_results = value != 0;
   else if (n == "sn_preassemble") h->sn_preassemble = value != 0;
+  else if (n == "sn_chol_kernel") h->sn_chol_kernel_gen = (int)value;
   else if (n == "spline_kernel") h->spline_kernel = (value == 1) ? 1 : 2;
   else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 4) ? (int)value : 4;
   else return fail(h, "set_option: unknown option " + n);

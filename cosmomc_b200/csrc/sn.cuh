@@ -282,6 +282,169 @@ __global__ void __launch_bounds__(256, 2) sn_chol_kernel(CholParams p) {
   if (tid == 0 && p.status) p.status[pt] = s_bad;
 }
 
+// ---- blocked Cholesky, second generation (the per-point path; V pre-assembled in W) -----------------------------------
+// ncu of the kernel above (profiles/r01_sn_chol_ncu_full.txt): 0.23 of the DMMA peak, 7.9 barrier stalls per issued
+// instruction - two __syncthreads per 32-wide k-chunk around a shared-memory copy of BOTH operands, 128-row passes so the
+// column panel is re-staged six times for the early block columns, half of the threads idle in the panel solve.  Here:
+//   * a warp owns 32 rows of the pass and takes its A fragments straight from global memory, two k-values per lane with
+//     one 16-byte load (lane (r, c) holds k = 2c, 2c+1: the even and the odd values feed two DMMAs whose k-order is
+//     permuted identically for A and B, which a sum over k does not see) - no shared-memory round trip, no barrier;
+//   * only the 32 x K column panel L[c0.., 0..c0) goes through shared memory, 128 k-values per stage, double-buffered with
+//     cp.async: ONE barrier per 128 k-values instead of two per 32;
+//   * passes of 256 rows (8 warps x 32): the panel is staged at most three times, all 256 threads solve a row each;
+//   * warps whose 32 rows lie past the matrix skip the k-loop (they only meet the barriers).
+constexpr int C2_NB = 32, C2_ROWS = 256, C2_KS = 128, C2_BST = C2_KS + 8, C2_CS = C2_NB + 1, C2_LS = C2_NB + 2;
+constexpr size_t C2_BUF = sizeof(double) * 2 * C2_NB * C2_BST;                          // two stages of the column panel
+constexpr size_t C2_SMEM = (C2_BUF > sizeof(double) * C2_ROWS * C2_CS ? C2_BUF : sizeof(double) * C2_ROWS * C2_CS) +
+                           sizeof(double) * C2_NB * C2_LS;
+
+__device__ __forceinline__ void c2_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void c2_cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(256, 2) sn_chol2_kernel(CholParams p) {
+  extern __shared__ __align__(16) unsigned char c2_smem[];
+  double* Bs = reinterpret_cast<double*>(c2_smem);             // [2][32][C2_BST]; aliased by Cs [256][33] in the epilogue
+  double* Cs = Bs;
+  double* Ls = reinterpret_cast<double*>(c2_smem + (C2_BUF > sizeof(double) * C2_ROWS * C2_CS ? C2_BUF : sizeof(double) * C2_ROWS * C2_CS));
+  __shared__ int s_bad;
+  const int pt = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fc = lane & 3;   // fragment row / k-pair (A), n / k-pair (B), row / column pair (C)
+  const int n = p.n, nrows = p.n + p.nr, ld = p.ld;
+  double* W = p.W + (size_t)pt * p.pt_stride;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+
+  for (int c0 = 0; c0 < n; c0 += C2_NB) {
+    const int wcols = min(C2_NB, n - c0);
+    const int K = c0;
+    const int tiles = (nrows - c0 + 31) >> 5, passes = (tiles + 7) >> 3;
+    const int nsc = (K + C2_KS - 1) / C2_KS;
+    for (int pass = 0; pass < passes; pass++) {
+      const int tile = pass * 8 + warp;
+      const bool active = tile < tiles;
+      const int row0 = c0 + tile * 32;
+      double acc[4][4][2];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+      // stage sc of the column panel: rows c0 .. c0+31, k in [sc*128, sc*128 + kw)
+      auto fill = [&](int sc) {
+        const int kw = min(C2_KS, K - sc * C2_KS);
+        double* dst = Bs + (size_t)(sc & 1) * C2_NB * C2_BST;
+        const int per_row = kw >> 1;   // 16-byte pieces per row
+        for (int e = tid; e < C2_NB * per_row; e += 256) {
+          const int rr = e / per_row, kk = (e - rr * per_row) * 2;
+          const int row = c0 + rr;
+          if (row < nrows) c2_cp_async16(dst + rr * C2_BST + kk, W + (size_t)row * ld + sc * C2_KS + kk);
+          else *reinterpret_cast<double2*>(dst + rr * C2_BST + kk) = make_double2(0.0, 0.0);
+        }
+      };
+      if (nsc > 0) fill(0);
+      for (int sc = 0; sc < nsc; sc++) {
+        c2_cp_async_wait_all();
+        __syncthreads();                       // stage sc landed; everybody is done with stage sc - 1
+        if (sc + 1 < nsc) fill(sc + 1);
+        if (active) {
+          const int kw = min(C2_KS, K - sc * C2_KS);
+          const double* bs = Bs + (size_t)(sc & 1) * C2_NB * C2_BST + fr * C2_BST + 2 * fc;
+          const double* ag = W + (size_t)(row0 + fr) * ld + sc * C2_KS + 2 * fc;
+#pragma unroll 2
+          for (int k8 = 0; k8 < kw; k8 += 8) {
+            double2 a2[4], b2[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+              a2[mi] = (row0 + mi * 8 + fr < nrows) ? *reinterpret_cast<const double2*>(ag + (size_t)mi * 8 * ld + k8) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) b2[ni] = *reinterpret_cast<const double2*>(bs + ni * 8 * C2_BST + k8);
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+              for (int ni = 0; ni < 4; ni++) {
+                dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a2[mi].x, b2[ni].x);
+                dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a2[mi].y, b2[ni].y);
+              }
+          }
+        }
+      }
+      __syncthreads();                         // the panel stages are dead: Cs takes their place
+      // ---- Cs = A - acc for this warp's 32 rows
+      if (active) {
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+          const int rr = warp * 32 + mi * 8 + fr;
+          const int row = row0 + mi * 8 + fr;
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) {
+            const int cc = ni * 8 + 2 * fc;
+            double2 av = make_double2(0.0, 0.0);
+            if (row < nrows) av = *reinterpret_cast<const double2*>(W + (size_t)row * ld + c0 + cc);
+            Cs[rr * C2_CS + cc] = (cc < wcols) ? av.x - acc[mi][ni][0] : 0.0;
+            Cs[rr * C2_CS + cc + 1] = (cc + 1 < wcols) ? av.y - acc[mi][ni][1] : 0.0;
+          }
+        }
+      }
+      __syncthreads();
+      if (pass == 0) {
+        // ---- factor the diagonal block (warp 0, lane = row): rows 0..31 of this pass
+        if (warp == 0) {
+          double rowv[C2_NB];
+#pragma unroll
+          for (int j = 0; j < C2_NB; j++) rowv[j] = (lane < wcols && j < wcols) ? Cs[lane * C2_CS + j] : (lane == j ? 1.0 : 0.0);
+          bool bad = false;
+#pragma unroll
+          for (int k = 0; k < C2_NB; k++) {
+            double dkk = __shfl_sync(0xffffffffu, rowv[k], k);
+            if (!(dkk > 0.0)) { bad = true; dkk = 1.0; }
+            const double d = sqrt(dkk);
+            const double lik = (lane >= k) ? ((lane == k) ? d : rowv[k] / d) : 0.0;
+            rowv[k] = lik;
+#pragma unroll
+            for (int j = k + 1; j < C2_NB; j++) {
+              const double ljk = __shfl_sync(0xffffffffu, lik, j);
+              if (lane >= j) rowv[j] -= lik * ljk;
+            }
+          }
+          if (bad && lane == 0) s_bad = 1;
+#pragma unroll
+          for (int j = 0; j < C2_NB; j++) Ls[lane * C2_LS + j] = (j <= lane) ? rowv[j] : 0.0;
+          Ls[lane * C2_LS + C2_NB] = 1.0 / rowv[lane];
+        }
+        __syncthreads();
+      }
+      // ---- every thread one row: the diagonal block's rows take L_jj, the others solve X L_jj^T = Cs
+      {
+        const int row = c0 + pass * C2_ROWS + tid;
+        if (row < nrows) {
+          double* out = W + (size_t)row * ld + c0;
+          if (pass == 0 && tid < wcols) {
+            for (int c = 0; c < wcols; c++) out[c] = Ls[tid * C2_LS + c];
+          } else {   // (in the last block column the rows right below the diagonal block are the right-hand sides)
+            double x[C2_NB];
+#pragma unroll
+            for (int c = 0; c < C2_NB; c++) x[c] = Cs[tid * C2_CS + c];
+#pragma unroll
+            for (int k = 0; k < C2_NB; k++) {
+              const double xk = x[k] * Ls[k * C2_LS + C2_NB];
+              x[k] = xk;
+#pragma unroll
+              for (int c = k + 1; c < C2_NB; c++) x[c] -= xk * Ls[c * C2_LS + k];
+            }
+#pragma unroll
+            for (int c = 0; c < C2_NB; c++)
+              if (c < wcols) out[c] = x[c];
+          }
+        }
+      }
+      __syncthreads();                         // Cs is dead before the next pass refills the stages
+    }
+    __threadfence_block();
+  }
+  if (tid == 0 && p.status) p.status[pt] = s_bad;
+}
+
 // chi^2 from the solved right-hand-side rows y_d, y_1, y_2 (each [n], row stride ld)
 __global__ void __launch_bounds__(256) sn_final_kernel(int np, int n, int twoscriptm, const double* __restrict__ Y,
                                                        size_t pt_stride, int ld, const int* __restrict__ bad,

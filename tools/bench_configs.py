@@ -70,10 +70,11 @@ def config2(args):
             "achieved": flop_pt * npts / sec_like / 1e12, "peak": dmma, "unit": "TFLOP/s",
             "peak_source": "FP64 DMMA m8n8k4 micro-kernel measured live (cb200_measure_fp64_peaks); MEASURED_PEAKS.json "
                            "holds bf16 only", "flop_per_point": flop_pt, "share_of_step": tm["ms_like"] / (ms / 1.0) * 1.0,
-            "traffic": 6.03e9 / 256 * npts, "traffic_source": "ncu dram bytes of a 256-point launch "
-            "(profiles/r01_sn_chol_ncu_full.txt), scaled per point; algorithmic: 4.4 MB/point (V written once, read once)",
+            "traffic": 5.835e9 / 256 * npts, "traffic_source": "ncu dram bytes of a 256-point launch of sn_chol2_kernel "
+            "(profiles/r02_sn_chol2_ncu_full.txt), scaled per point; algorithmic: 4.4 MB/point (V written once, read once)",
             "note": "left-looking blocked Cholesky: one CTA per point re-reads the factored panels (16.9 MB/point) from DRAM "
-                    "because ~300 points (1.3 GB of factors) are in flight, far beyond the 126 MB L2"}
+                    "because ~300 points (1.3 GB of factors) are in flight, far beyond the 126 MB L2; second-generation kernel "
+                    "(A fragments straight from global memory, column panel double-buffered by cp.async, 256-row passes)"}
     roof["frac"] = roof["achieved"] / dmma
     roof["share_of_step"] = tm["ms_like"] / ms
     # CPU: the oracle's restatement (numpy/scipy LAPACK for DPOTRF/DPOTRI/DSYMV) on a bounded sample, one point at a time
