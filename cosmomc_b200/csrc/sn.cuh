@@ -322,8 +322,13 @@ __global__ void __launch_bounds__(256, 2) sn_chol2_kernel(CholParams p) {
     const int tiles = (nrows - c0 + 31) >> 5, passes = (tiles + 7) >> 3;
     const int nsc = (K + C2_KS - 1) / C2_KS;
     for (int pass = 0; pass < passes; pass++) {
-      const int tile = pass * 8 + warp;
-      const bool active = tile < tiles;
+      // a pass with few row tiles (the late block columns, the tail pass of the early ones) splits the k-range of every
+      // stage over SF warps per tile instead of leaving warps idle at the stage barriers; partial sums meet in shared memory
+      const int tp = min(8, tiles - pass * 8);
+      const int SF = tp <= 1 ? 8 : (tp <= 2 ? 4 : (tp <= 4 ? 2 : 1));
+      const int TPW = 8 / SF, tslot = warp % TPW, kpart = warp / TPW;
+      const int tile = pass * 8 + tslot;
+      const bool active = tslot < tp;
       const int row0 = c0 + tile * 32;
       double acc[4][4][2];
 #pragma unroll
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(256, 2) sn_chol2_kernel(CholParams p) {
           const double* bs = Bs + (size_t)(sc & 1) * C2_NB * C2_BST + fr * C2_BST + 2 * fc;
           const double* ag = W + (size_t)(row0 + fr) * ld + sc * C2_KS + 2 * fc;
 #pragma unroll 2
-          for (int k8 = 0; k8 < kw; k8 += 8) {
+          for (int k8 = 8 * kpart; k8 < kw; k8 += 8 * SF) {
             double2 a2[4], b2[4];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
@@ -370,11 +375,38 @@ __global__ void __launch_bounds__(256, 2) sn_chol2_kernel(CholParams p) {
         }
       }
       __syncthreads();                         // the panel stages are dead: Cs takes their place
-      // ---- Cs = A - acc for this warp's 32 rows
-      if (active) {
+      if (SF > 1) {                            // (block-uniform) add the k-parts: scratch [part - 1][tile slot][value][lane]
+        double* scr = Cs;
+        if (active && kpart > 0) {
+          double* d = scr + ((size_t)((kpart - 1) * TPW + tslot) * 32) * 32 + lane;
+#pragma unroll
+          for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+              d[((mi * 4 + ni) * 2) * 32] = acc[mi][ni][0];
+              d[((mi * 4 + ni) * 2 + 1) * 32] = acc[mi][ni][1];
+            }
+        }
+        __syncthreads();
+        if (active && kpart == 0) {
+          for (int q = 1; q < SF; q++) {
+            const double* d = scr + ((size_t)((q - 1) * TPW + tslot) * 32) * 32 + lane;
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+              for (int ni = 0; ni < 4; ni++) {
+                acc[mi][ni][0] += d[((mi * 4 + ni) * 2) * 32];
+                acc[mi][ni][1] += d[((mi * 4 + ni) * 2 + 1) * 32];
+              }
+          }
+        }
+        __syncthreads();                       // scratch read before Cs (same memory) is written
+      }
+      // ---- Cs = A - acc for this tile's 32 rows
+      if (active && kpart == 0) {
 #pragma unroll
         for (int mi = 0; mi < 4; mi++) {
-          const int rr = warp * 32 + mi * 8 + fr;
+          const int rr = tslot * 32 + mi * 8 + fr;
           const int row = row0 + mi * 8 + fr;
 #pragma unroll
           for (int ni = 0; ni < 4; ni++) {
@@ -394,12 +426,17 @@ __global__ void __launch_bounds__(256, 2) sn_chol2_kernel(CholParams p) {
 #pragma unroll
           for (int j = 0; j < C2_NB; j++) rowv[j] = (lane < wcols && j < wcols) ? Cs[lane * C2_CS + j] : (lane == j ? 1.0 : 0.0);
           bool bad = false;
+          double rinv = 1.0;
 #pragma unroll
           for (int k = 0; k < C2_NB; k++) {
             double dkk = __shfl_sync(0xffffffffu, rowv[k], k);
             if (!(dkk > 0.0)) { bad = true; dkk = 1.0; }
-            const double d = sqrt(dkk);
-            const double lik = (lane >= k) ? ((lane == k) ? d : rowv[k] / d) : 0.0;
+            // this chain of 32 pivots runs on ONE warp while the other seven wait (24 % of the kernel's stall samples
+            // sat on the barrier behind it): one reciprocal square root per pivot instead of a square root and a division
+            const double rk = rsqrt(dkk);
+            const double d = dkk * rk;
+            const double lik = (lane >= k) ? ((lane == k) ? d : rowv[k] * rk) : 0.0;
+            rinv = (lane == k) ? rk : rinv;
             rowv[k] = lik;
 #pragma unroll
             for (int j = k + 1; j < C2_NB; j++) {
@@ -410,7 +447,7 @@ __global__ void __launch_bounds__(256, 2) sn_chol2_kernel(CholParams p) {
           if (bad && lane == 0) s_bad = 1;
 #pragma unroll
           for (int j = 0; j < C2_NB; j++) Ls[lane * C2_LS + j] = (j <= lane) ? rowv[j] : 0.0;
-          Ls[lane * C2_LS + C2_NB] = 1.0 / rowv[lane];
+          Ls[lane * C2_LS + C2_NB] = rinv;   // 1 / L_lane,lane (1 beyond wcols)
         }
         __syncthreads();
       }

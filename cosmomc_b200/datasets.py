@@ -22,6 +22,7 @@ class IniFile:
     def __init__(self, path=None):
         self.params = {}
         self.order = []
+        self.read_values = {}   # key -> value as handed out, in first-read order (Ini%ReadValues of the reference)
         self.dir = "."
         if path is not None:
             self.dir = os.path.dirname(os.path.abspath(path))
@@ -61,10 +62,19 @@ class IniFile:
 
     def string(self, key, default=None):
         if self.has(key):
+            self.read_values.setdefault(key, self.params[key])
             return self.params[key]
         if default is None:
             raise KeyError("ini key not found: " + key)
+        self.read_values.setdefault(key, str(default))
         return default
+
+    def save_read_values(self, path):
+        """`<root>.inputparams` (Ini%SaveReadValues, source/IniObjects.f90:870-884; called from source/driver.F90:198):
+        one `name = value` line per key the run actually read, defaults included, in the order of the first read."""
+        with open(path, "w") as f:
+            for k, v in self.read_values.items():
+                f.write("%s = %s\n" % (k, v))
 
     def int(self, key, default=None):
         return int(self.string(key, None if default is None else str(default)))

@@ -56,3 +56,16 @@ def test_derived_block_order_and_values_match_the_golden_minimum():
     want = np.array([g[n] for n in names[:len(d)]])
     assert names[:3] == ["H0", "omegal", "omegam"] and names[len(d) - 1] == "DM233"
     assert np.abs(d / want - 1).max() < 2e-6, dict(zip(names, d / want - 1))
+
+
+def test_inputparams_writer_lists_the_keys_read_in_order(tmp_path):
+    """`<root>.inputparams` = Ini%SaveReadValues (source/IniObjects.f90:870-884): `name = value` per key read, defaults
+    included, first-read order; keys never read are not listed."""
+    from cosmomc_b200 import datasets as ds
+    p = tmp_path / "a.ini"
+    p.write_text("x = 3\nunused = 1\ny = hello # comment\n")
+    ini = ds.IniFile(str(p))
+    assert ini.int("x") == 3 and ini.string("z", "dflt") == "dflt" and ini.string("y") == "hello" and ini.int("x") == 3
+    out = tmp_path / "run.inputparams"
+    ini.save_read_values(str(out))
+    assert out.read_text() == "x = 3\nz = dflt\ny = hello\n"
