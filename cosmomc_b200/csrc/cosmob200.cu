@@ -91,7 +91,8 @@ struct LikeEntry {
   // BK foreground model attached to a cmblikes entry (TBK_planck extends TCMBLikes)
   bool has_fg = false;
   BkParams bk{};
-  DevBuf<double> bk_nu, bk_R, bk_dnu, bk_fgW;
+  DevBuf<double> bk_nu, bk_R, bk_dnu, bk_lnnu, bk_w, bk_fgW;   // bk_fgW: [l][nbins * ncl]
+  DevBuf<int> bk_lrange;                         // [nbins][2] first / last multipole with a non-zero window
 };
 
 enum Phase { PH_SPLINE = 0, PH_PROJECT, PH_CONTRACT, PH_INTERP, PH_LENS, PH_LIKE, PH_BG, PH_COUNT };
@@ -154,6 +155,8 @@ struct cb200_handle {
   DevBuf<unsigned long long> d_ring_stats;
   DevBuf<unsigned char> w_fallback;  // [chunk][NQB] blocks left to the chunked kernel by project4_kernel
   DevBuf<CUtensorMap> d_tmaps[2];
+  DevBuf<double> w_bk_shapes, w_bk_scal, w_bk_G;   // BK15 foregrounds in GEMM form: l-shapes, map scalings, band powers
+  int bk_scalar_foregrounds = 0;                    // option "bk_scalar_foregrounds": force the per-point scalar kernel
   DevBuf<double> w_nl_in, w_nl_work;             // non-linear lensing: inputs / power tables, ratios, sigma_8
   DevBuf<int> w_nl_status;
   DevBuf<double> w_th_work, w_th_in, w_th_out;   // thermal history: work tables [sample][point], input / result rows
@@ -1431,7 +1434,30 @@ int cb200_like_set_bk_foregrounds(cb200_handle* h, int like_id, int nmaps, const
   b.bp_off[nmaps] = bp_offset[nmaps];
   const size_t nb = bp_offset[nmaps];
   L.bk_nu.upload(bp_nu, nb, h->stream); L.bk_R.upload(bp_R, nb, h->stream); L.bk_dnu.upload(bp_dnu, nb, h->stream);
-  L.bk_fgW.upload(fgW, (size_t)L.nbins * L.ncl * (lmax + 1), h->stream);
+  {  // ln(nu) and R dnu of every bandpass sample: the kernel's nu^(3+beta) becomes one exp
+    std::vector<double> ln((size_t)nb), w((size_t)nb);
+    for (int k = 0; k < nb; k++) { ln[k] = std::log(bp_nu[k]); w[k] = bp_dnu[k] * bp_R[k]; }
+    L.bk_lnnu.upload(ln, h->stream); L.bk_w.upload(w, h->stream);
+    CB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  {  // windows transposed to [l][bin * ncl] (coalesced over the kernel's threads) + the multipole support of every bin
+    const int NTc = L.nbins * L.ncl, LW = lmax + 1;
+    std::vector<double> wt((size_t)LW * NTc);
+    std::vector<int> lr((size_t)L.nbins * 2);
+    for (int b = 0; b < L.nbins; b++) {
+      int lo = LW, hi = -1;
+      for (int c = 0; c < L.ncl; c++)
+        for (int l = 0; l < LW; l++) {
+          const double w = fgW[((size_t)b * L.ncl + c) * LW + l];
+          wt[(size_t)l * NTc + (size_t)b * L.ncl + c] = w;
+          if (w != 0.0) { lo = std::min(lo, l); hi = std::max(hi, l); }
+        }
+      lr[2 * b] = std::max(lo, lmin); lr[2 * b + 1] = std::min(hi, lmax);
+    }
+    L.bk_fgW.upload(wt, h->stream);
+    L.bk_lrange.upload(lr, h->stream);
+    CB_CUDA(cudaStreamSynchronize(h->stream));
+  }
   CB_CUDA(cudaStreamSynchronize(h->stream));
   L.has_fg = true;
   return 0;
@@ -1785,10 +1811,30 @@ static int loglike_device(cb200_handle* h, int bg_first, int npts, const double*
           if (L.bk.nuis_off + 16 > n_nuis) return fail(h, "loglike: BK foreground parameters outside the nuisance vector");
           BkParams bk = L.bk;
           bk.np = npts; bk.n_nuis = n_nuis; bk.nuis = h->w_nuis.p; bk.binned = h->w_bc.p;
-          bk.bp_nu = L.bk_nu.p; bk.bp_R = L.bk_R.p; bk.bp_dnu = L.bk_dnu.p; bk.fgW = L.bk_fgW.p;
-          bk_foreground_kernel<<<npts, 256, 0, s>>>(bk);
-          CB_LAUNCH_CHECK();
-          h->n_launches += 1;
+          bk.bp_nu = L.bk_nu.p; bk.bp_R = L.bk_R.p; bk.bp_dnu = L.bk_dnu.p; bk.bp_lnnu = L.bk_lnnu.p; bk.bp_w = L.bk_w.p; bk.fgW = L.bk_fgW.p; bk.lrange = L.bk_lrange.p;
+          // frequency decorrelation makes the foreground of a map pair non-separable in l: the scalar kernel handles it;
+          // otherwise (Delta_dust = Delta_sync = 1 for every point, the BK15 baseline) the sum is one GEMM for the batch
+          bool decorr = false;
+          for (int i = 0; i < npts && !decorr; i++) {
+            const double* d = nuisance + (size_t)i * n_nuis + L.bk.nuis_off;
+            decorr = std::fabs(d[10] - 1) > 1e-5 || std::fabs(d[11] - 1) > 1e-5;
+          }
+          if (decorr || h->bk_scalar_foregrounds) {
+            bk_foreground_kernel<<<npts, 256, 0, s>>>(bk);
+            CB_LAUNCH_CHECK();
+            h->n_launches += 1;
+          } else {
+            const int LW = bk.lmax + 1;
+            h->w_bk_shapes.alloc((size_t)npts * 3 * LW); h->w_bk_scal.alloc((size_t)npts * 3 * BK_MAXMAPS);
+            h->w_bk_G.alloc((size_t)npts * 3 * nb);
+            bk_shapes_kernel<<<npts, 256, 0, s>>>(bk, h->w_bk_shapes.p, h->w_bk_scal.p);
+            CB_LAUNCH_CHECK();
+            dgemm(s, false, false, 3 * npts, nb, LW, 1.0, h->w_bk_shapes.p, LW, L.bk_fgW.p, nb, h->w_bk_G.p, nb, &h->n_launches);
+            dim3 gc((nb + 127) / 128, npts);
+            bk_combine_kernel<<<gc, 128, 0, s>>>(bk, h->w_bk_G.p, h->w_bk_scal.p);
+            CB_LAUNCH_CHECK();
+            h->n_launches += 2;
+          }
         }
         CmbLikesBinParams cp;
         cp.np = npts; cp.nmaps = L.nmaps; cp.ncl = L.ncl; cp.nbins = L.nbins; cp.ncl_used = L.ncl_used;
@@ -1796,8 +1842,7 @@ static int loglike_device(cb200_handle* h, int bg_first, int npts, const double*
         cp.bc = h->w_bc.p; cp.bp = h->w_bp.p; cp.offset = L.offset.p; cp.noise = L.has_noise ? L.noise.p : nullptr;
         cp.chat = L.chat.p; cp.sqrt_fid = L.has_sqrt_fid ? L.sqrt_fid.p : nullptr; cp.cl_use = L.cl_use.p;
         cp.nuis = h->w_nuis.p; cp.bigx = h->w_bigx.p; cp.binned_out = h->w_binned.p;
-        dim3 grid((L.nbins + 31) / 32, npts);
-        cmblikes_bin_kernel<<<grid, 32, 0, s>>>(cp);
+        cmblikes_bin_kernel<<<(unsigned)(((long long)npts * L.nbins + CMBL_THREADS - 1) / CMBL_THREADS), CMBL_THREADS, 0, s>>>(cp);
         CB_LAUNCH_CHECK();
         dgemm(s, false, false, npts, nx, nx, 1.0, h->w_bigx.p, nx, L.invcov.p, nx, h->w_T.p, nx, &h->n_launches);
         rowdot_kernel<<<(npts + 3) / 4, 128, 0, s>>>(npts, nx, h->w_T.p, h->w_bigx.p, 1.0, h->w_quad.p, 1, 0);
@@ -2157,6 +2202,7 @@ int cb200_set_option(cb200_handle* h, const char* name, double value) {
   else if (n == "async_results") h->async_results = value != 0;
   else if (n == "sn_preassemble") h->sn_preassemble = value != 0;
   else if (n == "sn_chol_kernel") h->sn_chol_kernel_gen = (int)value;
+  else if (n == "bk_scalar_foregrounds") h->bk_scalar_foregrounds = value != 0;
   else if (n == "spline_kernel") h->spline_kernel = (value == 1) ? 1 : 2;
   else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 4) ? (int)value : 4;
   else return fail(h, "set_option: unknown option " + n);

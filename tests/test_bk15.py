@@ -95,3 +95,30 @@ def test_gpu_bk15_loglike(plan, templates):
     for i in range(B):
         want = o.bk_loglike(plan, cls[i], P[i])
         assert abs(ll[i, lid] / want - 1) < 1e-9, (i, ll[i, lid], want)   # north_star: |Delta lnL| < 0.01
+
+
+@pytest.mark.gpu
+def test_gpu_bk15_foregrounds_gemm_form_matches_scalar_kernel(plan, templates):
+    """Without frequency decorrelation the foreground band powers go through one GEMM for the batch (three l-shapes per
+    point x the transposed windows); with it, or with option bk_scalar_foregrounds, through the per-point kernel.  Both
+    against the oracle, and against each other, incl. band-centre errors and E/B ratios."""
+    import pyoracle as o
+    from cosmomc_b200 import lib
+    h = lib.Handle(max_points=16, chunk_points=8, lmax_out=H.LMAX_OUT)
+    lid = plan.register(h, nuis_offset=0)
+    rng = np.random.default_rng(11)
+    B = 5
+    P = np.tile(P0, (B, 1))
+    P[:, 0] = rng.uniform(2.0, 6.0, B); P[:, 1] = rng.uniform(0.0, 3.0, B); P[:, 2] = rng.uniform(-0.8, -0.2, B)
+    P[:, 3] = rng.normal(1.59, 0.11, B); P[:, 5] = rng.uniform(-1.0, -0.2, B); P[:, 6] = rng.normal(-3.1, 0.3, B)
+    P[:, 7] = rng.uniform(-0.5, 0.5, B); P[:, 8] = rng.uniform(1.5, 2.5, B); P[:, 9] = rng.uniform(1.5, 2.5, B)
+    P[2, 12:16] = [0.01, 0.02, -0.015, 0.01]
+    assert np.all(P[:, 10:12] == 1.0)                      # no decorrelation: the GEMM form is taken
+    cls = np.stack([theory_cls(templates, r) for r in rng.uniform(0.5, 3.0, B)])
+    ll_gemm, _, _ = h.loglike_cls(cls, P)
+    h.set_option("bk_scalar_foregrounds", 1)
+    ll_scalar, _, _ = h.loglike_cls(cls, P)
+    assert np.abs(ll_gemm[:, lid] / ll_scalar[:, lid] - 1).max() < 1e-11
+    for i in range(B):
+        want = o.bk_loglike(plan, cls[i], P[i])
+        assert abs(ll_gemm[i, lid] / want - 1) < 1e-9
