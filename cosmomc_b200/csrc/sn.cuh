@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256, 2) sn_chol_kernel(CholParams p) {
 constexpr int C2_NB = 32, C2_ROWS = 256, C2_KS = 128, C2_BST = C2_KS + 8, C2_CS = C2_NB + 1, C2_LS = C2_NB + 2;
 constexpr size_t C2_BUF = sizeof(double) * 2 * C2_NB * C2_BST;                          // two stages of the column panel
 constexpr size_t C2_SMEM = (C2_BUF > sizeof(double) * C2_ROWS * C2_CS ? C2_BUF : sizeof(double) * C2_ROWS * C2_CS) +
-                           sizeof(double) * C2_NB * C2_LS;
+                           sizeof(double) * C2_NB * C2_LS + sizeof(double) * 2 * C2_NB;   // + column broadcast of the diagonal-block factor
 
 __device__ __forceinline__ void c2_cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -427,21 +427,30 @@ __global__ void __launch_bounds__(256, 2) sn_chol2_kernel(CholParams p) {
           for (int j = 0; j < C2_NB; j++) rowv[j] = (lane < wcols && j < wcols) ? Cs[lane * C2_CS + j] : (lane == j ? 1.0 : 0.0);
           bool bad = false;
           double rinv = 1.0;
+          // Column k of the block (one value per lane) is broadcast through shared memory: one store, then every lane reads
+          // the pivot and the 31 - k values below it with 16-byte loads.  (The first version fetched each l_jk with its own
+          // pair of shuffles: 2 x 496 dependent shuffles per block put 27 % of the kernel's time on this ONE warp while the
+          // other seven waited at the barrier behind it - ncu source page, profiles/r02_sn_chol2_ncu_full.txt.)
+          double* colb = Ls + C2_NB * C2_LS;   // [2][32], double-buffered: one __syncwarp per pivot
 #pragma unroll
           for (int k = 0; k < C2_NB; k++) {
-            double dkk = __shfl_sync(0xffffffffu, rowv[k], k);
+            double* col = colb + (k & 1) * C2_NB;
+            col[lane] = rowv[k];
+            __syncwarp();
+            double dkk = col[k];
             if (!(dkk > 0.0)) { bad = true; dkk = 1.0; }
-            // this chain of 32 pivots runs on ONE warp while the other seven wait (24 % of the kernel's stall samples
-            // sat on the barrier behind it): one reciprocal square root per pivot instead of a square root and a division
-            const double rk = rsqrt(dkk);
+            const double rk = rsqrt(dkk);   // one reciprocal square root per pivot instead of a square root and a division
             const double d = dkk * rk;
             const double lik = (lane >= k) ? ((lane == k) ? d : rowv[k] * rk) : 0.0;
             rinv = (lane == k) ? rk : rinv;
             rowv[k] = lik;
+            const double t = lik * rk;      // l_ik l_jk = (l_ik / sqrt(d_kk)) a_jk
+            // unpredicated (entries above the diagonal are never read back), two columns per 16-byte load
 #pragma unroll
-            for (int j = k + 1; j < C2_NB; j++) {
-              const double ljk = __shfl_sync(0xffffffffu, lik, j);
-              if (lane >= j) rowv[j] -= lik * ljk;
+            for (int j2 = (k + 1) & ~1; j2 < C2_NB; j2 += 2) {
+              const double2 cj = *reinterpret_cast<const double2*>(col + j2);
+              if (j2 > k) rowv[j2] -= t * cj.x;
+              rowv[j2 + 1] -= t * cj.y;
             }
           }
           if (bad && lane == 0) s_bad = 1;
