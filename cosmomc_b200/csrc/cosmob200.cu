@@ -150,6 +150,8 @@ struct cb200_handle {
   bool count_triples = false, ring_stats = false;
   int proj_kernel = 4;
   int sn_preassemble = 1;  // V(alpha, beta) assembled by its own coalesced kernel ahead of the Cholesky
+  int sn_chol_warps = 0;       // warps per CTA of sn_chol2_kernel (8: two CTAs per SM, 4: four, 0: by launch size)
+  int sn_chunk = 1024;         // points per launch of the supernova kernels
   int sn_chol_kernel_gen = 2;  // 2: sn_chol2_kernel (A fragments from global, column panel double-buffered), 1: sn_chol_kernel
   int spline_kernel = 2;  // 1: one thread per row straight from global memory, 2: tiled through shared memory
   DevBuf<unsigned long long> d_ring_stats;
@@ -467,7 +469,8 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
       h->d_nu_dr1.upload(dr1, h->stream);
       CB_CUDA(cudaStreamSynchronize(h->stream));
       CB_CUDA(cudaFuncSetAttribute(sn_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM));
-      CB_CUDA(cudaFuncSetAttribute(sn_chol2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2_SMEM));
+      CB_CUDA(cudaFuncSetAttribute(sn_chol2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<8>::SMEM));
+      CB_CUDA(cudaFuncSetAttribute(sn_chol2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<4>::SMEM));
     }
     h->chunk = c.chunk_points > 0 ? c.chunk_points : std::min(c.max_points, 1024);
     h->chunk = std::min(h->chunk, c.max_points);
@@ -1870,7 +1873,10 @@ static int loglike_device(cb200_handle* h, int bg_first, int npts, const double*
           // K6: per-point covariance, blocked DMMA Cholesky with ride-along right-hand sides
           const int nr = L.sn_nr, ld = L.sn_ld;
           const size_t pst = (size_t)(n + nr) * ld;
-          const int sub = std::min(npts, h->chunk);
+          // points per launch: independent of the C_l chunk (4.4 MB of work matrix per point).  One launch of many CTAs keeps
+          // every SM busy to the end (CTAs are scheduled as others finish): 1 024 points in one launch 9.6 us/point against
+          // 10.8 in four launches of 256 (0.86 of a wave each)
+          const int sub = std::min(npts, std::max(h->chunk, h->sn_chunk));
           h->w_snW.alloc((size_t)sub * pst);
           h->w_snbad.alloc(sub);
           for (int a = 0; a < npts; a += sub) {
@@ -1891,7 +1897,11 @@ static int loglike_device(cb200_handle* h, int bg_first, int npts, const double*
             cp.n = n; cp.nr = nr; cp.ld = ld; cp.np = m; cp.assemble = pre ? 0 : 1; cp.S = L.sn;
             cp.nuis = h->w_nuis.p + (size_t)a * n_nuis; cp.n_nuis = n_nuis; cp.ia = L.sn_ia; cp.ib = L.sn_ib;
             cp.W = h->w_snW.p; cp.pt_stride = pst; cp.status = h->w_snbad.p;
-            if (pre && h->sn_chol_kernel_gen == 2) sn_chol2_kernel<<<m, 256, C2_SMEM, s>>>(cp);
+            // four 4-warp CTAs per SM cover each other's serial phases slightly better than two 8-warp ones once the launch
+            // fills all of them (>= 592 CTAs: 9.35 against 9.56 us/point); below that the 8-warp form wins
+            const bool w4 = h->sn_chol_warps == 4 || (h->sn_chol_warps == 0 && m >= 592);
+            if (pre && h->sn_chol_kernel_gen == 2 && w4) sn_chol2_kernel<4><<<m, 128, C2Cfg<4>::SMEM, s>>>(cp);
+            else if (pre && h->sn_chol_kernel_gen == 2) sn_chol2_kernel<8><<<m, 256, C2Cfg<8>::SMEM, s>>>(cp);
             else sn_chol_kernel<<<m, 256, CH_SMEM, s>>>(cp);
             CB_LAUNCH_CHECK();
             sn_final_kernel<<<m, 256, 0, s>>>(m, n, L.sn.twoscriptm, h->w_snW.p + (size_t)n * ld, pst, ld, h->w_snbad.p,
@@ -2202,6 +2212,8 @@ int cb200_set_option(cb200_handle* h, const char* name, double value) {
   else if (n == "async_results") h->async_results = value != 0;
   else if (n == "sn_preassemble") h->sn_preassemble = value != 0;
   else if (n == "sn_chol_kernel") h->sn_chol_kernel_gen = (int)value;
+  else if (n == "sn_chol_warps") h->sn_chol_warps = ((int)value == 4) ? 4 : ((int)value == 8 ? 8 : 0);
+  else if (n == "sn_chunk") h->sn_chunk = std::max(1, (int)value);
   else if (n == "bk_scalar_foregrounds") h->bk_scalar_foregrounds = value != 0;
   else if (n == "spline_kernel") h->spline_kernel = (value == 1) ? 1 : 2;
   else if (n == "proj_kernel") h->proj_kernel = (value >= 1 && value <= 4) ? (int)value : 4;

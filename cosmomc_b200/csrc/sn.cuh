@@ -293,21 +293,38 @@ __global__ void __launch_bounds__(256, 2) sn_chol_kernel(CholParams p) {
 //     cp.async: ONE barrier per 128 k-values instead of two per 32;
 //   * passes of 256 rows (8 warps x 32): the panel is staged at most three times, all 256 threads solve a row each;
 //   * warps whose 32 rows lie past the matrix skip the k-loop (they only meet the barriers).
-constexpr int C2_NB = 32, C2_ROWS = 256, C2_KS = 128, C2_BST = C2_KS + 8, C2_CS = C2_NB + 1, C2_LS = C2_NB + 2;
-constexpr size_t C2_BUF = sizeof(double) * 2 * C2_NB * C2_BST;                          // two stages of the column panel
-constexpr size_t C2_SMEM = (C2_BUF > sizeof(double) * C2_ROWS * C2_CS ? C2_BUF : sizeof(double) * C2_ROWS * C2_CS) +
-                           sizeof(double) * C2_NB * C2_LS + sizeof(double) * 2 * C2_NB;   // + column broadcast of the diagonal-block factor
+//   * NW warps per CTA (template): with 4 warps and 64 k-values per stage four CTAs share an SM, so the serial phases of one
+//     matrix (diagonal-block factor, row solves, stage barriers) are covered by the k-loops of three others.
+#ifndef CB200_C2_PF
+#define CB200_C2_PF 1      // prefetch of the A rows: 0 off, 1 into L1, 2 into L2 (1 024 points: 9.33 -> 9.05 us/point; distance 64: 9.20, L2 / 128: 9.88)
+#endif
+#ifndef CB200_C2_PD
+#define CB200_C2_PD 32     // prefetch distance in k-values
+#endif
+constexpr int C2_NB = 32, C2_CS = C2_NB + 1, C2_LS = C2_NB + 2;
+template <int NW> struct C2Cfg {
+  static constexpr int ROWS = 32 * NW;                    // rows per pass
+  static constexpr int KS = NW >= 8 ? 128 : 64;           // k-values per stage of the column panel
+  static constexpr int BST = KS + 8;
+  static constexpr size_t BUF = sizeof(double) * 2 * C2_NB * BST;                     // two stages of the column panel
+  static constexpr size_t CSB = sizeof(double) * ROWS * C2_CS;
+  static constexpr size_t SCR = sizeof(double) * (NW - 1) * 1024;                     // k-split partial sums
+  static constexpr size_t A0 = BUF > CSB ? (BUF > SCR ? BUF : SCR) : (CSB > SCR ? CSB : SCR);
+  static constexpr size_t SMEM = A0 + sizeof(double) * C2_NB * C2_LS + sizeof(double) * 2 * C2_NB;  // + L_jj + column broadcast
+};
 
 __device__ __forceinline__ void c2_cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void c2_cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-__global__ void __launch_bounds__(256, 2) sn_chol2_kernel(CholParams p) {
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 16 / NW) sn_chol2_kernel(CholParams p) {
+  constexpr int C2_ROWS = C2Cfg<NW>::ROWS, C2_KS = C2Cfg<NW>::KS, C2_BST = C2Cfg<NW>::BST, NT = 32 * NW;
   extern __shared__ __align__(16) unsigned char c2_smem[];
   double* Bs = reinterpret_cast<double*>(c2_smem);             // [2][32][C2_BST]; aliased by Cs [256][33] in the epilogue
   double* Cs = Bs;
-  double* Ls = reinterpret_cast<double*>(c2_smem + (C2_BUF > sizeof(double) * C2_ROWS * C2_CS ? C2_BUF : sizeof(double) * C2_ROWS * C2_CS));
+  double* Ls = reinterpret_cast<double*>(c2_smem + C2Cfg<NW>::A0);
   __shared__ int s_bad;
   const int pt = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fc = lane & 3;   // fragment row / k-pair (A), n / k-pair (B), row / column pair (C)
@@ -319,15 +336,16 @@ __global__ void __launch_bounds__(256, 2) sn_chol2_kernel(CholParams p) {
   for (int c0 = 0; c0 < n; c0 += C2_NB) {
     const int wcols = min(C2_NB, n - c0);
     const int K = c0;
-    const int tiles = (nrows - c0 + 31) >> 5, passes = (tiles + 7) >> 3;
+    const int tiles = (nrows - c0 + 31) >> 5, passes = (tiles + NW - 1) / NW;
     const int nsc = (K + C2_KS - 1) / C2_KS;
     for (int pass = 0; pass < passes; pass++) {
       // a pass with few row tiles (the late block columns, the tail pass of the early ones) splits the k-range of every
       // stage over SF warps per tile instead of leaving warps idle at the stage barriers; partial sums meet in shared memory
-      const int tp = min(8, tiles - pass * 8);
-      const int SF = tp <= 1 ? 8 : (tp <= 2 ? 4 : (tp <= 4 ? 2 : 1));
-      const int TPW = 8 / SF, tslot = warp % TPW, kpart = warp / TPW;
-      const int tile = pass * 8 + tslot;
+      const int tp = min(NW, tiles - pass * NW);
+      int SF = 1;                            // largest power of two with SF * tp <= NW
+      while (2 * SF * tp <= NW) SF *= 2;
+      const int TPW = NW / SF, tslot = warp % TPW, kpart = warp / TPW;
+      const int tile = pass * NW + tslot;
       const bool active = tslot < tp;
       const int row0 = c0 + tile * 32;
       double acc[4][4][2];
@@ -340,7 +358,7 @@ __global__ void __launch_bounds__(256, 2) sn_chol2_kernel(CholParams p) {
         const int kw = min(C2_KS, K - sc * C2_KS);
         double* dst = Bs + (size_t)(sc & 1) * C2_NB * C2_BST;
         const int per_row = kw >> 1;   // 16-byte pieces per row
-        for (int e = tid; e < C2_NB * per_row; e += 256) {
+        for (int e = tid; e < C2_NB * per_row; e += NT) {
           const int rr = e / per_row, kk = (e - rr * per_row) * 2;
           const int row = c0 + rr;
           if (row < nrows) c2_cp_async16(dst + rr * C2_BST + kk, W + (size_t)row * ld + sc * C2_KS + kk);
@@ -359,6 +377,18 @@ __global__ void __launch_bounds__(256, 2) sn_chol2_kernel(CholParams p) {
 #pragma unroll 2
           for (int k8 = 8 * kpart; k8 < kw; k8 += 8 * SF) {
             double2 a2[4], b2[4];
+#if CB200_C2_PF
+            // the A fragments come straight from global memory (23 MB per point of left-looking re-reads, half of them
+            // DRAM misses): each lane prefetches the line of ONE of the warp's 32 rows a few k-steps ahead
+            if (row0 + fc * 8 + fr < nrows) {
+              const double* pa = ag + (size_t)fc * 8 * ld - 2 * fc + k8 + CB200_C2_PD;
+#if CB200_C2_PF == 1
+              asm volatile("prefetch.global.L1 [%0];\n" ::"l"(pa));
+#else
+              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pa));
+#endif
+            }
+#endif
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
               a2[mi] = (row0 + mi * 8 + fr < nrows) ? *reinterpret_cast<const double2*>(ag + (size_t)mi * 8 * ld + k8) : make_double2(0.0, 0.0);
