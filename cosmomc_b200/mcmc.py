@@ -370,3 +370,166 @@ def read_minimum(path):
             typ, rest = ln[25:].split(": ", 1)
             contribs.append((float(ln[:11]), typ, rest))
     return loglike, rows, contribs
+
+
+# ---- binary `.data` files (full model output for importance sampling) -------------------------------------------------
+# ParamSet_WriteModel (source/ParamSet.f90:32-73) + TCosmoTheoryPredictions_WriteTheory (source/CosmoTheory.f90:235-282) on a
+# Fortran access='stream' unit (source/FileUtils.f90: no record markers; strings as int32 length + bytes, "sized" arrays as
+# int32 extent(s) + values, 2-D arrays column-major).  The first record of the theory block is the memory image of the
+# derived type TCosmoTheoryParams (source/CosmologyTypes.f90:30-71), which is processor-dependent: the layout below is the
+# one gfortran and ifort produce on x86-64 (4-byte default logical / integer, 8-byte reals on 8-byte boundaries, 160 bytes;
+# .true. written as 1).  No `.data` file ships with the reference, so this writer is pinned only by the reader next to it
+# (the mirror of ParamSet_ReadModel / ReadTheory) - parity unpinned, stated in DESIGN.md.  The matter-power block
+# (use_matterpower) is not written: the path has no P(k) arrays.
+_THEORY_PARAMS_FMT = "<4i6i5d4i3i4xdi4x2d2i2i"
+_THEORY_PARAMS_KEYS = ("get_sigma8", "use_LSS", "use_CMB", "use_nonlinear", "lmax", "num_cls", "lmax_tensor",
+                       "lmax_computed_cl", "lmin_computed_cl", "lmin_store_all_cmb", "z_outputs", "CMB_lensing",
+                       "use_lensing_potential", "use_nonlinear_lensing", "compute_tensors", "use_matterpower",
+                       "use_Weylpower", "use_sigmaR", "power_kmax", "num_power_redshifts", "pivot_k", "tensor_pivot_k",
+                       "inflation_consistency", "bbn_consistency", "num_massive_neutrinos", "neutrino_hierarchy")
+THEORY_PARAMS_DEFAULT = dict(get_sigma8=1, use_LSS=0, use_CMB=1, use_nonlinear=0, lmax=2500, num_cls=4, lmax_tensor=600,
+                             lmax_computed_cl=2500, lmin_computed_cl=2000, lmin_store_all_cmb=2500,
+                             z_outputs=(0.15, 0.38, 0.51, 0.61, 2.33), CMB_lensing=1, use_lensing_potential=1,
+                             use_nonlinear_lensing=1, compute_tensors=0, use_matterpower=0, use_Weylpower=0, use_sigmaR=0,
+                             power_kmax=0.8, num_power_redshifts=0, pivot_k=0.05, tensor_pivot_k=0.05,
+                             inflation_consistency=1, bbn_consistency=1, num_massive_neutrinos=-1, neutrino_hierarchy=1)
+
+
+def _pack_theory_params(s):
+    import struct
+    v = []
+    for k in _THEORY_PARAMS_KEYS:
+        x = s[k]
+        v.extend(x if k == "z_outputs" else [x])
+    return struct.pack(_THEORY_PARAMS_FMT, *v)
+
+
+def _unpack_theory_params(b):
+    import struct
+    v = list(struct.unpack(_THEORY_PARAMS_FMT, b))
+    out = {}
+    for k in _THEORY_PARAMS_KEYS:
+        if k == "z_outputs":
+            out[k] = tuple(v[:5]); v = v[5:]
+        else:
+            out[k] = v.pop(0)
+    return out
+
+
+def _wstr(f, s):
+    import struct
+    b = s.strip().encode()
+    f.write(struct.pack("<i", len(b))); f.write(b)
+
+
+def _wsized(f, a):
+    import struct
+    a = np.asarray(a)
+    f.write(struct.pack("<%di" % a.ndim, *a.shape))
+    f.write(np.asfortranarray(a).astype("<i4" if a.dtype.kind in "iu" else "<f8").tobytes(order="F"))
+
+
+def write_data_model(f, first, mult, like, likelihoods, params_used, theory, param_names=None, like_names=(),
+                     settings=None, cl_lmax=None):
+    """One model of a `.data` file.  f: binary file object; first: write the file header too (ParamSet.f90:40-63,
+    CosmoTheory.f90:243-250).  theory: dict(derived=[...], cls={(i, j): array over l = 1..cl_lmax[i, j]} with 1-based
+    field indices T, E, B, Phi and i >= j, tensor_ratio_02, tensor_ratio_C10, tensor_ratio_BB, tensor_AT,
+    lensing_rms_deflect, sigma_8).  cl_lmax: [num_cls][num_cls] int array (0 = spectrum not stored)."""
+    import struct
+    s = dict(THEORY_PARAMS_DEFAULT, **(settings or {}))
+    if s["use_matterpower"] or s["use_LSS"]:
+        raise NotImplementedError("matter-power block of .data files")
+    cl_lmax = np.asarray(cl_lmax, dtype=np.int32)
+    params_used = np.asarray(params_used, dtype="<f8")
+    if first:
+        f.write(struct.pack("<2i", 4, len(params_used)))                       # 4: double-precision mcp
+        has_names = param_names is not None and all(n != "" for n in param_names)
+        f.write(struct.pack("<i", 1 if has_names else 0))
+        if has_names:
+            for n in param_names:
+                _wstr(f, n)
+        f.write(struct.pack("<i", len(like_names)))
+        for n in like_names:
+            _wstr(f, n)
+        f.write(struct.pack("<i", 0))                                          # "unused"
+    f.write(struct.pack("<2d", mult, like))
+    f.write(np.asarray(likelihoods, dtype="<f8").tobytes())
+    f.write(params_used.tobytes())
+    if first:
+        f.write(_pack_theory_params(s))
+        if s["use_CMB"]:
+            _wsized(f, cl_lmax)
+        _wsized(f, np.array([6], dtype=np.int32))                              # ArraySizes = size(valArray)
+    d = np.asarray(theory.get("derived", ()), dtype="<f8")
+    f.write(struct.pack("<i", len(d))); f.write(d.tobytes())
+    for i in range(1, s["num_cls"] + 1):
+        for j in range(i, 0, -1):
+            if cl_lmax[i - 1, j - 1] > 0:
+                cl = np.asarray(theory["cls"][(i, j)], dtype="<f8")
+                assert len(cl) == cl_lmax[i - 1, j - 1], ((i, j), len(cl))
+                _wsized(f, cl)
+    _wsized(f, np.array([theory.get(k, 0.0) for k in ("tensor_ratio_02", "tensor_ratio_C10", "tensor_ratio_BB",
+                                                      "tensor_AT", "lensing_rms_deflect", "sigma_8")]))
+
+
+def read_data_models(path, n_likes_expected=None):
+    """Mirror of ParamSet_ReadModel (ParamSet.f90:75-150) + ReadTheory (CosmoTheory.f90:297-372): every model of a `.data`
+    file as a list of dicts, plus the header."""
+    import struct
+    b = open(path, "rb").read()
+    pos = [0]
+
+    def rd(fmt):
+        n = struct.calcsize(fmt)
+        v = struct.unpack(fmt, b[pos[0]:pos[0] + n]); pos[0] += n
+        return v
+
+    def rstr():
+        n, = rd("<i")
+        s = b[pos[0]:pos[0] + n].decode(); pos[0] += n
+        return s
+
+    def rarr(dtype, shape):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        a = np.frombuffer(b[pos[0]:pos[0] + n], dtype=dtype).reshape(shape, order="F"); pos[0] += n
+        return a.copy()
+    fmt, npar = rd("<2i")
+    if fmt != 4:
+        raise ValueError("ReadModel: wrong file format (single-precision or old cosmomc version)")
+    has_names, = rd("<i")
+    names = [rstr() for _ in range(npar)] if has_names else None
+    nl, = rd("<i")
+    like_names = [rstr() for _ in range(nl)]
+    unused, = rd("<i")
+    if unused != 0:
+        raise ValueError("ReadModel: don't know what the extra info is")
+    header = dict(param_names=names, like_names=like_names)
+    models, first = [], True
+    while pos[0] < len(b):
+        mult, like = rd("<2d")
+        likes = rarr("<f8", (nl,))
+        P = rarr("<f8", (npar,))
+        if first:
+            s = _unpack_theory_params(b[pos[0]:pos[0] + 160]); pos[0] += 160
+            cl_lmax = None
+            if s["use_CMB"]:
+                n1, n2 = rd("<2i")
+                cl_lmax = rarr("<i4", (n1, n2))
+            nas, = rd("<i")
+            array_sizes = rarr("<i4", (nas,))
+            header.update(settings=s, cl_lmax=cl_lmax, array_sizes=array_sizes)
+            first = False
+        nd, = rd("<i")
+        derived = rarr("<f8", (nd,))
+        cls = {}
+        for i in range(1, s["num_cls"] + 1):
+            for j in range(i, 0, -1):
+                if cl_lmax[i - 1, j - 1] > 0:
+                    n, = rd("<i")
+                    cls[(i, j)] = rarr("<f8", (n,))
+        nv, = rd("<i")
+        val = rarr("<f8", (nv,))
+        models.append(dict(mult=mult, like=like, likelihoods=likes, params=P, derived=derived, cls=cls,
+                           tensor_ratio_02=val[0], tensor_ratio_C10=val[1], tensor_ratio_BB=val[2], tensor_AT=val[3],
+                           lensing_rms_deflect=val[4], sigma_8=val[5]))
+    return header, models

@@ -69,3 +69,45 @@ def test_inputparams_writer_lists_the_keys_read_in_order(tmp_path):
     out = tmp_path / "run.inputparams"
     ini.save_read_values(str(out))
     assert out.read_text() == "x = 3\nz = dflt\ny = hello\n"
+
+
+def test_data_file_layout_and_round_trip(tmp_path):
+    """`.data` binary (ParamSet_WriteModel, ParamSet.f90:32-73 + WriteTheory, CosmoTheory.f90:235-282): header fields at the
+    byte offsets a Fortran stream unit gives them, the 160-byte TCosmoTheoryParams image, and a round trip through the
+    mirror of ReadModel / ReadTheory (no `.data` file ships with the reference: unpinned beyond this)."""
+    import struct
+    rng = np.random.default_rng(5)
+    cl_lmax = np.zeros((4, 4), dtype=np.int32)
+    cl_lmax[0, 0] = 2508; cl_lmax[1, 0] = 2508; cl_lmax[1, 1] = 2508; cl_lmax[3, 3] = 2500   # TT, ET, EE, PhiPhi
+    names = ["omegabh2", "omegach2", "theta", "tau", "logA", "ns"]
+    likes = ["lensing", "BAO"]
+    models = []
+    path = tmp_path / "chain_1.data"
+    with open(path, "wb") as f:
+        for m in range(3):
+            th = dict(derived=rng.normal(size=44),
+                      cls={(i + 1, j + 1): rng.normal(size=cl_lmax[i, j]) for i in range(4) for j in range(i + 1) if cl_lmax[i, j] > 0},
+                      lensing_rms_deflect=2.5e-3 + m, sigma_8=0.81 + m)
+            P, L = rng.normal(size=6), rng.normal(size=2)
+            mcmc.write_data_model(f, m == 0, 1.0 + m, 1382.9 + m, L, P, th, param_names=names, like_names=likes, cl_lmax=cl_lmax)
+            models.append((P, L, th))
+    b = path.read_bytes()
+    assert struct.unpack("<3i", b[:12]) == (4, 6, 1)                          # format 4 (double), num_params_used, has names
+    assert struct.unpack("<i", b[12:16]) == (8,) and b[16:24] == b"omegabh2"  # WriteTrim: length then characters
+    assert struct.calcsize(mcmc._THEORY_PARAMS_FMT) == 160
+    s = mcmc._unpack_theory_params(mcmc._pack_theory_params(mcmc.THEORY_PARAMS_DEFAULT))
+    assert s["z_outputs"] == (0.15, 0.38, 0.51, 0.61, 2.33) and s["pivot_k"] == 0.05 and s["num_massive_neutrinos"] == -1
+    # power_kmax sits on the 8-byte boundary after three logicals + 4 bytes of padding (offset 112)
+    assert struct.unpack("<d", mcmc._pack_theory_params(mcmc.THEORY_PARAMS_DEFAULT)[112:120]) == (0.8,)
+    hdr, got = mcmc.read_data_models(str(path))
+    assert hdr["param_names"] == names and hdr["like_names"] == likes and hdr["array_sizes"].tolist() == [6]
+    assert np.array_equal(hdr["cl_lmax"], cl_lmax) and hdr["settings"]["lmax_computed_cl"] == 2500
+    assert len(got) == 3
+    for m, (P, L, th) in enumerate(models):
+        g = got[m]
+        assert g["mult"] == 1.0 + m and g["like"] == 1382.9 + m
+        assert np.array_equal(g["params"], P) and np.array_equal(g["likelihoods"], L) and np.array_equal(g["derived"], th["derived"])
+        assert list(g["cls"].keys()) == [(1, 1), (2, 2), (2, 1), (4, 4)]      # i = 1..4, j = i..1
+        for k in th["cls"]:
+            assert np.array_equal(g["cls"][k], th["cls"][k])
+        assert g["sigma_8"] == th["sigma_8"] and g["lensing_rms_deflect"] == th["lensing_rms_deflect"] and g["tensor_AT"] == 0
