@@ -265,6 +265,31 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def bind_to_gpu_numa_node(local):
+    """Several ranks on one host: run this rank (and so first-touch its pinned staging buffers) on the CPUs of the NUMA
+    node its GPU hangs off, so that the per-block uploads do not cross the socket interconnect.  No-op on a single-node
+    host or when sysfs does not say.  Returns what was done (reported in the e2e object)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) < 2:
+            return {"gpu_pci": bdf, "numa_node": node, "nodes": len(nodes), "bound": False}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"gpu_pci": bdf, "numa_node": node, "nodes": len(nodes), "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"gpu_pci": bdf, "numa_node": node, "nodes": len(nodes), "bound": True, "cpus": len(cpus)}
+    except Exception as e:   # never fatal: this is placement, not correctness
+        return {"bound": False, "error": str(e)[:120]}
+
+
 def main():
     args = parse()
     if args.config != 4:
@@ -282,6 +307,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -446,6 +472,8 @@ def main():
                        "result copy of block i-1 overlap on three streams; C_l [pt][5][%d] %s"
                        % (len(blocks), B, LMAX_OUT + 1,
                           "copied back to a pinned host buffer" if cls_host is not None else "left on the device")}
+        if numa is not None:
+            e2e["host_placement_rank0"] = numa
 
     # ---- roofline of the dominant kernel (K1 projection; launched once per chunk of points)
     n_chunks = -(-P // min(args.chunk, P))

@@ -252,9 +252,12 @@ def config5(args):
         D.SNPlan(os.path.join(DATA, "Pantheon", "full_long.dataset"), covs=pan_cov).register(h)
         h.upload_sources(src1["thermo"], src1["n_k"], src1["k"], src1["src"], first=K)   # fiducial transfers, slot K
 
-        def loglike(P):   # columns: ombh2, omch2, H0, logA, ns, calPlanck
+        def loglike(P, thermo=False):   # columns: ombh2, omch2, H0, logA, ns, calPlanck
             K_ = len(P)
             bg = PR.background_batch(P[:, 0], P[:, 1], P[:, 2], rdrag_fit(P[:, 0], P[:, 1]))
+            if thermo:   # r_drag from the batched thermal history on the device (RECFAST + inithermo)
+                th, st_th = h.thermo(bg, 0.2453985, optical_depth=0.0544)
+                bg[:, 15] = np.where(st_th == 0, th[:, 18], bg[:, 15])
             h.set_background(bg)
             ip = np.tile(src1["initpower"][0], (K_, 1))
             ip[:, 0] = 1e-10 * np.exp(P[:, 3]); ip[:, 1] = P[:, 4]
@@ -319,7 +322,22 @@ def config5(args):
                  "R_minus_1_first_last": [float(R[0]), float(R[-1])] if len(R) else None}
         if not (len(R) == len(R1) and np.allclose(R, R1, rtol=1e-8) and np.allclose(m.cov, m1.cov, rtol=1e-8)):
             raise SystemExit("config 5: the %d-rank R-1 trajectory differs from the single-process one: %s" % (world, check))
+    # ---- the same lockstep step with r_drag from the GPU thermal history instead of the fitting formula: a few steps,
+    #      every rank its own chains (the thermal history is latency-bound: ~0.5 s per launch at these batch sizes)
+    nth = 6
+    Pth = start_all[rank * K:(rank + 1) * K]
+    f(Pth, thermo=True)
+    sync()
+    t0 = time.perf_counter()
+    for i in range(nth):
+        tot_th = f(Pth + 1e-4 * (i + 1) * width, thermo=True)
+    sync()
+    dt_th = (time.perf_counter() - t0) / nth
+    tot_fit = f(Pth + 1e-4 * nth * width)
     if dist is not None:
+        t = torch.tensor([dt_th], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_th = float(t.item())
         dist.barrier()
     if rank == 0:
         value = KTOT * steps / dt
@@ -335,6 +353,15 @@ def config5(args):
                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(50 * K * (16 + 10 + 1 + 1) * 8),
                        "d2h_bytes_per_step": int(50 * K * (3 + 1 + 1) * 8),
                        "note": "every MCMC step hands host parameter rows to the library and takes host -lnL back"},
+               "with_thermal_history": {"value": KTOT / dt_th, "unit": UNIT, "ms_per_lockstep_step": 1e3 * dt_th,
+                                        "steps_timed": nth, "max_abs_dlnl_vs_rdrag_fit": float(np.abs(tot_th - tot_fit).max()),
+                                        "note": "r_drag of every proposal from cb200_thermo (RECFAST + inithermo on the device) "
+                                                "instead of the fitting formula the trajectory run uses.  One thread per point "
+                                                "runs ~3.1e4 dependent RECFAST derivative evaluations: ~0.45 s per launch whatever "
+                                                "the batch size below ~2e4 points, against ~10 ms per point and core for the "
+                                                "reference's own thermal history on the host - at 64 proposals per step a chain "
+                                                "driver keeps r_drag on the host path (bg[15] is an input of cb200_set_background) "
+                                                "and uses cb200_thermo for throughput batches (22 us/point at 32 768 points)"},
                "trajectory_check": check, "roofline": None, "cpu_baseline": None,
                "phase_ms_per_mcmc_step": {k: tm[k] / steps for k in ["ms_project", "ms_contract", "ms_interp", "ms_lens",
                                                                      "ms_like", "ms_background"]},
