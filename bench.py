@@ -339,6 +339,13 @@ def main():
     #      block per upload, each holding ITS points' sources.  All outside every timed region.
     B = min(args.block_points if args.block_points > 0 else max(128, min(512, P // 16)), P)
     blocks = [(a, min(P, a + B)) for a in range(0, P, B)]
+    if B >= 256 and P >= 4 * B:
+        # the first upload has nothing to hide behind: start with small blocks (B/8, B/8, B/4, B/2) so that the pipeline
+        # fills in an eighth of the time, then continue with blocks of B points
+        ramp, a = [], 0
+        for n in (B // 8, B // 8, B // 4, B // 2):
+            ramp.append((a, a + n)); a += n
+        blocks = ramp + [(x, min(P, x + B)) for x in range(a, P, B)]
     stage = []
     for a, b in blocks:
         s = syn.make_sources(W["thermo"][a:b], W["tau"][a:b], W["k"][a:b], W["pert"][a:b], device=dev)
@@ -467,7 +474,7 @@ def main():
                "h2d_bound_evals_per_s_per_gpu": link * 1e9 / (h2d / P),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms2 / args.steps,
                "equals_resident_result": True,
-               "note": "%d pinned host blocks of %d points per GPU, each holding its own points' sources packed at their "
+               "note": "%d pinned host blocks of up to %d points per GPU (the first four smaller: the pipeline fills on a short upload), each holding its own points' sources packed at their "
                        "exact sizes (cb200_upload_sources_packed); upload of block i+1, kernels of block i and the "
                        "result copy of block i-1 overlap on three streams; C_l [pt][5][%d] %s"
                        % (len(blocks), B, LMAX_OUT + 1,
