@@ -78,10 +78,10 @@ static_assert(W4_PNN >= 1 && W4_S % W4_PNN == 0, "slab shape");
 constexpr int W4_MS = CB200_W4_MS;  // slabs per metadata iteration: their independent chains overlap in one thread
 static_assert(W4_MS == 1 || W4_PPT == 1, "several slabs per metadata iteration need one pair per thread and slab");
 #ifndef CB200_W4_CREG
-#define CB200_W4_CREG 136
-#endif
+#define CB200_W4_CREG 128   // (136 / 104 until the two-pairs-per-step consumers: with those the metadata warps pace the kernel and
+#endif                      //  do better with their full share of registers: 113.2 -> 111.8 us/point)
 #ifndef CB200_W4_PREG
-#define CB200_W4_PREG 104
+#define CB200_W4_PREG 128
 #endif
 #define CB200_STR2(x) #x
 #define CB200_STR(x) CB200_STR2(x)
@@ -178,6 +178,10 @@ __device__ __forceinline__ int w4_locate(const Proj4Params& p, double v, double&
   return g.npoints;
 }
 
+#ifndef CB200_W4_PAIR2
+#define CB200_W4_PAIR2 1   // 1: a consumer warp takes BOTH of its time samples of a slab in one step (S = 4, time-split): one prologue
+                           //    per two pairs, octet-granular batches whose two chains belong to the two samples
+#endif
 #ifndef CB200_W4_KB
 #define CB200_W4_KB 2   // octets per batch of loads in flight (time-split consumers: 1: 136.3 us/point, 2: 132.8, 3: 137.3, 4: 145.6)
 #endif
@@ -785,6 +789,55 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     const Proj4Rec* m_rec = reinterpret_cast<const Proj4Rec*>(mb);
     const double2* m_s01 = reinterpret_cast<const double2*>(mb + NPAIR * 16);
     const double* m_s2 = reinterpret_cast<const double*>(mb + NPAIR * 32);
+#if CB200_W4_PAIR2
+    {
+      static_assert(!CB200_W4_PAIR2 || (W4_TS && !W4_OS && W4_S == 4), "PAIR2: time-split consumers, 4-sample slabs");
+      // the warp's two time samples of this slab (lh, lh + 2) in ONE step: their metadata loads, weight chains and the warp-wide
+      // OR of the masks overlap, and a batch is one octet of both pairs (4 node loads in flight, two independent chains).  The
+      // sums are added in the order of the one-pair-per-step loop (sample lh first), so the results are bit-identical.
+      const int pr0 = lh * QC + myqi, pr1 = pr0 + 2 * QC;
+      const Proj4Rec rec0 = m_rec[pr0], rec1 = m_rec[pr1];
+      const double2 sA = m_s01[pr0], sB = m_s01[pr1];
+      const double s2A = m_s2[pr0], s2B = m_s2[pr1];
+      auto mask_of = [&](const Proj4Rec& rec) {
+        const int klo = max((int)((rec.jr & 0xff) + ORND - lc) >> OSH, 0);
+        const int khi1 = ((rec.jr >> 8) + ORND - lc) >> OSH;
+        return ((1u << khi1) - 1u) & ~((1u << klo) - 1u);
+      };
+      const unsigned mA = mask_of(rec0), mB = mask_of(rec1);
+      if (COUNT) {
+        unsigned mxA = 0, mxB = 0;
+#pragma unroll
+        for (int k = 0; k < LKH; k++) {
+          const unsigned tA = (unsigned)(n_base + lh) - (win[k] & 0xffffu), tB = tA + 2u;
+          mxA |= (tA <= (win[k] >> 16)) ? (1u << k) : 0u;
+          mxB |= (tB <= (win[k] >> 16)) ? (1u << k) : 0u;
+        }
+        if (mxA != mA) st_mismatch++;
+        if (mxB != mB) st_mismatch++;
+        if (p.triples) my_triples += __popc(mA) + __popc(mB);
+      }
+      const double aA = rec0.a, bA = 1 - aA, tA2 = -(bA * (aA * p.h2o6[rec0.off & 7]));
+      const double g0A = tA2 * (aA + 1), g1A = tA2 * (2 - aA);
+      const double aB = rec1.a, bB = 1 - aB, tB2 = -(bB * (aB * p.h2o6[rec1.off & 7]));
+      const double g0B = tB2 * (aB + 1), g1B = tB2 * (2 - aB);
+      const unsigned rpA = ring_lane + (rec0.off & ~127), rpB = ring_lane + (rec1.off & ~127);
+      const unsigned U = __reduce_or_sync(0xffffffffu, mA | mB);
+#pragma unroll
+      for (int k = 0; k < LKH; k++) {
+        if (!((U >> k) & 1u)) continue;   // warp-uniform
+        const double2 A0 = lds128(rpA + k * OSTR), A1 = lds128(rpA + k * OSTR + rb);
+        const double2 B0 = lds128(rpB + k * OSTR), B1 = lds128(rpB + k * OSTR + rb);
+        double JA = fma(g1A, A1.y, fma(g0A, A0.y, fma(bA, A1.x, aA * A0.x)));
+        double JB = fma(g1B, B1.y, fma(g0B, B0.y, fma(bB, B1.x, aB * B0.x)));
+        JA = ((mA >> k) & 1u) ? JA : 0.0;
+        JB = ((mB >> k) & 1u) ? JB : 0.0;
+        acc[k][0] = fma(sB.x, JB, fma(sA.x, JA, acc[k][0]));
+        acc[k][1] = fma(sB.y, JB, fma(sA.y, JA, acc[k][1]));
+        if (k < K2) acc2[k < K2 ? k : 0] = fma(s2B, JB, fma(s2A, JA, acc2[k < K2 ? k : 0]));
+      }
+    }
+#else
     // quarter-warp r works on pair (q_r, n); every lane covers LK multipoles
 #pragma unroll W4_UNROLL
     for (int nn = W4_TS ? lh : 0; nn < S; nn += W4_TS ? 2 : 1) {
@@ -877,6 +930,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
         }
       }
     }
+#endif
     __syncwarp();
     if (lane == 0) mbar_arrive(s_bar + W4_NST + par);
     CK4(ck_c);
