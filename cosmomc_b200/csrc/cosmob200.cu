@@ -155,6 +155,9 @@ struct cb200_handle {
   int sn_chol_kernel_gen = 2;  // 2: sn_chol2_kernel (A fragments from global, column panel double-buffered), 1: sn_chol_kernel
   int spline_kernel = 2;  // 1: one thread per row straight from global memory, 2: tiled through shared memory
   DevBuf<unsigned long long> d_ring_stats;
+  DevBuf<ProjQ3> w_qcg;              // [chunk][NQB][QC] wavenumber constants of kernel 4's blocks
+  DevBuf<unsigned> w_flg;            // [chunk][NQB][consumer warp][lane] reached / doint bits
+  DevBuf<double> w_raw;              // [chunk][NQB of kernel 4][group][3 LK][32]: kernel 4's time integrals (split epilogue)
   DevBuf<unsigned char> w_fallback;  // [chunk][NQB] blocks left to the chunked kernel by project4_kernel
   DevBuf<CUtensorMap> d_tmaps[2];
   DevBuf<double> w_bk_shapes, w_bk_scal, w_bk_G;   // BK15 foregrounds in GEMM form: l-shapes, map scalings, band powers
@@ -373,6 +376,12 @@ void ensure_work(cb200_handle* h) {
   h->w_part.alloc((size_t)C * NQB * 6 * PROJ_LP);
   h->w_fallback.alloc((size_t)C * NQB);
   h->w_fallback.zero(h->stream);
+#if CB200_W4_SPLIT_EPI
+  // time integrals of kernel 4 on their way to project4_finish_kernel: 50 KB per (point, wavenumber block), 6.2 MB per point
+  h->w_raw.alloc((size_t)C * ((NQ + W4_QC - 1) / W4_QC) * w4_raw_doubles(12));
+  h->w_qcg.alloc((size_t)C * ((NQ + W4_QC - 1) / W4_QC) * W4_QC);
+  h->w_flg.alloc((size_t)C * ((NQ + W4_QC - 1) / W4_QC) * W4_NCW * 32);
+#endif
   if (tens) {
     h->w_clt.alloc((size_t)C * 4 * h->LST);
     h->r_icl_t.alloc((size_t)h->cfg.max_points * 6 * PROJ_LP);
@@ -912,6 +921,7 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       pp.triples = h->count_triples ? h->d_triples.p : nullptr;
       pp.ring_stats = h->ring_stats ? h->d_ring_stats.p : nullptr;
       pp.fallback = h->w_fallback.p;
+      pp.raw = h->w_raw.p; pp.qcg = h->w_qcg.p; pp.flg = h->w_flg.p;
       pp.bseg = K.bseg;
       w4_set_last_stretch(pp);
       if (!h->d_tmaps[kind].p) {  // descriptors of this perturbation type's source arrays (fixed buffers: built once)
@@ -935,6 +945,9 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       else if (LK == 11) w4_launch<11, 11>(cnt, grid, smem, s, pp);
       else w4_launch<12, 12>(cnt, grid, smem, s, pp);
       CB_LAUNCH_CHECK();
+#if CB200_W4_SPLIT_EPI
+      h->n_launches += 1;   // project4_finish_kernel
+#endif
       // fallback pass: blocks whose table window does not fit the ring (the first, log-spaced wavenumber block)
       Proj3Params p3;
       p3.v = v; p3.p0 = p0; p3.nl = nl; p3.num_xx = K.num_xx; p3.NQB = pl.nqb_total; p3.tensors = kind;

@@ -108,6 +108,9 @@ struct Proj4Params {
   const double* initpower;
   double* part;             // [chunk][NQB][6][PROJ_LP]
   double* delta;            // optional [chunk][NQ][PROJ_LP][3]
+  double* raw;              // [chunk][NQB][wavenumber group][3 LK][32 lanes]: the time integrals as the consumers leave them
+  ProjQ3* qcg;              // [chunk][NQB][QC]: the per-wavenumber constants of the block (for project4_finish_kernel)
+  unsigned* flg;            // [chunk][NQB][consumer warp][lane]: reached | doint << 16, one bit per octet of the lane
   unsigned long long* triples;
   unsigned long long* ring_stats;  // optional [16]
   unsigned char* fallback;  // [chunk][NQB]: 1 = a slab of this block needs more table rows than the ring holds
@@ -298,6 +301,98 @@ __device__ __forceinline__ double2 lds128(unsigned saddr) {
   return r;
 }
 
+#ifndef CB200_W4_SPLIT_EPI
+#define CB200_W4_SPLIT_EPI 1   // 1: Limber values and the partial k-contraction run in project4_finish_kernel, not in this CTA's tail
+#endif
+
+// per-wavenumber constants (InterpolateSources set-up, cmbmain.f90:1307-1320): shared by the projection kernel's prologue and
+// by project4_finish_kernel
+__device__ __forceinline__ ProjQ3 w4_q_consts(const Proj4Params& p, int pt, int qi, int nq, const double* ip) {
+  const PointView& v = p.v;
+  const int nt = v.n_tau[pt], nk = v.n_k[pt];
+  const double tau0 = v.thermo[(size_t)pt * 5];
+  const double* tau = v.tau + (size_t)pt * v.NT;
+  const double* ksrc = v.ksrc + (size_t)pt * v.NK;
+  ProjQ3 c;
+  c.valid = qi < nq;
+  c.pad = 0;
+  if (c.valid) {
+    const double qv = v.q[(size_t)pt * v.NQ + qi];
+    const double dqv = v.dq[(size_t)pt * v.NQ + qi];
+    c.q = qv;
+    c.w = (p.tensors ? tensor_power_dev(ip, qv) : scalar_power_dev(ip, qv)) * (dqv / qv);
+    // klo = first index in [1, nk-1] with qv <= ksrc[klo] (else nk-1): the reference's linear scan
+    // (cmbmain.f90:1313-1316) as a binary search - same result on the ascending source grid, 8 loads instead of ~100
+    int klo = nk - 1;
+    {
+      int lo_ = 1, hi_ = nk - 1;
+      while (lo_ < hi_) {
+        const int mid = (lo_ + hi_) >> 1;
+        if (qv > ksrc[mid]) lo_ = mid + 1; else hi_ = mid;
+      }
+      klo = lo_;
+    }
+    c.klo = klo;
+    const double ho = ksrc[klo] - ksrc[klo - 1];
+    c.a0 = (ksrc[klo] - qv) / ho;
+    c.b0 = (qv - ksrc[klo - 1]) / ho;
+    c.ho2o6 = ho * ho / 6;
+    c.a03h = (c.a0 * c.a0 * c.a0 - c.a0);
+    c.b03h = (c.b0 * c.b0 * c.b0 - c.b0);
+    const double max_etak_tensor = p.max_eta_k / 10;
+    int step = 2;
+    for (int i = nt; i >= 2; i--) {
+      double xf = __dmul_rn(qv, __dsub_rn(tau0, tau[i - 1]));
+      bool ok = xf > 1.e-8;
+      if (p.tensors) ok = ok && (__dmul_rn(qv, tau[i - 1]) < max_etak_tensor);
+      if (ok) { step = i; break; }
+    }
+    c.steps = step;
+  } else {
+    c.q = 1; c.w = 0; c.klo = 1; c.a0 = c.b0 = c.a03h = c.b03h = c.ho2o6 = 0; c.steps = 0;
+  }
+  return c;
+}
+
+// integration window [n1, n2] of one (wavenumber, multipole) and the two flags the epilogue needs (cmbmain.f90:1387-1420,
+// 1440-1470): reached = the window is entered at all, doint = the time integral is formed (else Limber only)
+__device__ __forceinline__ void w4_window(const Proj4Params& p, const ProjQ3& myq, bool lvalid, int l, double tau0,
+                                          const double* tau, const LinSegs& tseg, int& n1, int& n2, bool& reached, bool& doint) {
+  n1 = 0; n2 = 0; reached = false; doint = false;
+  if (myq.valid && lvalid) {
+    const double qv = myq.q;
+    int llmax = (int)llround(__dmul_rn(qv, tau0));
+    if (llmax < 15) llmax = 17;
+    else llmax = (int)llround(__dmul_rn(qv, __dadd_rn(tau0, __ddiv_rn(6 * kPi, qv))));
+    if (l <= llmax) {
+      double xlim = 0.05 * l;
+      xlim = fmax(xlim, 35.0);
+      xlim = l - xlim;
+      const double tau2 = tau[1];
+      double tmin = __dsub_rn(tau0, __ddiv_rn((double)(80 * l), qv));
+      tmin = fmax(tau2, tmin);
+      double tmax = __dsub_rn(tau0, __ddiv_rn(xlim, qv));
+      tmax = fmin(tau0, tmax);
+      if (!(tmax < tau2)) {
+        reached = true;
+        bool di = true;
+        if (!p.tensors) {
+          double qmax_int = __ddiv_rn((double)(max(850, l) * 3), tau0);
+          qmax_int = __dmul_rn(qmax_int, (double)1.2f);
+          di = qv < qmax_int;
+        }
+        if (di) {
+          doint = true;
+          n1 = lin_index_of(tseg, tmin);
+          n2 = min(myq.steps, lin_index_of(tseg, tmax));
+        } else {
+          n1 = n2 = 0x7fff;
+        }
+      }
+    }
+  }
+}
+
 template <int LK, bool COUNT, int KLIM>
 __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p) {
   constexpr int NCW = W4_NCW, NQG = W4_NQG, QC = W4_QC, S = W4_S, NPAIR = W4_NPAIR;
@@ -354,46 +449,11 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
 
   // ---- per-wavenumber constants (InterpolateSources set-up, cmbmain.f90:1307-1320) ----
   if (tid < QC) {
-    ProjQ3 c;
-    const int qi = q0 + tid;
-    c.valid = qi < nq;
-    c.pad = 0;
-    if (c.valid) {
-      const double qv = v.q[(size_t)pt * v.NQ + qi];
-      const double dqv = v.dq[(size_t)pt * v.NQ + qi];
-      c.q = qv;
-      c.w = (p.tensors ? tensor_power_dev(ip, qv) : scalar_power_dev(ip, qv)) * (dqv / qv);
-      // klo = first index in [1, nk-1] with qv <= ksrc[klo] (else nk-1): the reference's linear scan
-      // (cmbmain.f90:1313-1316) as a binary search - same result on the ascending source grid, 8 loads instead of ~100
-      int klo = nk - 1;
-      {
-        int lo_ = 1, hi_ = nk - 1;
-        while (lo_ < hi_) {
-          const int mid = (lo_ + hi_) >> 1;
-          if (qv > ksrc[mid]) lo_ = mid + 1; else hi_ = mid;
-        }
-        klo = lo_;
-      }
-      c.klo = klo;
-      const double ho = ksrc[klo] - ksrc[klo - 1];
-      c.a0 = (ksrc[klo] - qv) / ho;
-      c.b0 = (qv - ksrc[klo - 1]) / ho;
-      c.ho2o6 = ho * ho / 6;
-      c.a03h = (c.a0 * c.a0 * c.a0 - c.a0);
-      c.b03h = (c.b0 * c.b0 * c.b0 - c.b0);
-      const double max_etak_tensor = p.max_eta_k / 10;
-      int step = 2;
-      for (int i = nt; i >= 2; i--) {
-        double xf = __dmul_rn(qv, __dsub_rn(tau0, tau[i - 1]));
-        bool ok = xf > 1.e-8;
-        if (p.tensors) ok = ok && (__dmul_rn(qv, tau[i - 1]) < max_etak_tensor);
-        if (ok) { step = i; break; }
-      }
-      c.steps = step;
-    } else {
-      c.q = 1; c.w = 0; c.klo = 1; c.a0 = c.b0 = c.a03h = c.b03h = c.ho2o6 = 0; c.steps = 0;
-    }
+    const ProjQ3 c = w4_q_consts(p, pt, q0 + tid, nq, ip);
     qc[tid] = c;
+#if CB200_W4_SPLIT_EPI
+    p.qcg[((size_t)lp * p.NQB + qb) * QC + tid] = c;
+#endif
     s_q1[tid] = 0x7fffffff; s_q2[tid] = 0;
   }
   if (tid == 0) {
@@ -424,42 +484,14 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     const int kb = (W4_TS && !COUNT && lh == 1) ? KS : 0, ke = (W4_TS && !COUNT && lh == 0) ? KS : LKH;
 #pragma unroll(COUNT || !W4_TS ? LKH : 1)
     for (int k = kb; k < ke; k++) {
-      int n1 = 0, n2 = 0;
+      int n1, n2;
+      bool w_reached, w_doint;
       const int j = li + 8 * W4_OCT(k);
       const bool lvalid = j < p.nl;
       const int l = lvalid ? p.ls[j] : 0;
-      if (myq.valid && lvalid) {
-        const double qv = myq.q;
-        int llmax = (int)llround(__dmul_rn(qv, tau0));
-        if (llmax < 15) llmax = 17;
-        else llmax = (int)llround(__dmul_rn(qv, __dadd_rn(tau0, __ddiv_rn(6 * kPi, qv))));
-        if (l <= llmax) {
-          double xlim = 0.05 * l;
-          xlim = fmax(xlim, 35.0);
-          xlim = l - xlim;
-          const double tau2 = tau[1];
-          double tmin = __dsub_rn(tau0, __ddiv_rn((double)(80 * l), qv));
-          tmin = fmax(tau2, tmin);
-          double tmax = __dsub_rn(tau0, __ddiv_rn(xlim, qv));
-          tmax = fmin(tau0, tmax);
-          if (!(tmax < tau2)) {
-            reached |= 1u << k;
-            bool di = true;
-            if (!p.tensors) {
-              double qmax_int = __ddiv_rn((double)(max(850, l) * 3), tau0);
-              qmax_int = __dmul_rn(qmax_int, (double)1.2f);
-              di = qv < qmax_int;
-            }
-            if (di) {
-              doint |= 1u << k;
-              n1 = lin_index_of(tseg, tmin);
-              n2 = min(myq.steps, lin_index_of(tseg, tmax));
-            } else {
-              n1 = n2 = 0x7fff;
-            }
-          }
-        }
-      }
+      w4_window(p, myq, lvalid, l, tau0, tau, tseg, n1, n2, w_reached, w_doint);
+      if (w_reached) reached |= 1u << k;
+      if (w_doint) doint |= 1u << k;
       if (j < NJ) s_wtab[myqi * NJP + j] = (unsigned)n1 | ((unsigned)n2 << 16);
       const bool live = (n2 >= n1) && n1 > 0 && n1 < 0x7fff;
       if (live) {
@@ -468,6 +500,9 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
       }
       if (COUNT) win[k] = live ? ((unsigned)n1 | ((unsigned)(n2 - n1) << 16)) : 0x7fffu;
     }
+#if CB200_W4_SPLIT_EPI
+    p.flg[(((size_t)lp * p.NQB + qb) * NCW + warp) * 32 + lane] = reached | (doint << 16);
+#endif
     // union over the quarter's multipoles: which (q, tau) pairs have to be visited at all
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
@@ -948,6 +983,43 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     atomicAdd(p.ring_stats + 8, (unsigned long long)ck_c);
   }
 #undef CK4
+#if CB200_W4_SPLIT_EPI
+  // ---- the two time halves of a wavenumber group add their sums (through the now free ring), and the half that owns an octet
+  //      writes its three time integrals to global memory.  The Limber values and the partial k-contraction - ~25 k clocks of
+  //      dependent global loads, divisions and CTA-wide barriers at the end of every CTA (12 % of the consumers' time in the
+  //      ncu source page, with nothing else resident on the SM) - run in project4_finish_kernel at full occupancy.
+  static_assert(!CB200_W4_SPLIT_EPI || (W4_TS && !W4_OS), "the split epilogue is written for the time-split consumers");
+  asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W4_NCW) : "memory");
+  {
+    unsigned e_tid, e_bx, e_by;
+    asm volatile("mov.u32 %0, %%tid.x;\n" : "=r"(e_tid));
+    asm volatile("mov.u32 %0, %%ctaid.x;\n" : "=r"(e_bx));
+    asm volatile("mov.u32 %0, %%ctaid.y;\n" : "=r"(e_by));
+    const int tid = (int)e_tid, lane = tid & 31, warp = tid >> 5;
+    const int wg = warp % NQG, lh = (warp / NQG) & 1;
+    constexpr int NE = 3 * LKH;
+    static_assert(32 * 1024 + (size_t)NQG * NE * 32 * 8 <= 128 * 1024, "exchange scratch inside the ring");
+    double* xs = reinterpret_cast<double*>(smem_raw + 32 * 1024) + (size_t)wg * NE * 32 + lane;  // [group][entry][lane]
+#pragma unroll
+    for (int k = 0; k < LKH; k++) {
+      if ((k < KS) == (lh == 1)) {   // not mine to finish
+        xs[(3 * k) * 32] = acc[k][0];
+        xs[(3 * k + 1) * 32] = acc[k][1];
+        if (k < K2) xs[(3 * k + 2) * 32] = acc2[k < K2 ? k : 0];
+      }
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W4_NCW) : "memory");
+    double* rw = p.raw + ((((size_t)e_by * p.NQB + e_bx) * NQG + wg) * NE) * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < LKH; k++) {
+      if ((k < KS) == (lh == 0)) {
+        rw[(3 * k) * 32] = acc[k][0] + xs[(3 * k) * 32];
+        rw[(3 * k + 1) * 32] = acc[k][1] + xs[(3 * k + 1) * 32];
+        if (k < K2) rw[(3 * k + 2) * 32] = acc2[k < K2 ? k : 0] + xs[(3 * k + 2) * 32];
+      }
+    }
+  }
+#else
   // all consumer warps are done with the ring: it is reused for the contraction partials
   asm volatile("bar.sync 1, %0;\n" ::"n"(32 * W4_NCW) : "memory");
 
@@ -1074,7 +1146,115 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     }
   }
   }
+#endif
 #undef W4_OCT
+}
+
+// Second half of the projection (split off the tail of project4_kernel): Limber value of the lensing source
+// (cmbmain.f90:1546-1556), Delta_l(q) output, partial k-contraction of a wavenumber block (cmbmain.f90:2132-2264) in the
+// fixed order the in-kernel epilogue used (the four wavenumbers of a warp by two shuffle steps, then the groups in order), so
+// the C_l are bit-identical.  Same thread layout as the consumers: warp = (wavenumber group, half), quarter = wavenumber,
+// lane = l-slot li + 8 k; half 0 finishes the octets below KS, half 1 the others.  The block's wavenumber constants and the
+// reached / doint bits come from the projection kernel's prologue; the octets of a lane are independent chains (unrolled),
+// and five such CTAs share an SM, so the dependent loads and divisions of the Limber branch overlap instead of stalling an SM.
+template <int LK, int KLIM>
+__global__ void __launch_bounds__(32 * W4_NCW, 3) project4_finish_kernel(const Proj4Params p) {
+  constexpr int NCW = W4_NCW, NQG = W4_NQG, QC = W4_QC;
+  constexpr int LKH = LK, K2 = KLIM, KS = (LKH + 1) / 2, NE = 3 * LKH;
+  __shared__ double red[NQG * 6 * PROJ_LP];
+  __shared__ double limfac[PROJ_LP];   // sqrt(pi / 2 / (l + 1/2)) of every l-slot: once per CTA instead of once per thread and octet
+  const PointView& v = p.v;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lp = blockIdx.y, pt = p.p0 + lp, qb = blockIdx.x, q0 = qb * QC;
+  const int nq = v.n_q[pt];
+  if (q0 >= nq) return;
+  if (p.fallback && p.fallback[(size_t)lp * p.NQB + qb]) return;   // this block was left to project3_kernel
+  const int qr = lane >> 3, li = lane & 7, wg = warp % NQG, lh = (warp / NQG) & 1;
+  const double tau0 = v.thermo[(size_t)pt * 5];
+  const double* tau = v.tau + (size_t)pt * v.NT;
+  const LinSegs& tseg = v.tseg[pt];
+  const size_t row_stride = (size_t)v.NK;
+  const size_t tau_stride = (size_t)v.NSRC * v.NK;
+  const double* src = v.src + (size_t)pt * v.NT * tau_stride;
+  const double* dds = p.ddsrc + (size_t)lp * v.NT * tau_stride;
+  const int noct = (p.nl + 7) >> 3;
+  const int myqi = wg * 4 + qr;
+  const ProjQ3 myq = p.qcg[((size_t)lp * p.NQB + qb) * QC + myqi];
+  const unsigned fl = p.flg[(((size_t)lp * p.NQB + qb) * NCW + warp) * 32 + lane];
+  const double* rw = p.raw + ((((size_t)lp * p.NQB + qb) * NQG + wg) * NE) * 32 + lane;
+  if (tid < PROJ_LP) limfac[tid] = tid < p.nl ? sqrt(kPi / 2 / ((double)p.ls[tid] + 0.5)) : 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < LKH; k++) {
+    if ((k < KS) != (lh == 0)) continue;   // finished by the other half (warp-uniform)
+    double cl[6];
+#pragma unroll
+    for (int X = 0; X < 6; X++) cl[X] = 0.0;
+    const int j = li + 8 * k;
+    const bool lvalid = j < p.nl;
+    const int l = lvalid ? p.ls[j] : 0;
+    const double d0 = rw[(3 * k) * 32], d1 = rw[(3 * k + 1) * 32];
+    double d2 = (k < K2) ? rw[(3 * k + 2) * 32] : 0.0;
+    if (myq.valid && k < noct) {
+      const bool reached = (fl >> k) & 1u, doint = (fl >> (16 + k)) & 1u;
+      if (!p.tensors && lvalid && reached) {
+        const bool use_limber = l > 400;
+        if (!doint || use_limber) {
+          double xf = __dsub_rn(tau0, __ddiv_rn((double)l + 0.5, myq.q));
+          double s3 = 0;
+          if (xf < tseg.highest && xf > tau[0]) {
+            const int n = lin_index_of(tseg, xf);
+            xf = __ddiv_rn(__dsub_rn(xf, tau[n - 1]), __dsub_rn(tau[n], tau[n - 1]));
+            double sa2 = 0, sb2 = 0;
+            const double* S2p = src + 2 * row_stride + (myq.klo - 1);
+            const double* D2p = dds + 2 * row_stride + (myq.klo - 1);
+            if (n >= 2 && n <= myq.steps) {
+              const double* a = S2p + (size_t)(n - 1) * tau_stride;
+              const double* d = D2p + (size_t)(n - 1) * tau_stride;
+              sa2 = myq.a0 * a[0] + myq.b0 * a[1] + (myq.a03h * d[0] + myq.b03h * d[1]) * myq.ho2o6;
+            }
+            if (n + 1 >= 2 && n + 1 <= myq.steps) {
+              const double* a = S2p + (size_t)n * tau_stride;
+              const double* d = D2p + (size_t)n * tau_stride;
+              sb2 = myq.a0 * a[0] + myq.b0 * a[1] + (myq.a03h * d[0] + myq.b03h * d[1]) * myq.ho2o6;
+            }
+            s3 = (sa2 * (1 - xf) + xf * sb2) * limfac[j] / myq.q;
+          }
+          d2 = s3;
+        }
+      }
+      if (p.delta) {
+        double* dp = p.delta + (((size_t)lp * v.NQ + (q0 + myqi)) * PROJ_LP + j) * 3;
+        dp[0] = d0; dp[1] = d1; dp[2] = d2;
+      }
+      const double w = myq.w;
+      if (p.tensors) {
+        cl[0] = w * d0 * d0; cl[1] = w * d1 * d1; cl[2] = w * d2 * d2; cl[3] = w * d0 * d1;
+      } else {
+        cl[0] = w * d0 * d0; cl[1] = w * d1 * d1; cl[2] = w * d0 * d1;
+        cl[3] = w * d2 * d2; cl[4] = w * d2 * d0; cl[5] = w * d2 * d1;
+      }
+    }
+    // sum over the warp's four wavenumbers (quarters); the groups are added below in a fixed order
+#pragma unroll
+    for (int X = 0; X < 6; X++) {
+      double sm = cl[X];
+      sm += __shfl_xor_sync(0xffffffffu, sm, 8);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 16);
+      if (qr == 0) red[((size_t)wg * 6 + X) * PROJ_LP + j] = sm;
+    }
+  }
+  __syncthreads();
+  double* pp = p.part + (((size_t)lp * p.NQB + qb) * 6) * PROJ_LP;
+  for (int e = tid; e < 6 * PROJ_LP; e += 32 * NCW) {
+    const int X = e / PROJ_LP, j = e - X * PROJ_LP;
+    double sm = 0;
+    if (j < 8 * LK) {
+#pragma unroll
+      for (int w = 0; w < NQG; w++) sm += red[((size_t)w * 6 + X) * PROJ_LP + j];
+    }
+    pp[e] = sm;
+  }
 }
 
 // host side: the template instances in use (octets per row, octets that keep the lensing-potential accumulator)
@@ -1082,7 +1262,12 @@ template <int LK, int KLIM>
 inline void w4_launch(bool count, dim3 grid, size_t smem, cudaStream_t s, const Proj4Params& pp) {
   if (count) project4_kernel<LK, true, KLIM><<<grid, W4_NT, smem, s>>>(pp);
   else project4_kernel<LK, false, KLIM><<<grid, W4_NT, smem, s>>>(pp);
+#if CB200_W4_SPLIT_EPI
+  project4_finish_kernel<LK, KLIM><<<grid, 32 * W4_NCW, 0, s>>>(pp);
+#endif
 }
+// doubles of Proj4Params::raw per (point, wavenumber block)
+inline size_t w4_raw_doubles(int LK) { return (size_t)W4_NQG * 3 * LK * 32; }
 template <int LK, int KLIM>
 inline cudaError_t w4_set_smem_attr() {
   cudaError_t e = cudaFuncSetAttribute(project4_kernel<LK, false, KLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_TOTAL);
