@@ -305,8 +305,20 @@ __device__ __forceinline__ double2 lds128(unsigned saddr) {
 #define CB200_W4_SPLIT_EPI 1   // 1: Limber values and the partial k-contraction run in project4_finish_kernel, not in this CTA's tail
 #endif
 
-// per-wavenumber constants (InterpolateSources set-up, cmbmain.f90:1307-1320): shared by the projection kernel's prologue and
-// by project4_finish_kernel
+// last time sample a wavenumber integrates to (SourceSteps of IntegrationVars_Init, cmbmain.f90:1387-1400)
+__device__ __forceinline__ int w4_steps(const Proj4Params& p, double qv, int nt, double tau0, const double* tau) {
+  const double max_etak_tensor = p.max_eta_k / 10;
+  int step = 2;
+  for (int i = nt; i >= 2; i--) {
+    double xf = __dmul_rn(qv, __dsub_rn(tau0, tau[i - 1]));
+    bool ok = xf > 1.e-8;
+    if (p.tensors) ok = ok && (__dmul_rn(qv, tau[i - 1]) < max_etak_tensor);
+    if (ok) { step = i; break; }
+  }
+  return step;
+}
+
+// per-wavenumber constants (InterpolateSources set-up, cmbmain.f90:1307-1320)
 __device__ __forceinline__ ProjQ3 w4_q_consts(const Proj4Params& p, int pt, int qi, int nq, const double* ip) {
   const PointView& v = p.v;
   const int nt = v.n_tau[pt], nk = v.n_k[pt];
@@ -339,15 +351,7 @@ __device__ __forceinline__ ProjQ3 w4_q_consts(const Proj4Params& p, int pt, int 
     c.ho2o6 = ho * ho / 6;
     c.a03h = (c.a0 * c.a0 * c.a0 - c.a0);
     c.b03h = (c.b0 * c.b0 * c.b0 - c.b0);
-    const double max_etak_tensor = p.max_eta_k / 10;
-    int step = 2;
-    for (int i = nt; i >= 2; i--) {
-      double xf = __dmul_rn(qv, __dsub_rn(tau0, tau[i - 1]));
-      bool ok = xf > 1.e-8;
-      if (p.tensors) ok = ok && (__dmul_rn(qv, tau[i - 1]) < max_etak_tensor);
-      if (ok) { step = i; break; }
-    }
-    c.steps = step;
+    c.steps = w4_steps(p, qv, nt, tau0, tau);
   } else {
     c.q = 1; c.w = 0; c.klo = 1; c.a0 = c.b0 = c.a03h = c.b03h = c.ho2o6 = 0; c.steps = 0;
   }
@@ -415,9 +419,9 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   unsigned char* ring = smem_raw;                                            // [(R+1)][rb]
   unsigned char* meta_base = smem_raw + (size_t)(R + 1) * rb;                // 2 x {af[NPAIR], s01[NPAIR], rec[NPAIR]}
   ProjQ3* qc = reinterpret_cast<ProjQ3*>(meta_base + W4_META_BYTES);         // [QC]
-  int* s_q1 = reinterpret_cast<int*>(meta_base + W4_META_BYTES + W4_QC_BYTES);  // [QC]
-  int* s_q2 = s_q1 + QC;                                                     // [QC]
-  int* s_misc = s_q2 + QC;                                                   // n_lo, n_hi
+  int* s_q1 = reinterpret_cast<int*>(meta_base + W4_META_BYTES + W4_QC_BYTES);  // [2][QC]: first visited sample, per consumer half
+  int* s_q2 = s_q1 + 2 * QC;                                                 // [2][QC]: last visited sample
+  int* s_misc = s_q2 + 2 * QC;                                               // [2]: block needs the fallback
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_misc + 4);  // (s_misc[2]: block needs the fallback)  // full[NST], empty[NST]
   constexpr int NJ = 8 * LK, NJP = NJ + 1;
   unsigned* s_wtab = reinterpret_cast<unsigned*>(meta_base + W4_META_BYTES + W4_QC_BYTES + W4_MISC_BYTES);  // [QC][NJP]
@@ -448,27 +452,32 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   const int noct = (p.nl + 7) >> 3;  // octets that hold multipoles
 
   // ---- per-wavenumber constants (InterpolateSources set-up, cmbmain.f90:1307-1320) ----
-  if (tid < QC) {
-    const ProjQ3 c = w4_q_consts(p, pt, q0 + tid, nq, ip);
-    qc[tid] = c;
+  // The full set (source-grid bracket by binary search, spline weights, primordial power: a chain of dependent global
+  // loads) is computed by 24 lanes of the ring warp WHILE the consumers derive their integration windows, which only need
+  // q and the last time sample: one CTA-wide barrier instead of two, and the two latency chains overlap.
+  if (tid >= 32 * NCW && tid < 32 * NCW + QC) {
+    const int t = tid - 32 * NCW;
+    const ProjQ3 c = w4_q_consts(p, pt, q0 + t, nq, ip);
+    qc[t] = c;
 #if CB200_W4_SPLIT_EPI
-    p.qcg[((size_t)lp * p.NQB + qb) * QC + tid] = c;
+    p.qcg[((size_t)lp * p.NQB + qb) * QC + t] = c;
 #endif
-    s_q1[tid] = 0x7fffffff; s_q2[tid] = 0;
   }
-  if (tid == 0) {
-    s_misc[0] = 0x7fffffff; s_misc[1] = 0; s_misc[2] = 0;
+  if (tid == 32 * NCW + 31) {
+    s_misc[2] = 0;
     for (int i = 0; i < W4_NST; i++) {
       mbar_init(s_bar + i, 32 * (1 + W4_MW)); // full: ring warp + one metadata group arrive (+ the bytes of the bulk copies)
       mbar_init(s_bar + W4_NST + i, NCW);    // empty: one lane per consumer warp
     }
     for (int i = 0; i < W4_NSR; i++) mbar_init(s_bar + 32 + i, 1);  // raw source rows of a slab landed
   }
-  __syncthreads();
 
   // ---- integration windows of this lane's wavenumber (quarter) and its LK multipoles (consumer warps) ----
   const int myqi = wg * 4 + qr;
-  const ProjQ3& myq = qc[myqi];
+  ProjQ3 myq;   // the three fields the windows need; the full record is in qc[] after the barrier
+  myq.valid = consumer && (q0 + myqi < nq);
+  myq.q = myq.valid ? v.q[(size_t)pt * v.NQ + q0 + myqi] : 1.0;
+  myq.steps = myq.valid ? w4_steps(p, myq.q, nt, tau0, tau) : 0;
   // Integration windows [n1, n2] of every (wavenumber, multipole) go to shared memory; both bounds fall with l
   // (tmin and tmax do, and the index lookup is monotone), so for a given (q, tau) pair the active multipoles are
   // ONE run of l-slots [jlo, jhi], which the producer tracks incrementally and ships with the pair metadata.
@@ -509,13 +518,20 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
       un1 = min(un1, __shfl_xor_sync(0xffffffffu, un1, o));
       un2 = max(un2, __shfl_xor_sync(0xffffffffu, un2, o));
     }
-    if (li == 0 && un1 <= un2) {  // union over both multipole halves
-      atomicMin(&s_q1[myqi], un1); atomicMax(&s_q2[myqi], un2);
-      atomicMin(&s_misc[0], un1); atomicMax(&s_misc[1], un2);
+    if (li == 0) {  // per half; the halves (and the block's union) meet after the barrier
+      s_q1[lh * QC + myqi] = un1 <= un2 ? un1 : 0x7fffffff;
+      s_q2[lh * QC + myqi] = un1 <= un2 ? un2 : 0;
     }
   }
   __syncthreads();
-  const int n_lo = s_misc[0], n_hi = s_misc[1];
+  static_assert(W4_QC <= 32, "the block's union of visited samples is reduced by one warp-wide shuffle tree");
+  int n_lo = 0x7fffffff, n_hi = 0;
+  if (lane < QC) { n_lo = min(s_q1[lane], s_q1[QC + lane]); n_hi = max(s_q2[lane], s_q2[QC + lane]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_lo = min(n_lo, __shfl_xor_sync(0xffffffffu, n_lo, o));
+    n_hi = max(n_hi, __shfl_xor_sync(0xffffffffu, n_hi, o));
+  }
   const int nslab = (n_lo <= n_hi) ? (n_hi - n_lo) / S + 1 : 0;
 
   // ---- analytic table-row window of every slab (superset of the rows its visited pairs touch):
@@ -571,8 +587,8 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
     if (!ring_warp && m_grp >= W4_MG) return;
     const int m_qi = m_live ? m_pair % QC : 0, m_nn = W4_PBAL ? warp - NCW : m_pair / QC;
     const ProjQ3& pc = qc[m_qi];  // read from shared memory where needed: the producer runs on few registers
-    const int pw1 = (pc.valid && m_live) ? max(s_q1[m_qi], 1) : 0x7fffffff;  // (ring warp: never valid)
-    const int pw2 = pc.valid ? min(s_q2[m_qi], pc.steps) : 0;
+    const int pw1 = (pc.valid && m_live) ? max(min(s_q1[m_qi], s_q1[QC + m_qi]), 1) : 0x7fffffff;  // (ring warp: never valid)
+    const int pw2 = pc.valid ? min(max(s_q2[m_qi], s_q2[QC + m_qi]), pc.steps) : 0;
     constexpr int PPT = W4_PPT, PNN = W4_PNN, MS = W4_MS, NU = PPT * MS;
     double f_tau[NU], f_dtau[NU];
     bool f_valid[NU];
