@@ -488,13 +488,17 @@ def main():
     k1_ms = tm["ms_project"] / n_launch_k1
     pts_per_launch = P / n_chunks
     # algorithmic HBM bytes per point: Src + ddSrc read once, one partial-sum block [6][96] written per 24 wavenumbers
-    bytes_pt = float(np.mean(W["n_tau"].astype(np.float64) * 3 * W["n_k"] * 8 * 2)) + (2910 / 24.0) * 6 * 96 * 8
+    # + the time integrals of a block on their way from the projection kernel to its finish kernel (6 groups x 33 values x 32
+    #   lanes, written once and read once)
+    bytes_pt = float(np.mean(W["n_tau"].astype(np.float64) * 3 * W["n_k"] * 8 * 2)) + (2910 / 24.0) * 6 * 96 * 8 \
+        + (2910 / 24.0) * 6 * 33 * 32 * 8 * 2
     trip_pt = triples / P
     flop_per_triple = 13  # cubic j_l interpolation: 1 mul + 3 FMA; 3 FMA accumulations (T, E, lensing potential)
     sm_clock_hz = 1e6 * float(clocks.get("sm_mhz") or 1965.0)
     sec = k1_ms * 1e-3
     ncu = load_ncu_metrics()
-    roof = {"kernel": "project4_kernel (K1+K2 fused: line-of-sight projection + partial k-contraction)",
+    roof = {"kernel": "project4_kernel + project4_finish_kernel (K1+K2: line-of-sight projection, then Limber values and the "
+                      "partial k-contraction; the phase time also holds the project3_kernel pass over the first wavenumber block)",
             "bound": "fp64", "achieved": trip_pt * flop_per_triple * pts_per_launch / sec / 1e12, "peak": dfma_peak,
             "unit": "TFLOP/s", "peak_source": "measured live (cb200_measure_fp64_peaks: DFMA micro-kernel; "
             "MEASURED_PEAKS.json has no FP64 entry)", "peak_dmma": dmma_peak, "flop_per_triple": flop_per_triple,

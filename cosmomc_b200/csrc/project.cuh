@@ -124,15 +124,38 @@ __global__ void __launch_bounds__(SPL_THREADS) source_spline_tiled_kernel(PointV
   const double* y = v.src + ((size_t)pt * rows_per_pt + row0) * NK;
   double* d2 = ddsrc + ((size_t)lp * rows_per_pt + row0) * NK;
   const int tid = threadIdx.x;
-  for (int e = tid; e < 5 * NK; e += SPL_THREADS) sc[e] = c[e];
+  // sweep coefficients.  The reference's forward step u_i = (6 (d_i - d_i-1) c0_i - c1_i u_i-1) c2_i puts three dependent
+  // FP64 operations per wavenumber on ONE thread's chain (FP64 latency, not bandwidth, is what this kernel waits for);
+  // with c1 c2 and 6 c0 c2 formed here the chain is one fused multiply-add per step (rounding differs in the last bit)
+  for (int e = tid; e < NK; e += SPL_THREADS) {
+    const double c0 = c[e], c1 = c[NK + e], c2 = c[2 * NK + e];
+    sc[e] = 6. * c0 * c2;
+    sc[NK + e] = c1 * c2;
+    sc[2 * NK + e] = c2;
+    sc[3 * NK + e] = c[3 * NK + e];
+    sc[4 * NK + e] = c[4 * NK + e];
+  }
   // NK is a multiple of 2: 16-byte loads of the contiguous block, scattered into the padded rows
   const double2* y2 = reinterpret_cast<const double2*>(y);
   const int n2 = nrows * NK / 2;
-  for (int e = tid; e < n2; e += SPL_THREADS) {
-    const double2 val = __ldg(y2 + e);
-    const int r = (2 * e) / NK, k = 2 * e - r * NK;
-    sy[r * NKP + k] = val.x;
-    sy[r * NKP + k + 1] = val.y;
+  // eight loads in flight per thread: one load per iteration left the 28 iterations of this loop at one DRAM latency each
+  constexpr int SPL_U = 8;
+  for (int e0 = tid; e0 < n2; e0 += SPL_U * SPL_THREADS) {
+    double2 val[SPL_U];
+#pragma unroll
+    for (int u = 0; u < SPL_U; u++) {
+      const int e = e0 + u * SPL_THREADS;
+      if (e < n2) val[u] = __ldg(y2 + e);
+    }
+#pragma unroll
+    for (int u = 0; u < SPL_U; u++) {
+      const int e = e0 + u * SPL_THREADS;
+      if (e < n2) {
+        const int r = (2 * e) / NK, k = 2 * e - r * NK;
+        sy[r * NKP + k] = val[u].x;
+        sy[r * NKP + k + 1] = val[u].y;
+      }
+    }
   }
   __syncthreads();
   if (tid < nrows) {
@@ -144,7 +167,7 @@ __global__ void __launch_bounds__(SPL_THREADS) source_spline_tiled_kernel(PointV
       const double y2v = yr[i + 1];
       d1l = d1r;
       d1r = (y2v - y1) * sc[4 * NK + i];
-      u = (6. * (d1r - d1l) * sc[0 * NK + i] - sc[1 * NK + i] * u) * sc[2 * NK + i];
+      u = fma(-sc[1 * NK + i], u, (d1r - d1l) * sc[0 * NK + i]);
       yr[i] = u;          // y[i] is no longer needed
       y1 = y2v;
     }
