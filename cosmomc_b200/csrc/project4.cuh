@@ -185,6 +185,10 @@ __device__ __forceinline__ int w4_locate(const Proj4Params& p, double v, double&
 #define CB200_W4_PAIR2 1   // 1: a consumer warp takes BOTH of its time samples of a slab in one step (S = 4, time-split): one prologue
                            //    per two pairs, octet-granular batches whose two chains belong to the two samples
 #endif
+#ifndef CB200_W4_WUNROLL
+#define CB200_W4_WUNROLL 1   // unroll of the window set-up loop (its FP64 divisions are one dependent chain per octet)
+#endif
+constexpr int W4_WUNROLL = CB200_W4_WUNROLL;
 #ifndef CB200_W4_KB
 #define CB200_W4_KB 2   // octets per batch of loads in flight (time-split consumers: 1: 136.3 us/point, 2: 132.8, 3: 137.3, 4: 145.6)
 #endif
@@ -196,6 +200,8 @@ __device__ __forceinline__ int w4_locate(const Proj4Params& p, double v, double&
 #endif
 constexpr bool W4_PBAL = CB200_W4_PBAL != 0;
 static_assert(!W4_PBAL || (W4_S == W4_NPW && W4_QC <= 32 && W4_MG == 1 && W4_MS == 1), "balanced producers: one time sample per producer warp");
+// (last measured with the final consumers: 157.7 us/point against 109.6, and its C_l differ from the default build's at 1e-6 -
+//  the variant has not followed the source staging; kept as a record of the experiment, not as an option to ship)
 #ifndef CB200_W4_UNSAFE_FREEMETA
 #define CB200_W4_UNSAFE_FREEMETA 0    // timing experiment only: WRONG results
 #endif
@@ -360,14 +366,19 @@ __device__ __forceinline__ ProjQ3 w4_q_consts(const Proj4Params& p, int pt, int 
 
 // integration window [n1, n2] of one (wavenumber, multipole) and the two flags the epilogue needs (cmbmain.f90:1387-1420,
 // 1440-1470): reached = the window is entered at all, doint = the time integral is formed (else Limber only)
-__device__ __forceinline__ void w4_window(const Proj4Params& p, const ProjQ3& myq, bool lvalid, int l, double tau0,
+// highest multipole a wavenumber contributes to (cmbmain.f90:1402-1408): a constant of the wavenumber, taken out of the
+// per-multipole window so that a lane derives it once instead of once per octet
+__device__ __forceinline__ int w4_llmax(double qv, double tau0) {
+  int llmax = (int)llround(__dmul_rn(qv, tau0));
+  if (llmax < 15) llmax = 17;
+  else llmax = (int)llround(__dmul_rn(qv, __dadd_rn(tau0, __ddiv_rn(6 * kPi, qv))));
+  return llmax;
+}
+__device__ __forceinline__ void w4_window(const Proj4Params& p, const ProjQ3& myq, int llmax, bool lvalid, int l, double tau0,
                                           const double* tau, const LinSegs& tseg, int& n1, int& n2, bool& reached, bool& doint) {
   n1 = 0; n2 = 0; reached = false; doint = false;
   if (myq.valid && lvalid) {
     const double qv = myq.q;
-    int llmax = (int)llround(__dmul_rn(qv, tau0));
-    if (llmax < 15) llmax = 17;
-    else llmax = (int)llround(__dmul_rn(qv, __dadd_rn(tau0, __ddiv_rn(6 * kPi, qv))));
     if (l <= llmax) {
       double xlim = 0.05 * l;
       xlim = fmax(xlim, 35.0);
@@ -488,17 +499,18 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
   constexpr int KS = (LKH + 1) / 2;  // W4_TS: half 0 owns the windows / the epilogue of the octets below KS, half 1 the others
   if (consumer) {
     int un1 = 0x7fffffff, un2 = 0;
+    const int my_llmax = myq.valid ? w4_llmax(myq.q, tau0) : 0;
     // each half derives the windows of its own octets only (they meet in s_wtab / the atomics below); COUNT builds
     // need every window in registers.  Not unrolled when split: the body is ~150 instructions
     const int kb = (W4_TS && !COUNT && lh == 1) ? KS : 0, ke = (W4_TS && !COUNT && lh == 0) ? KS : LKH;
-#pragma unroll(COUNT || !W4_TS ? LKH : 1)
+#pragma unroll(COUNT || !W4_TS ? LKH : W4_WUNROLL)
     for (int k = kb; k < ke; k++) {
       int n1, n2;
       bool w_reached, w_doint;
       const int j = li + 8 * W4_OCT(k);
       const bool lvalid = j < p.nl;
       const int l = lvalid ? p.ls[j] : 0;
-      w4_window(p, myq, lvalid, l, tau0, tau, tseg, n1, n2, w_reached, w_doint);
+      w4_window(p, myq, my_llmax, lvalid, l, tau0, tau, tseg, n1, n2, w_reached, w_doint);
       if (w_reached) reached |= 1u << k;
       if (w_doint) doint |= 1u << k;
       if (j < NJ) s_wtab[myqi * NJP + j] = (unsigned)n1 | ((unsigned)n2 << 16);
