@@ -319,7 +319,9 @@ int cb200_sync(cb200_handle* h);
 /* options: "async_upload" (0/1: cb200_upload_sources returns with the source copy in flight on a separate stream, so
  * that the upload of one block of points overlaps cb200_powers of the previous block; the source buffer must then
  * stay untouched until cb200_sync or a call that returns results), "count_triples" (0/1), "keep_transfers" (0/1), "ring_stats" (0/1), "proj_kernel" (1 = L2 gathers, 2 = windowed warp-per-pair,
- * 3 = quarter-warp pairs per 32-multipole chunk, 4 = all multipoles per quarter-warp, producer/consumer warps; default) */
+ * 3 = quarter-warp pairs per 32-multipole chunk, 4 = all multipoles per quarter-warp, producer/consumer warps; default),
+ * "sn_chunk" (points per launch of the supernova kernels, default 1024; 4.4 MB of work matrix per point),
+ * "sn_chol_warps" (warps per CTA of the per-point Cholesky: 8, 4, or 0 = by launch size; default 0) */
 int cb200_set_option(cb200_handle* h, const char* name, double value);
 /* CUDA-event stopwatch on the library's stream (device-side timing of whole calls) */
 int cb200_timer_start(cb200_handle* h);

@@ -101,3 +101,33 @@ def test_config2_likelihoods():
         assert abs(tot[i] - sum(want)) < 1e-7 * abs(sum(want))
     t = h.timing()
     assert t["n_launches"] > 0 and t["ms_background"] > 0
+
+
+@pytest.mark.gpu
+def test_sn_cholesky_variants_agree():
+    """K6 launch shapes (supernovae_JLA.f90:1074-1168 per point): the 4-warp and the 8-warp instance of the blocked Cholesky, one
+    launch for the whole batch or several of 3 points (option "sn_chunk") give the same -lnL (1e-10) and match the oracle."""
+    import pyoracle as o
+    from cosmomc_b200 import lib, datasets as D, synthetic as syn
+    bg, alpha, beta = draw_bg(7, seed=9)
+    zj = np.loadtxt(os.path.join(DATA, "jla_lcparams.txt"), usecols=1)
+    covs = syn.synthetic_sn_covs({"zcmb": zj})
+    nuis = np.stack([alpha, beta], axis=1)
+    res = []
+    for warps, chunk in ((0, 1024), (8, 1024), (4, 1024), (4, 3), (8, 3)):
+        h = lib.Handle(lmax_computed_cl=0, max_points=16, chunk_points=2)
+        jla = D.SNPlan(os.path.join(DATA, "jla.dataset"), covs=covs)
+        jla.register(h, 0, 1)
+        h.set_option("sn_chol_warps", warps)
+        h.set_option("sn_chunk", chunk)
+        h.set_background(bg)
+        ll, tot, st = h.loglike_batch(7, nuis)
+        assert (st == 0).all()
+        res.append(ll[:, 0].copy())
+    for r in res[1:]:
+        assert np.abs(r - res[0]).max() < 1e-10 * np.abs(res[0]).max(), np.abs(r - res[0]).max()
+    sj = o.SN(jla.lc, jla.covs, pecz=jla.pecz, twoscriptmfit=True, scriptmcut=jla.scriptmcut)
+    for i in (0, 6):
+        DAj, _, _ = o.background(bg[i], jla.lc["zcmb"])
+        w = sj.loglike(DAj, alpha[i], beta[i])
+        assert abs(res[2][i] - w) < 1e-8 * max(1.0, abs(w)), (res[2][i], w)
