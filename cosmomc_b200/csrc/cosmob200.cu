@@ -522,6 +522,8 @@ int cb200_create(const cb200_config* cfg, cb200_handle** out) {
 #endif
     CB_CUDA(cudaFuncSetAttribute(project3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
     CB_CUDA(cudaFuncSetAttribute(project3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
+    CB_CUDA(cudaFuncSetAttribute(project3_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
+    CB_CUDA(cudaFuncSetAttribute(project3_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W3_SMEM));
     CB_CUDA(cudaFuncSetAttribute(source_spline_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CB_CUDA((w4_set_smem_attr<6, 6>()));
     CB_CUDA((w4_set_smem_attr<11, 11>()));
@@ -960,9 +962,9 @@ void project_chunk(cb200_handle* h, int kind, int p0, int np, bool have_alens, d
       p3.qc_rt = W4_QC;
       p3.bseg = K.bseg;
       for (int i = 0; i < PROJ_LP; i++) p3.ls[i] = i < nl ? K.ls[i] : 0;
-      dim3 grid3((nq_max + W4_QC - 1) / W4_QC, (nl + 31) / 32, np);
-      if (h->count_triples) project3_kernel<true><<<grid3, 32 * W3_NW, W3_SMEM, s>>>(p3);
-      else project3_kernel<false><<<grid3, 32 * W3_NW, W3_SMEM, s>>>(p3);
+      dim3 grid3(1, (nl + 31) / 32, np);
+      if (h->count_triples) project3_sweep_kernel<true><<<grid3, 32 * W3_NW, W3_SMEM, s>>>(p3);
+      else project3_sweep_kernel<false><<<grid3, 32 * W3_NW, W3_SMEM, s>>>(p3);
       h->n_launches += 1;
     } else if (h->proj_kernel == 3) {
       pl.q_per_block = W3_QC;
