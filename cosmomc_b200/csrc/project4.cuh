@@ -307,6 +307,9 @@ __device__ __forceinline__ double2 lds128(unsigned saddr) {
   return r;
 }
 
+#ifndef CB200_W4_FIN_MINB
+#define CB200_W4_FIN_MINB 3   // CTAs of project4_finish_kernel per SM (register cap 56; 2: 70 registers, 2.86 ms per 512 points against 2.48)
+#endif
 #ifndef CB200_W4_SPLIT_EPI
 #define CB200_W4_SPLIT_EPI 1   // 1: Limber values and the partial k-contraction run in project4_finish_kernel, not in this CTA's tail
 #endif
@@ -1186,7 +1189,7 @@ __global__ void __launch_bounds__(W4_NT, 1) project4_kernel(const Proj4Params p)
 // reached / doint bits come from the projection kernel's prologue; the octets of a lane are independent chains (unrolled),
 // and five such CTAs share an SM, so the dependent loads and divisions of the Limber branch overlap instead of stalling an SM.
 template <int LK, int KLIM>
-__global__ void __launch_bounds__(32 * W4_NCW, 3) project4_finish_kernel(const Proj4Params p) {
+__global__ void __launch_bounds__(32 * W4_NCW, CB200_W4_FIN_MINB) project4_finish_kernel(const Proj4Params p) {
   constexpr int NCW = W4_NCW, NQG = W4_NQG, QC = W4_QC;
   constexpr int LKH = LK, K2 = KLIM, KS = (LKH + 1) / 2, NE = 3 * LKH;
   __shared__ double red[NQG * 6 * PROJ_LP];
