@@ -195,7 +195,10 @@ __global__ void lens_prep_kernel(int np, LensGeom g, int LS, int LL, const doubl
 // ------------------------------------------------------------------------------------------------ K4 (2)
 // correlation-function sums over the sampled multipoles (lensing.f90:312-436).  Thread = theta sample,
 // PB points per CTA so each table element fetched from L2 is used PB times.
-constexpr int LENS_PB = 4;
+#ifndef CB200_LENS_PB
+#define CB200_LENS_PB 2   // points per CTA of lens_corr_kernel (1 024 points per launch: 1 / 2 / 3 / 4 -> 2.23 / 1.85 / 2.35 / 2.04 us per point for the lensing phase)
+#endif
+constexpr int LENS_PB = CB200_LENS_PB;
 
 struct LensCorrParams {
   int np, LL;
