@@ -1,8 +1,9 @@
+"""Dev utility (GPU): lensing-phase time of every tuning build variants/lib_*.so against the in-tree library (1 024 points)."""
 import glob, os, subprocess, sys
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
 import sys, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
 import numpy as np
 import helpers as H
 from cosmomc_b200 import lib, synthetic as syn
@@ -22,8 +23,8 @@ for rep in range(3):
     t = h.timing(reset=True)
     best = min(best, 1e3 * t["ms_lens"] / n)
 cls, der, st = h.powers(ip, al)
-print("%-8s lens %.3f us/point  checksum %.12e" % (name, best, float(np.abs(cls).sum())), flush=True)
-'''
+print("%%-8s lens %%.3f us/point  checksum %%.12e" %% (name, best, float(np.abs(cls).sum())), flush=True)
+''' % (ROOT, ROOT)
 libs = [("base", os.path.join(ROOT, "cosmomc_b200", "libcosmob200.so"))]
 libs += [(os.path.basename(p)[4:-3], p) for p in sorted(glob.glob(os.path.join(ROOT, "variants", "lib_*.so")))]
 for name, path in libs:
